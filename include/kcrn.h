@@ -1,0 +1,148 @@
+/*
+ * kcrn.h -- C ABI of the B200-native Krylov cubic-regularised-Newton engine (libkcrn.so).
+ *
+ * The reference (Raymond30/Krylov-Cubic-Regularized-Newton) is pure Python and has no FFI of its
+ * own; its boundary for this path is the duck-typed loss oracle handed to every optimizer plus two
+ * free functions.  Each entry point below names the reference interface it stands in for
+ * (file:line in the reference tree).  INTEGRATION.md shows the ctypes stub that binds them.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative KCRN_E_* code otherwise;
+ *     kcrn_last_error() gives the message of the last failure on the calling thread.
+ *   - pointers named *_dev are device pointers (float64 / int32), *_host are host pointers.
+ *   - all work is enqueued on the stream given to kcrn_create / kcrn_set_stream (a cudaStream_t
+ *     passed as void*; NULL = the legacy default stream) and is asynchronous unless stated.
+ *   - one handle = one row shard of the data matrix on one GPU; one process per GPU.
+ *   - there is no CPU fallback: every call fails with KCRN_E_CUDA when no sm_100 device is usable.
+ */
+#ifndef KCRN_H
+#define KCRN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KCRN_ABI_VERSION 1
+
+#define KCRN_OK 0
+#define KCRN_E_ARG (-1)     /* bad argument (shape, null pointer, unsupported size) */
+#define KCRN_E_CUDA (-2)    /* CUDA runtime / launch failure */
+#define KCRN_E_STATE (-3)   /* call order violated (e.g. gradient before set_x) */
+#define KCRN_E_NOTPD (-4)   /* T + r I not positive definite (LAPACK dposv info > 0 in the reference) */
+#define KCRN_E_NCCL (-5)    /* NCCL unavailable or failed */
+
+typedef struct kcrn_problem *kcrn_handle;
+
+int kcrn_abi_version(void);
+const char *kcrn_last_error(void);
+
+/* ---- problem set-up ------------------------------------------------------------------------
+ * Replaces LogisticRegression.__init__ (optimizer/loss.py:186-213) and the driver's A.tocsc()
+ * (cubic_newton.py:55).  Takes one CSR row shard (int32 indices, float64 values), labels already
+ * mapped to {0,1} (the host mirror does loss.py:190-207), the l2 coefficient and the GLOBAL number
+ * of samples (the 1/n of loss.py:220,227,302).  Copies the arrays to the device (arrays_on_device
+ * = 0) or adopts device arrays by copy (= 1), builds the CSC copy on the device with a stable
+ * counting sort (bit-identical to scipy's csr_tocsc) and the nnz-balanced tile lists. */
+int kcrn_create(kcrn_handle *out, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                const int32_t *indptr, const int32_t *indices, const double *data,
+                const double *labels01, double l2, int64_t n_global, int arrays_on_device,
+                void *stream);
+int kcrn_destroy(kcrn_handle h);
+int kcrn_set_stream(kcrn_handle h, void *stream);
+int kcrn_sync(kcrn_handle h);
+
+/* Row-sharded runs: join an NCCL communicator (one rank per handle).  unique_id is the 128-byte
+ * ncclUniqueId produced by kcrn_nccl_unique_id on rank 0 and broadcast by the host plumbing
+ * (torch.distributed).  After this every gradient / HVP / value adds one allreduce. */
+int kcrn_nccl_unique_id(void *unique_id_128_host);
+int kcrn_comm_init(kcrn_handle h, const void *unique_id_128_host, int rank, int world);
+
+/* Device CSC copy -> host arrays (int32[n_cols+1], int32[nnz], float64[nnz]); synchronous.
+ * Lets the tests compare with A.tocsc() (cubic_newton.py:55) bit for bit. */
+int kcrn_csc_view(kcrn_handle h, int32_t *indptr_host, int32_t *indices_host, double *data_host);
+
+/* ---- loss oracle ---------------------------------------------------------------------------
+ * kcrn_set_x: forward sweep at x -- caches A x, sigma(Ax), the Hessian weights a(1-a), the
+ * residual a-b and the per-sample loss terms.  Replaces the value-equality memo
+ * mat_vec_product (loss.py:266-277): the host mirror decides when x changed.            */
+int kcrn_set_x(kcrn_handle h, const double *x_dev);
+/* value at the current x -> *out_dev (1 double).  Oracle._value, loss.py:215-220 (+ logsig :161-176). */
+int kcrn_value(kcrn_handle h, double *out_dev);
+/* gradient at the current x -> out_dev[n_cols] (NULL: keep it in the handle for kcrn_lanczos).
+ * LogisticRegression.gradient, loss.py:223-232. */
+int kcrn_gradient(kcrn_handle h, double *out_dev);
+/* Hessian-vector product at the current x.  LogisticRegression.hess_vec_prod, loss.py:289-302. */
+int kcrn_hvp(kcrn_handle h, const double *v_dev, double *out_dev);
+/* Same three through HOST buffers (pinned staging inside; synchronous) -- the end-to-end entry
+ * points a numpy caller of the reference oracle would use. */
+int kcrn_value_grad_host(kcrn_handle h, const double *x_host, double *value_host, double *grad_host);
+int kcrn_hvp_host(kcrn_handle h, const double *x_host_or_null, const double *v_host, double *out_host);
+/* Cached A x of the current x -> device pointer (n_rows doubles), for tests. */
+int kcrn_cached_Ax(kcrn_handle h, const double **Ax_dev);
+/* SSCN support (loss.py:279-286): overwrite the cached A x (and everything derived from it). */
+int kcrn_set_Ax(kcrn_handle h, const double *Ax_dev);
+
+/* ---- Lanczos -------------------------------------------------------------------------------
+ * m-step Lanczos on v -> H(x) v started from g (NULL: the gradient kept by kcrn_gradient), the
+ * whole loop enqueued as one CUDA graph without host round trips.  Lanczos(), cubic.py:77-111,
+ * including its breakdown rules (:98-99, :105-109).  reorth = 0 is the reference recurrence;
+ * reorth = 1 adds two classical Gram-Schmidt passes against the basis per step (not in the
+ * reference; SURVEY.md section 8(c) "reorth oracle").  Results stay in the handle: */
+int kcrn_lanczos(kcrn_handle h, const double *g_dev, int m, int reorth);
+/* basis V as m contiguous d-vectors, alphas[m], bet[m] with bet[0] = |g| and bet[j+1] = beta_j,
+ * info[8] int32 = {m_eff, n_valid_columns, broke, hvps, 0...}.  Any pointer may be NULL. */
+int kcrn_lanczos_view(kcrn_handle h, const double **V_dev, const double **alphas_dev,
+                      const double **bet_dev, const int32_t **info_dev);
+/* Step-wise form for an arbitrary operator (the host calls the operator between steps):
+ * begin normalises g into V[0]; feed consumes hv = A(V[cur]) and advances the recurrence;
+ * cur_dev points at the vector the operator must be applied to next.  Host-driven, so each
+ * feed returns whether the recurrence is finished (synchronises on one int). */
+int kcrn_lanczos_begin(kcrn_handle h, const double *g_dev, int m, int reorth);
+int kcrn_lanczos_current(kcrn_handle h, const double **cur_dev);
+int kcrn_lanczos_feed(kcrn_handle h, const double *hv_dev, int *finished_host);
+
+/* ---- cubic sub-problem ---------------------------------------------------------------------
+ * argmin_s <g,s> + 1/2 s'Ts + M/3 |s|^3 for tridiagonal T (alphas, betas) and g = gnorm e1, by
+ * Newton on the secular equation exactly as cubic_solver_root (cubic.py:40-75) drives scipy's
+ * newton (x0 = r0, |p - p0| <= eps stop, it_max).  Single-CTA kernel.
+ * out_dev[0..m) = s, out_dev[m..m+4) = {r, model_decrease, iterations, status}. */
+int kcrn_cubic_tridiag(const double *alphas_dev, const double *betas_dev, int m, double gnorm,
+                       double M, double r0, double eps, int it_max, double *out_dev, void *stream);
+/* Same, on the handle's Lanczos result (m_eff and |g| read on the device). */
+int kcrn_cubic_from_lanczos(kcrn_handle h, double M, double r0, double eps, int it_max);
+
+/* ---- trial point ---------------------------------------------------------------------------
+ * out = x + V s  (cubic.py:291,301), generic form and the handle form (V, s, m_eff from the
+ * handle).  */
+int kcrn_axpy_basis(const double *x_dev, const double *V_dev, const double *s_dev, int m,
+                    int64_t d, double *out_dev, void *stream);
+int kcrn_trial_point(kcrn_handle h, const double *x_dev, double *out_dev);
+/* One D2H of the step record {value, model_decrease, r, iterations, status, m_eff, |g|, hvps,
+ * |x_trial - x|, basis columns written, breakdown flag, 0}; synchronous.  value is the value at
+ * the current x (the value reduction is enqueued by this call when with_value != 0). */
+int kcrn_step_record(kcrn_handle h, int with_value, double *rec12_host);
+
+/* ---- config-4 rows (full-Hessian CRN, SSCN) -------------------------------------------------
+ * dense A' D A / n + l2 I, row-major [n_cols x n_cols]  (loss.py:249-255), FP64 tensor cores. */
+int kcrn_hessian_dense(kcrn_handle h, double *out_dev);
+/* block gradient / Hessian over the column set I (loss.py:234-247, :257-264) and the
+ * incremental A x update  Ax + A[:, I] delta  (loss.py:279-281). */
+int kcrn_partial_gradient(kcrn_handle h, const int64_t *I_dev, int m, double *out_dev);
+int kcrn_partial_hessian(kcrn_handle h, const int64_t *I_dev, int m, double *out_dev);
+int kcrn_update_Ax(kcrn_handle h, const int64_t *I_dev, const double *delta_dev, int m);
+
+/* ---- introspection for the benchmark --------------------------------------------------------
+ * counters[0..8): kernels launched, graph launches, HVPs, forward sweeps, transpose sweeps,
+ * allreduces, bytes H2D, bytes D2H.  */
+int kcrn_counters(kcrn_handle h, int64_t *counters8_host, int reset);
+/* timing probes used by bench.py's roofline leg: run `reps` back-to-back launches of one sweep
+ * kernel (which = 0: CSR pass of the HVP, 1: CSC pass of the HVP) between two CUDA events on the
+ * handle's stream and return the mean duration in microseconds. */
+int kcrn_time_sweep(kcrn_handle h, int which, int reps, double *mean_us_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KCRN_H */

@@ -1,0 +1,521 @@
+// C ABI of libkcrn.so (see include/kcrn.h for the contract of every entry point).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "kcrn_internal.cuh"
+
+namespace kcrn {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int launch_lanczos_finish(kcrn_problem *h);
+int launch_sumsq(kcrn_problem *h, const double *a, int64_t len, double *out);
+int launch_value_combine(kcrn_problem *h, double *out);
+int launch_scale(kcrn_problem *h, const double *y, const double *u, double *out);
+int config4_hessian_dense(kcrn_problem *h, double *out);
+int config4_partial_gradient(kcrn_problem *h, const int64_t *I, int m, double *out);
+int config4_partial_hessian(kcrn_problem *h, const int64_t *I, int m, double *out);
+int config4_update_Ax(kcrn_problem *h, const int64_t *I, const double *delta, int m);
+
+namespace {
+
+int check_device() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        set_error("no usable CUDA device: %s (libkcrn has no CPU path)", cudaGetErrorString(e));
+        return KCRN_E_CUDA;
+    }
+    cudaDeviceProp prop;
+    KCRN_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) {
+        set_error("device %s is sm_%d%d; libkcrn is built for sm_100a only", prop.name, prop.major, prop.minor);
+        return KCRN_E_CUDA;
+    }
+    return KCRN_OK;
+}
+
+template <class T>
+int upload(T **dst, const T *src, size_t count, int on_device, cudaStream_t s) {
+    KCRN_CUDA(cudaMalloc(dst, sizeof(T) * std::max<size_t>(count, 1)));
+    if (count)
+        KCRN_CUDA(cudaMemcpyAsync(*dst, src, sizeof(T) * count,
+                                  on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    return KCRN_OK;
+}
+
+int need_x(kcrn_problem *h, const char *what) {
+    if (!h) { set_error("%s: null handle", what); return KCRN_E_ARG; }
+    if (!h->have_x) { set_error("%s: no current x (call kcrn_set_x first)", what); return KCRN_E_STATE; }
+    return KCRN_OK;
+}
+
+// transpose sweep with the 1/n (+ l2 u) epilogue, allreduced when the rows are sharded
+int cols_product(kcrn_problem *h, const double *src, const double *u, double *out) {
+    if (h->world > 1) {
+        KCRN_TRY(launch_cols_raw(h, src, h->ypart));
+        KCRN_TRY(nccl_allreduce_sum(h, h->ypart, h->d));
+        return launch_scale(h, h->ypart, u, out);
+    }
+    return launch_cols_scaled(h, src, u, out);
+}
+
+int enqueue_value(kcrn_problem *h, double *out) {
+    KCRN_TRY(launch_sum(h, h->ell, h->n, 1.0, h->scal + 1));
+    if (h->world > 1) KCRN_TRY(nccl_allreduce_sum(h, h->scal + 1, 1));
+    if (h->l2 != 0.0) KCRN_TRY(launch_sumsq(h, h->x_cur, h->d, h->scal + 2));
+    return launch_value_combine(h, out);
+}
+
+// the whole m-step recurrence, enqueued on h->stream (captured into a graph by kcrn_lanczos)
+int enqueue_lanczos(kcrn_problem *h, int m, int reorth) {
+    KCRN_TRY(launch_lanczos_init(h, m));
+    for (int slot = 0; slot < m; ++slot) {
+        KCRN_TRY(launch_rows_lanczos(h));
+        if (h->world > 1) {
+            KCRN_TRY(launch_cols_raw(h, h->t, h->ypart));
+            KCRN_TRY(nccl_allreduce_sum(h, h->ypart, h->d));
+            KCRN_TRY(launch_lanczos_post(h, h->ypart, 1));
+        } else {
+            KCRN_TRY(launch_cols_lanczos(h));
+        }
+        if (slot + 1 < m) KCRN_TRY(launch_lanczos_update(h, reorth));
+    }
+    return launch_lanczos_finish(h);
+}
+
+}  // namespace
+}  // namespace kcrn
+
+using namespace kcrn;
+
+extern "C" {
+
+int kcrn_abi_version(void) { return KCRN_ABI_VERSION; }
+const char *kcrn_last_error(void) { return g_error; }
+
+int kcrn_create(kcrn_handle *out, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t *indptr,
+                const int32_t *indices, const double *data, const double *labels01, double l2,
+                int64_t n_global, int arrays_on_device, void *stream) {
+    if (!out || !indptr || (nnz > 0 && (!indices || !data)) || !labels01) {
+        set_error("kcrn_create: null argument");
+        return KCRN_E_ARG;
+    }
+    if (n_rows < 1 || n_cols < 1 || nnz < 0 || nnz > 2147483647LL - kTileNnz || n_rows > 2147483646LL ||
+        n_cols > 2147483646LL) {
+        set_error("kcrn_create: shape (%lld, %lld, nnz %lld) outside the int32 index range", (long long)n_rows,
+                  (long long)n_cols, (long long)nnz);
+        return KCRN_E_ARG;
+    }
+    if (l2 < 0.0) {
+        set_error("Invalid value for l2 regularization: %g", l2);
+        return KCRN_E_ARG;
+    }
+    KCRN_TRY(check_device());
+    kcrn_problem *h = new kcrn_problem();
+    h->n = n_rows; h->d = n_cols; h->nnz = nnz; h->n_global = n_global > 0 ? n_global : n_rows; h->l2 = l2;
+    h->stream = (cudaStream_t)stream;
+    cudaStream_t s = h->stream;
+    int rc = KCRN_OK;
+    auto run = [&]() -> int {
+        h->csr.nseg = n_rows; h->csr.nnz = nnz;
+        KCRN_TRY(upload(&h->csr.ptr, indptr, (size_t)n_rows + 1, arrays_on_device, s));
+        KCRN_TRY(upload(&h->csr.idx, indices, (size_t)nnz, arrays_on_device, s));
+        KCRN_TRY(upload(&h->csr.val, data, (size_t)nnz, arrays_on_device, s));
+        KCRN_TRY(upload(&h->b, labels01, (size_t)n_rows, arrays_on_device, s));
+        h->counters[6] += arrays_on_device ? 0 : (int64_t)(sizeof(int32_t) * (n_rows + 1 + nnz) + sizeof(double) * (nnz + n_rows));
+        KCRN_TRY(build_csc(h->csr, n_cols, &h->csc, s));
+        KCRN_TRY(build_tiles(&h->csr, s));
+        KCRN_TRY(build_tiles(&h->csc, s));
+        const size_t n = (size_t)n_rows, d = (size_t)n_cols;
+        KCRN_CUDA(cudaMalloc(&h->x_cur, sizeof(double) * d));
+        KCRN_CUDA(cudaMalloc(&h->Ax, sizeof(double) * n));
+        KCRN_CUDA(cudaMalloc(&h->D, sizeof(double) * n));
+        KCRN_CUDA(cudaMalloc(&h->resid, sizeof(double) * n));
+        KCRN_CUDA(cudaMalloc(&h->ell, sizeof(double) * n));
+        KCRN_CUDA(cudaMalloc(&h->t, sizeof(double) * n));
+        KCRN_CUDA(cudaMalloc(&h->ypart, sizeof(double) * d));
+        KCRN_CUDA(cudaMalloc(&h->w, sizeof(double) * d));
+        KCRN_CUDA(cudaMalloc(&h->wp, sizeof(double) * d));
+        KCRN_CUDA(cudaMalloc(&h->g, sizeof(double) * d));
+        KCRN_CUDA(cudaMalloc(&h->x_stage, sizeof(double) * d));
+        KCRN_CUDA(cudaMalloc(&h->v_stage, sizeof(double) * d));
+        KCRN_CUDA(cudaMalloc(&h->o_stage, sizeof(double) * d));
+        KCRN_CUDA(cudaMalloc(&h->alphas, sizeof(double) * (kMaxM + 2)));
+        KCRN_CUDA(cudaMalloc(&h->bet, sizeof(double) * (kMaxM + 2)));
+        KCRN_CUDA(cudaMalloc(&h->coef, sizeof(double) * (kMaxM + 2)));
+        KCRN_CUDA(cudaMalloc(&h->coef2, sizeof(double) * (kMaxM + 2)));
+        KCRN_CUDA(cudaMalloc(&h->sub, sizeof(double) * (kMaxM + 8)));
+        KCRN_CUDA(cudaMalloc(&h->scal, sizeof(double) * 16));
+        KCRN_CUDA(cudaMalloc(&h->ctl, sizeof(LanczosCtl)));
+        KCRN_CUDA(cudaMalloc(&h->info, sizeof(int32_t) * 8));
+        KCRN_CUDA(cudaMalloc(&h->red_ticket, sizeof(unsigned) * 8));
+        KCRN_CUDA(cudaMemsetAsync(h->red_ticket, 0, sizeof(unsigned) * 8, s));
+        KCRN_CUDA(cudaMemsetAsync(h->scal, 0, sizeof(double) * 16, s));
+        KCRN_CUDA(cudaMemsetAsync(h->sub, 0, sizeof(double) * (kMaxM + 8), s));
+        KCRN_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(LanczosCtl), s));
+        KCRN_CUDA(cudaMemsetAsync(h->info, 0, sizeof(int32_t) * 8, s));
+        KCRN_CUDA(cudaMallocHost(&h->rec_host, sizeof(double) * 16));
+        h->vec_elems = n_cols > (int64_t)kNumSm * kVecThreads * 4 ? 4 : 1;
+        h->vec_grid = (int)((n_cols + (int64_t)kVecThreads * h->vec_elems - 1) / ((int64_t)kVecThreads * h->vec_elems));
+        KCRN_TRY(lanczos_alloc(h, 1));
+        KCRN_CUDA(cudaStreamSynchronize(s));
+        return KCRN_OK;
+    };
+    rc = run();
+    if (rc != KCRN_OK) {
+        kcrn_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return KCRN_OK;
+}
+
+int kcrn_destroy(kcrn_handle h) {
+    if (!h) return KCRN_OK;
+    cudaStreamSynchronize(h->stream);
+    nccl_destroy(h);
+    for (auto &ge : h->graphs) cudaGraphExecDestroy(ge.exec);
+    free_segmat(&h->csr);
+    free_segmat(&h->csc);
+    double *bufs[] = {h->b, h->x_cur, h->Ax, h->D, h->resid, h->ell, h->t, h->ypart, h->V, h->w, h->wp, h->g,
+                      h->alphas, h->bet, h->coef, h->coef2, h->sub, h->scal, h->red_partials, h->x_stage,
+                      h->v_stage, h->o_stage};
+    for (double *p : bufs) cudaFree(p);
+    cudaFree(h->ctl);
+    cudaFree(h->info);
+    cudaFree(h->red_ticket);
+    cudaFreeHost(h->rec_host);
+    delete h;
+    return KCRN_OK;
+}
+
+int kcrn_set_stream(kcrn_handle h, void *stream) {
+    if (!h) { set_error("kcrn_set_stream: null handle"); return KCRN_E_ARG; }
+    h->stream = (cudaStream_t)stream;
+    return KCRN_OK;
+}
+
+int kcrn_sync(kcrn_handle h) {
+    if (!h) { set_error("kcrn_sync: null handle"); return KCRN_E_ARG; }
+    KCRN_CUDA(cudaStreamSynchronize(h->stream));
+    return KCRN_OK;
+}
+
+int kcrn_nccl_unique_id(void *unique_id_128_host) { return nccl_unique_id(unique_id_128_host); }
+
+int kcrn_comm_init(kcrn_handle h, const void *unique_id_128_host, int rank, int world) {
+    if (!h || !unique_id_128_host || world < 1 || rank < 0 || rank >= world) {
+        set_error("kcrn_comm_init: bad argument");
+        return KCRN_E_ARG;
+    }
+    if (world == 1) return KCRN_OK;
+    for (auto &ge : h->graphs) cudaGraphExecDestroy(ge.exec);
+    h->graphs.clear();
+    return nccl_init(h, unique_id_128_host, rank, world);
+}
+
+int kcrn_csc_view(kcrn_handle h, int32_t *indptr_host, int32_t *indices_host, double *data_host) {
+    if (!h) { set_error("kcrn_csc_view: null handle"); return KCRN_E_ARG; }
+    cudaStream_t s = h->stream;
+    if (indptr_host) KCRN_CUDA(cudaMemcpyAsync(indptr_host, h->csc.ptr, sizeof(int32_t) * (h->d + 1), cudaMemcpyDeviceToHost, s));
+    if (indices_host && h->nnz) KCRN_CUDA(cudaMemcpyAsync(indices_host, h->csc.idx, sizeof(int32_t) * h->nnz, cudaMemcpyDeviceToHost, s));
+    if (data_host && h->nnz) KCRN_CUDA(cudaMemcpyAsync(data_host, h->csc.val, sizeof(double) * h->nnz, cudaMemcpyDeviceToHost, s));
+    KCRN_CUDA(cudaStreamSynchronize(s));
+    return KCRN_OK;
+}
+
+int kcrn_set_x(kcrn_handle h, const double *x_dev) {
+    if (!h || !x_dev) { set_error("kcrn_set_x: null argument"); return KCRN_E_ARG; }
+    if (x_dev != h->x_cur)
+        KCRN_CUDA(cudaMemcpyAsync(h->x_cur, x_dev, sizeof(double) * h->d, cudaMemcpyDeviceToDevice, h->stream));
+    KCRN_TRY(launch_forward(h, h->x_cur));
+    h->have_x = true;
+    return KCRN_OK;
+}
+
+int kcrn_value(kcrn_handle h, double *out_dev) {
+    KCRN_TRY(need_x(h, "kcrn_value"));
+    if (!out_dev) { set_error("kcrn_value: null output"); return KCRN_E_ARG; }
+    return enqueue_value(h, out_dev);
+}
+
+int kcrn_gradient(kcrn_handle h, double *out_dev) {
+    KCRN_TRY(need_x(h, "kcrn_gradient"));
+    return cols_product(h, h->resid, h->l2 != 0.0 ? h->x_cur : nullptr, out_dev ? out_dev : h->g);
+}
+
+int kcrn_hvp(kcrn_handle h, const double *v_dev, double *out_dev) {
+    KCRN_TRY(need_x(h, "kcrn_hvp"));
+    if (!v_dev || !out_dev) { set_error("kcrn_hvp: null argument"); return KCRN_E_ARG; }
+    KCRN_TRY(launch_rows_weighted(h, v_dev));
+    h->counters[2] += 1;
+    return cols_product(h, h->t, h->l2 != 0.0 ? v_dev : nullptr, out_dev);
+}
+
+int kcrn_value_grad_host(kcrn_handle h, const double *x_host, double *value_host, double *grad_host) {
+    if (!h || !x_host) { set_error("kcrn_value_grad_host: null argument"); return KCRN_E_ARG; }
+    cudaStream_t s = h->stream;
+    KCRN_CUDA(cudaMemcpyAsync(h->x_stage, x_host, sizeof(double) * h->d, cudaMemcpyHostToDevice, s));
+    h->counters[6] += (int64_t)sizeof(double) * h->d;
+    KCRN_TRY(kcrn_set_x(h, h->x_stage));
+    if (value_host) {
+        KCRN_TRY(enqueue_value(h, h->scal + 0));
+        KCRN_CUDA(cudaMemcpyAsync(value_host, h->scal + 0, sizeof(double), cudaMemcpyDeviceToHost, s));
+        h->counters[7] += (int64_t)sizeof(double);
+    }
+    if (grad_host) {
+        KCRN_TRY(kcrn_gradient(h, h->o_stage));
+        KCRN_CUDA(cudaMemcpyAsync(grad_host, h->o_stage, sizeof(double) * h->d, cudaMemcpyDeviceToHost, s));
+        h->counters[7] += (int64_t)sizeof(double) * h->d;
+    }
+    KCRN_CUDA(cudaStreamSynchronize(s));
+    return KCRN_OK;
+}
+
+int kcrn_hvp_host(kcrn_handle h, const double *x_host_or_null, const double *v_host, double *out_host) {
+    if (!h || !v_host || !out_host) { set_error("kcrn_hvp_host: null argument"); return KCRN_E_ARG; }
+    cudaStream_t s = h->stream;
+    if (x_host_or_null) {
+        KCRN_CUDA(cudaMemcpyAsync(h->x_stage, x_host_or_null, sizeof(double) * h->d, cudaMemcpyHostToDevice, s));
+        h->counters[6] += (int64_t)sizeof(double) * h->d;
+        KCRN_TRY(kcrn_set_x(h, h->x_stage));
+    }
+    KCRN_CUDA(cudaMemcpyAsync(h->v_stage, v_host, sizeof(double) * h->d, cudaMemcpyHostToDevice, s));
+    h->counters[6] += (int64_t)sizeof(double) * h->d;
+    KCRN_TRY(kcrn_hvp(h, h->v_stage, h->o_stage));
+    KCRN_CUDA(cudaMemcpyAsync(out_host, h->o_stage, sizeof(double) * h->d, cudaMemcpyDeviceToHost, s));
+    h->counters[7] += (int64_t)sizeof(double) * h->d;
+    KCRN_CUDA(cudaStreamSynchronize(s));
+    return KCRN_OK;
+}
+
+int kcrn_cached_Ax(kcrn_handle h, const double **Ax_dev) {
+    KCRN_TRY(need_x(h, "kcrn_cached_Ax"));
+    *Ax_dev = h->Ax;
+    return KCRN_OK;
+}
+
+int kcrn_set_Ax(kcrn_handle h, const double *Ax_dev) {
+    if (!h || !Ax_dev) { set_error("kcrn_set_Ax: null argument"); return KCRN_E_ARG; }
+    if (Ax_dev != h->Ax)
+        KCRN_CUDA(cudaMemcpyAsync(h->Ax, Ax_dev, sizeof(double) * h->n, cudaMemcpyDeviceToDevice, h->stream));
+    KCRN_TRY(launch_derive_from_Ax(h));
+    h->have_x = true;
+    return KCRN_OK;
+}
+
+int kcrn_lanczos(kcrn_handle h, const double *g_dev, int m, int reorth) {
+    KCRN_TRY(need_x(h, "kcrn_lanczos"));
+    if (m < 1 || m > kMaxM) { set_error("kcrn_lanczos: m = %d outside [1, %d]", m, kMaxM); return KCRN_E_ARG; }
+    reorth = reorth ? 1 : 0;
+    KCRN_TRY(lanczos_alloc(h, m));
+    if (g_dev && g_dev != h->g)
+        KCRN_CUDA(cudaMemcpyAsync(h->g, g_dev, sizeof(double) * h->d, cudaMemcpyDeviceToDevice, h->stream));
+    cudaGraphExec_t exec = nullptr;
+    for (auto &ge : h->graphs)
+        if (ge.m == m && ge.reorth == reorth) exec = ge.exec;
+    if (!exec) {
+        cudaStream_t user = h->stream, cap = nullptr;
+        KCRN_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+        int64_t saved[8];
+        memcpy(saved, h->counters, sizeof(saved));
+        h->stream = cap;
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed);
+        int rc = e == cudaSuccess ? enqueue_lanczos(h, m, reorth) : KCRN_E_CUDA;
+        cudaError_t e2 = cudaStreamEndCapture(cap, &graph);
+        h->stream = user;
+        for (int i = 0; i < 8; ++i) h->graph_delta[i] = h->counters[i] - saved[i];
+        memcpy(h->counters, saved, sizeof(saved));
+        if (e != cudaSuccess || e2 != cudaSuccess || rc != KCRN_OK || !graph) {
+            if (rc == KCRN_OK) set_error("kcrn_lanczos: graph capture failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+            if (graph) cudaGraphDestroy(graph);
+            cudaStreamDestroy(cap);
+            return rc != KCRN_OK ? rc : KCRN_E_CUDA;
+        }
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        cudaStreamDestroy(cap);
+        if (e != cudaSuccess) { set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e)); return KCRN_E_CUDA; }
+        kcrn_problem::GraphEntry ge;
+        ge.m = m; ge.reorth = reorth; ge.exec = exec;
+        memcpy(ge.delta, h->graph_delta, sizeof(ge.delta));
+        h->graphs.push_back(ge);
+    }
+    KCRN_CUDA(cudaGraphLaunch(exec, h->stream));
+    for (auto &ge : h->graphs)
+        if (ge.exec == exec)
+            for (int i = 0; i < 8; ++i) h->counters[i] += ge.delta[i];
+    h->counters[1] += 1;
+    h->counters[2] += m;
+    h->cur_m = m;
+    h->cur_reorth = reorth;
+    return KCRN_OK;
+}
+
+int kcrn_lanczos_view(kcrn_handle h, const double **V_dev, const double **alphas_dev, const double **bet_dev,
+                      const int32_t **info_dev) {
+    if (!h) { set_error("kcrn_lanczos_view: null handle"); return KCRN_E_ARG; }
+    if (V_dev) *V_dev = h->V;
+    if (alphas_dev) *alphas_dev = h->alphas;
+    if (bet_dev) *bet_dev = h->bet;
+    if (info_dev) *info_dev = h->info;
+    return KCRN_OK;
+}
+
+int kcrn_lanczos_begin(kcrn_handle h, const double *g_dev, int m, int reorth) {
+    if (!h || !g_dev) { set_error("kcrn_lanczos_begin: null argument"); return KCRN_E_ARG; }
+    if (m < 1 || m > kMaxM) { set_error("kcrn_lanczos_begin: m = %d outside [1, %d]", m, kMaxM); return KCRN_E_ARG; }
+    KCRN_TRY(lanczos_alloc(h, m));
+    if (g_dev != h->g)
+        KCRN_CUDA(cudaMemcpyAsync(h->g, g_dev, sizeof(double) * h->d, cudaMemcpyDeviceToDevice, h->stream));
+    h->cur_m = m;
+    h->cur_reorth = reorth ? 1 : 0;
+    KCRN_TRY(launch_lanczos_init(h, m));
+    KCRN_TRY(launch_normalise_current(h));
+    KCRN_TRY(launch_lanczos_finish(h));
+    h->step_col = 0;
+    return KCRN_OK;
+}
+
+int kcrn_lanczos_current(kcrn_handle h, const double **cur_dev) {
+    if (!h || !cur_dev) { set_error("kcrn_lanczos_current: null argument"); return KCRN_E_ARG; }
+    *cur_dev = h->V + (size_t)h->step_col * (size_t)h->d;
+    return KCRN_OK;
+}
+
+int kcrn_lanczos_feed(kcrn_handle h, const double *hv_dev, int *finished_host) {
+    if (!h || !hv_dev || !finished_host) { set_error("kcrn_lanczos_feed: null argument"); return KCRN_E_ARG; }
+    KCRN_TRY(launch_lanczos_post(h, hv_dev, 0));
+    KCRN_TRY(launch_lanczos_update(h, h->cur_reorth));   // no-op on the device once the last alpha is in
+    KCRN_TRY(launch_normalise_current(h));
+    KCRN_TRY(launch_lanczos_finish(h));
+    int32_t info[8];
+    KCRN_CUDA(cudaMemcpyAsync(info, h->info, sizeof(info), cudaMemcpyDeviceToHost, h->stream));
+    KCRN_CUDA(cudaStreamSynchronize(h->stream));
+    h->step_col = info[4];
+    *finished_host = info[5];
+    return KCRN_OK;
+}
+
+int kcrn_cubic_tridiag(const double *alphas_dev, const double *betas_dev, int m, double gnorm, double M, double r0,
+                       double eps, int it_max, double *out_dev, void *stream) {
+    if (!alphas_dev || !out_dev || (m > 1 && !betas_dev)) { set_error("kcrn_cubic_tridiag: null argument"); return KCRN_E_ARG; }
+    return launch_cubic(alphas_dev, betas_dev, m, nullptr, nullptr, gnorm, M, r0, eps, it_max, out_dev, out_dev + m,
+                        (cudaStream_t)stream);
+}
+
+int kcrn_cubic_from_lanczos(kcrn_handle h, double M, double r0, double eps, int it_max) {
+    if (!h || h->cur_m < 1) { set_error("kcrn_cubic_from_lanczos: no Lanczos result in the handle"); return KCRN_E_STATE; }
+    h->counters[0] += 1;
+    return launch_cubic(h->alphas, h->bet + 1, h->cur_m, h->info, h->bet, 0.0, M, r0, eps, it_max, h->sub,
+                        h->sub + kMaxM, h->stream);
+}
+
+int kcrn_axpy_basis(const double *x_dev, const double *V_dev, const double *s_dev, int m, int64_t d, double *out_dev,
+                    void *stream) {
+    if (!x_dev || !V_dev || !s_dev || !out_dev || m < 0 || m > kMaxM || d < 1) {
+        set_error("kcrn_axpy_basis: bad argument");
+        return KCRN_E_ARG;
+    }
+    return launch_axpy_basis(x_dev, V_dev, s_dev, m, nullptr, d, out_dev, (cudaStream_t)stream);
+}
+
+int kcrn_trial_point(kcrn_handle h, const double *x_dev, double *out_dev) {
+    if (!h || !x_dev || !out_dev || h->cur_m < 1) { set_error("kcrn_trial_point: bad argument or no Lanczos result"); return KCRN_E_ARG; }
+    h->counters[0] += 1;
+    return launch_axpy_basis(x_dev, h->V, h->sub, h->cur_m, h->info, h->d, out_dev, h->stream, h->red_partials,
+                             h->red_ticket + 5, h->scal + 3);
+}
+
+int kcrn_step_record(kcrn_handle h, int with_value, double *rec12_host) {
+    double *rec8_host = rec12_host;
+    if (!h || !rec8_host) { set_error("kcrn_step_record: null argument"); return KCRN_E_ARG; }
+    cudaStream_t s = h->stream;
+    if (with_value) {
+        KCRN_TRY(need_x(h, "kcrn_step_record"));
+        KCRN_TRY(enqueue_value(h, h->scal + 0));
+    }
+    double *r = h->rec_host;
+    int32_t *ri = reinterpret_cast<int32_t *>(r + 8);
+    KCRN_CUDA(cudaMemcpyAsync(r + 0, h->scal + 0, sizeof(double), cudaMemcpyDeviceToHost, s));
+    KCRN_CUDA(cudaMemcpyAsync(r + 1, h->sub + kMaxM, sizeof(double) * 4, cudaMemcpyDeviceToHost, s));
+    KCRN_CUDA(cudaMemcpyAsync(r + 5, h->bet, sizeof(double), cudaMemcpyDeviceToHost, s));
+    KCRN_CUDA(cudaMemcpyAsync(r + 6, h->scal + 3, sizeof(double), cudaMemcpyDeviceToHost, s));
+    KCRN_CUDA(cudaMemcpyAsync(ri, h->info, sizeof(int32_t) * 8, cudaMemcpyDeviceToHost, s));
+    KCRN_CUDA(cudaStreamSynchronize(s));
+    h->counters[7] += (int64_t)(sizeof(double) * 7 + sizeof(int32_t) * 8);
+    rec8_host[0] = r[0];           // value at the current x
+    rec8_host[1] = r[2];           // model decrease
+    rec8_host[2] = r[1];           // r
+    rec8_host[3] = r[3];           // Newton iterations
+    rec8_host[4] = r[4];           // status
+    rec8_host[5] = (double)ri[0];  // m_eff
+    rec8_host[6] = r[5];           // |g|
+    rec8_host[7] = (double)ri[3];  // operator applications of the last Lanczos run
+    rec12_host[8] = r[6];          // |x_trial - x| of the last kcrn_trial_point
+    rec12_host[9] = (double)ri[1]; // basis columns written
+    rec12_host[10] = (double)ri[2];// breakdown flag
+    rec12_host[11] = 0.0;
+    return KCRN_OK;
+}
+
+int kcrn_hessian_dense(kcrn_handle h, double *out_dev) {
+    KCRN_TRY(need_x(h, "kcrn_hessian_dense"));
+    return config4_hessian_dense(h, out_dev);
+}
+int kcrn_partial_gradient(kcrn_handle h, const int64_t *I_dev, int m, double *out_dev) {
+    KCRN_TRY(need_x(h, "kcrn_partial_gradient"));
+    return config4_partial_gradient(h, I_dev, m, out_dev);
+}
+int kcrn_partial_hessian(kcrn_handle h, const int64_t *I_dev, int m, double *out_dev) {
+    KCRN_TRY(need_x(h, "kcrn_partial_hessian"));
+    return config4_partial_hessian(h, I_dev, m, out_dev);
+}
+int kcrn_update_Ax(kcrn_handle h, const int64_t *I_dev, const double *delta_dev, int m) {
+    KCRN_TRY(need_x(h, "kcrn_update_Ax"));
+    return config4_update_Ax(h, I_dev, delta_dev, m);
+}
+
+int kcrn_counters(kcrn_handle h, int64_t *counters8_host, int reset) {
+    if (!h || !counters8_host) { set_error("kcrn_counters: null argument"); return KCRN_E_ARG; }
+    memcpy(counters8_host, h->counters, sizeof(h->counters));
+    if (reset) memset(h->counters, 0, sizeof(h->counters));
+    return KCRN_OK;
+}
+
+int kcrn_time_sweep(kcrn_handle h, int which, int reps, double *mean_us_host) {
+    KCRN_TRY(need_x(h, "kcrn_time_sweep"));
+    if (reps < 1 || !mean_us_host) { set_error("kcrn_time_sweep: bad argument"); return KCRN_E_ARG; }
+    cudaEvent_t e0, e1;
+    KCRN_CUDA(cudaEventCreate(&e0));
+    KCRN_CUDA(cudaEventCreate(&e1));
+    // v = x_cur is as good as any vector for timing; t then holds D .* (A x)
+    KCRN_TRY(launch_rows_weighted(h, h->x_cur));
+    KCRN_CUDA(cudaEventRecord(e0, h->stream));
+    for (int i = 0; i < reps; ++i) {
+        if (which == 0) KCRN_TRY(launch_rows_weighted(h, h->x_cur));
+        else KCRN_TRY(launch_cols_scaled(h, h->t, nullptr, h->o_stage));
+    }
+    KCRN_CUDA(cudaEventRecord(e1, h->stream));
+    KCRN_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    KCRN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *mean_us_host = (double)ms * 1000.0 / reps;
+    return KCRN_OK;
+}
+
+}  // extern "C"

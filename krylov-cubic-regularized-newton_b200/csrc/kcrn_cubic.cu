@@ -1,0 +1,152 @@
+// K7: the m x m cubic sub-problem, solved on the device by one CTA.
+//
+//   argmin_s  <g, s> + 1/2 s' T s + M/3 |s|^3 ,   T = tridiag(betas, alphas, betas),  g = |grad| e1
+//
+// Follows cubic_solver_root (optimizer/cubic.py:40-75): Newton's method on the secular equation
+//   phi(lam) = lam^2 - M^2 |s_lam|^2 ,  s_lam = -(T + lam I)^-1 g ,
+//   phi'(lam) = 2 lam + 2 M^2 s_lam' (T + lam I)^-1 s_lam ,
+// iterated exactly as scipy's scalar `newton` does for root_scalar(method='newton', x0=r0,
+// xtol=eps, maxiter=it_max) (scipy/optimize/_zeros_py.py:319-358): stop when phi == 0 or when
+// |p - p0| <= eps, report the number of iterations the same way.  The reference solves with LAPACK
+// dposv on the dense T + lam I; for a tridiagonal matrix Cholesky touches only the two diagonals, so
+// the same factorisation is done here in O(m) per solve, and a non-positive pivot is reported like
+// dposv's info > 0 (status = KCRN_E_NOTPD).
+//
+// m <= 512 and a handful of Newton iterations: the work is a chain of dependent divisions and square
+// roots, so one thread walks it while the rest of the warp only helps to load and store.
+#include "kcrn_device.cuh"
+#include "kcrn_internal.cuh"
+
+namespace kcrn {
+
+namespace {
+
+struct Tri {
+    double *a, *b;      // diagonal, off-diagonal
+    double *l, *e;      // Cholesky factor: diagonal, sub-diagonal
+    double *s, *q;      // s_lam and (T + lam I)^-1 s_lam
+    int m;
+};
+
+// Cholesky of T + lam I; false when a pivot is not positive.
+__device__ bool factor(const Tri &t, double lam) {
+    double prev_e = 0.0;
+    for (int j = 0; j < t.m; ++j) {
+        double piv = t.a[j] + lam;
+        piv = __dsub_rn(piv, __dmul_rn(prev_e, prev_e));
+        if (!(piv > 0.0)) return false;
+        const double lj = sqrt(piv);
+        t.l[j] = lj;
+        if (j + 1 < t.m) {
+            prev_e = t.b[j] / lj;
+            t.e[j] = prev_e;
+        }
+    }
+    return true;
+}
+
+// out = (T + lam I)^-1 rhs using the factor; rhs may alias out
+__device__ void solve(const Tri &t, const double *rhs, double *out) {
+    double prev = 0.0;
+    for (int j = 0; j < t.m; ++j) {
+        double v = rhs[j];
+        if (j > 0) v = __dsub_rn(v, __dmul_rn(t.e[j - 1], prev));
+        prev = v / t.l[j];
+        out[j] = prev;
+    }
+    prev = 0.0;
+    for (int j = t.m - 1; j >= 0; --j) {
+        double v = out[j];
+        if (j + 1 < t.m) v = __dsub_rn(v, __dmul_rn(t.e[j], prev));
+        prev = v / t.l[j];
+        out[j] = prev;
+    }
+}
+
+__device__ double sumsq(const double *x, int m) {
+    double acc = 0.0;
+    for (int j = 0; j < m; ++j) acc = __dadd_rn(acc, __dmul_rn(x[j], x[j]));
+    return acc;
+}
+
+__global__ void __launch_bounds__(32) cubic_kernel(const double *__restrict__ alphas,
+                                                   const double *__restrict__ betas, int m_arg,
+                                                   const int32_t *__restrict__ info,
+                                                   const double *__restrict__ gnorm_dev, double gnorm_arg,
+                                                   double M, double r0, double eps, int it_max,
+                                                   double *__restrict__ s_out, double *__restrict__ scal_out) {
+    __shared__ double sa[kMaxM], sb[kMaxM], sl[kMaxM], se[kMaxM], ss[kMaxM], sq[kMaxM];
+    const int m = info ? info[0] : m_arg;
+    const double gnorm = gnorm_dev ? gnorm_dev[0] : gnorm_arg;
+    for (int j = threadIdx.x; j < m; j += 32) {
+        sa[j] = alphas[j];
+        sb[j] = j + 1 < m ? betas[j] : 0.0;
+    }
+    __syncwarp();
+    double r = r0, dec = 0.0;
+    int its = 0, status = 0;
+    if (threadIdx.x == 0) {
+        Tri t{sa, sb, sl, se, ss, sq, m};
+        double p0 = r0, p = r0;
+        bool finished = false;
+        for (int itr = 0; itr < it_max && !finished; ++itr) {
+            if (!factor(t, p0)) { status = KCRN_E_NOTPD; r = p0; its = itr; finished = true; break; }
+            // s = -(T + p0 I)^-1 g with g = gnorm e1
+            for (int j = 0; j < m; ++j) ss[j] = 0.0;
+            ss[0] = gnorm;
+            solve(t, ss, ss);
+            for (int j = 0; j < m; ++j) ss[j] = -ss[j];
+            const double ns = sqrt(sumsq(ss, m));
+            const double fval = __dsub_rn(__dmul_rn(p0, p0), __dmul_rn(__dmul_rn(M, M), __dmul_rn(ns, ns)));
+            if (fval == 0.0) { r = p0; its = itr; finished = true; break; }
+            solve(t, ss, sq);
+            double sdot = 0.0;
+            for (int j = 0; j < m; ++j) sdot = __dadd_rn(sdot, __dmul_rn(ss[j], sq[j]));
+            // 2 lam - M^2 * (-2 s.q)
+            const double fder = __dsub_rn(__dmul_rn(2.0, p0), __dmul_rn(__dmul_rn(M, M), __dmul_rn(-2.0, sdot)));
+            if (fder == 0.0) { r = p0; its = itr + 1; finished = true; break; }
+            p = __dsub_rn(p0, fval / fder);
+            if (fabs(p - p0) <= eps) { r = p; its = itr + 1; finished = true; break; }
+            p0 = p;
+        }
+        if (!finished) { r = p; its = it_max; }
+        if (status == 0) {
+            if (!factor(t, r)) status = KCRN_E_NOTPD;
+        }
+        if (status == 0) {
+            for (int j = 0; j < m; ++j) ss[j] = 0.0;
+            ss[0] = gnorm;
+            solve(t, ss, ss);
+            for (int j = 0; j < m; ++j) ss[j] = -ss[j];
+            const double ns = sqrt(sumsq(ss, m));
+            // r/2 |s|^2 - M/3 |s|^3 - <g, s>/2
+            dec = (r / 2.0) * (ns * ns) - (M / 3.0) * (ns * ns * ns) - (gnorm * ss[0]) / 2.0;
+        } else {
+            for (int j = 0; j < m; ++j) ss[j] = 0.0;
+        }
+    }
+    __syncwarp();
+    for (int j = threadIdx.x; j < m_arg; j += 32) s_out[j] = j < m ? ss[j] : 0.0;
+    if (threadIdx.x == 0) {
+        scal_out[0] = r;
+        scal_out[1] = dec;
+        scal_out[2] = (double)its;
+        scal_out[3] = (double)status;
+    }
+}
+
+}  // namespace
+
+int launch_cubic(const double *alphas, const double *betas, int m, const int32_t *info, const double *gnorm_dev,
+                 double gnorm, double M, double r0, double eps, int it_max, double *s_out, double *scal_out,
+                 cudaStream_t st) {
+    if (m < 1 || m > kMaxM) {
+        set_error("cubic sub-problem: m = %d outside [1, %d]", m, kMaxM);
+        return KCRN_E_ARG;
+    }
+    cubic_kernel<<<1, 32, 0, st>>>(alphas, betas, m, info, gnorm_dev, gnorm, M, r0, eps, it_max, s_out, scal_out);
+    KCRN_LAUNCH_CHECK();
+    return KCRN_OK;
+}
+
+}  // namespace kcrn

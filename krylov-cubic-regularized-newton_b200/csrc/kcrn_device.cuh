@@ -1,0 +1,48 @@
+// Device-side helpers shared by the kernels of libkcrn.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace kcrn {
+
+// Fixed butterfly: every lane ends with the same total, the order of additions never changes.
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// streaming loads of the matrix arrays: read-only path, do not keep the line in L1
+__device__ __forceinline__ int ld_stream(const int32_t *p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_stream(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+// x / b with b fixed for the whole kernel: rinv = 1/b (IEEE) is formed once per thread, then one
+// Newton correction on the quotient (Markstein).  Bit-identical for every reader of the same x, so
+// the stored basis vector and the values gathered on the fly agree exactly.
+__device__ __forceinline__ double quotient(double x, double b, double rinv) {
+    const double q = x * rinv;
+    const double r = fma(-b, q, x);
+    return fma(r, rinv, q);
+}
+
+// scipy.special.expit as the reference calls it (optimizer/loss.py:225,296): 1 / (1 + exp(-x))
+__device__ __forceinline__ double sigmoid(double x) { return 1.0 / (1.0 + exp(-x)); }
+
+// log(sigmoid(x)) in the four ranges of the reference's jitted helper (optimizer/loss.py:161-176)
+__device__ __forceinline__ double log_sigmoid(double x) {
+    if (x < -33.0) return x;
+    if (x < -18.0) return x - exp(x);
+    if (x < 37.0) return -log1p(exp(-x));
+    return -exp(-x);
+}
+
+}  // namespace kcrn

@@ -1,0 +1,168 @@
+// Internal declarations shared by the translation units of libkcrn.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "kcrn.h"
+
+namespace kcrn {
+
+// ----------------------------------------------------------------------------- errors
+void set_error(const char *fmt, ...);
+#define KCRN_CUDA(call)                                                                        \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            kcrn::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return KCRN_E_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+#define KCRN_TRY(call)                 \
+    do {                               \
+        int r_ = (call);               \
+        if (r_ != KCRN_OK) return r_;  \
+    } while (0)
+#define KCRN_LAUNCH_CHECK() KCRN_CUDA(cudaGetLastError())
+
+// ----------------------------------------------------------------------------- geometry
+constexpr int kTileNnz = 256;      // non-zeros staged per warp tile (8 per lane)
+constexpr int kTileSegs = 256;     // at most this many segments (rows / columns) per tile
+constexpr int kSweepWarps = 8;     // warps per CTA of the sweep kernels
+constexpr int kSweepThreads = kSweepWarps * 32;
+constexpr int kVecThreads = 256;   // CTA size of the d-length vector kernels
+constexpr int kMaxM = 512;         // largest Lanczos subspace the single-CTA solver accepts
+constexpr int kNumSm = 148;        // B200
+
+// One sparse matrix stored by segments: rows (CSR) or columns (CSC).
+//   tiles[i] = {seg0, k0, z, nk | logG << 16}:
+//     z > 0 : "stream" tile -- z whole segments seg0..seg0+z whose non-zeros are [k0, k0+nk);
+//             every group of 2^logG lanes reduces one segment
+//     z < 0 : one 256-non-zero piece [k0, k0+nk) of the long segment seg0; -z-1 indexes longtab
+//   longtab[l] = {first partial slot, number of pieces, ptr[seg], seg}
+struct SegMat {
+    int64_t nseg = 0, nnz = 0;
+    int32_t *ptr = nullptr, *idx = nullptr;
+    double *val = nullptr;
+    int4 *tiles = nullptr;
+    int ntiles = 0;
+    int4 *longtab = nullptr;
+    int nlong = 0, npartial = 0;
+    double *partial = nullptr;   // [npartial] piece sums of long segments
+    double *longdot = nullptr;   // [nlong]    v.w contribution of each long segment (Lanczos)
+    unsigned *ticket = nullptr;  // [nlong]    self-resetting arrival counters
+    int grid = 0;                // CTAs of the sweep kernels over this matrix (fixed -> deterministic sums)
+};
+
+// Device-resident control block of the Lanczos recurrence (written by single threads on the device,
+// read by every kernel of the captured graph; no host involvement).
+struct LanczosCtl {
+    int col;        // index of the current Lanczos vector
+    int redo;       // 1: the next operator application re-uses V[col] as is (after a breakdown)
+    int final_;     // 1: the next operator application only produces alphas[store_idx]
+    int done;       // 1: recurrence finished, remaining graph nodes are no-ops
+    int m_eff;      // number of alphas the reference would return
+    int nvalid;     // number of basis columns written
+    int store_idx;  // where the final alpha goes
+    int m;
+    int broke;
+    int hvps;       // operator applications consumed
+    int pad0, pad1;
+    double last_beta;
+};
+
+struct Reduce {
+    double *partials = nullptr;  // [grid * width]
+    unsigned *ticket = nullptr;
+    int cap = 0;
+};
+
+}  // namespace kcrn
+
+struct kcrn_problem {
+    int64_t n = 0, d = 0, nnz = 0, n_global = 0;
+    double l2 = 0.0;
+    cudaStream_t stream = nullptr;
+    kcrn::SegMat csr, csc;
+    double *b = nullptr;
+    // caches at the current x
+    bool have_x = false;
+    double *x_cur = nullptr;                       // [d]
+    double *Ax = nullptr, *D = nullptr, *resid = nullptr, *ell = nullptr;  // [n]
+    // sweep temporaries
+    double *t = nullptr;        // [n]   D .* (A v)
+    double *ypart = nullptr;    // [d]   local A' t before the allreduce (row-sharded runs)
+    // Lanczos state
+    int m_cap = 0;
+    double *V = nullptr;        // [m_cap * d]
+    double *w = nullptr, *wp = nullptr, *g = nullptr;  // [d]
+    double *alphas = nullptr, *bet = nullptr, *coef = nullptr, *coef2 = nullptr;  // [kMaxM + 1]
+    kcrn::LanczosCtl *ctl = nullptr;
+    int32_t *info = nullptr;    // [8]
+    int cur_m = 0, cur_reorth = 0;
+    // sub-problem result {s[kMaxM], r, model_decrease, iterations, status}
+    double *sub = nullptr;
+    double *scal = nullptr;     // [16] device scalars: value, |x|^2, ...
+    double *rec_host = nullptr; // pinned [16]
+    // reductions
+    double *red_partials = nullptr;
+    unsigned *red_ticket = nullptr;   // [8]
+    int vec_grid = 0, vec_elems = 1, row_grid = 0;
+    // pinned staging for the host-buffer entry points
+    double *stage_host = nullptr;
+    size_t stage_bytes = 0;
+    double *x_stage = nullptr, *v_stage = nullptr, *o_stage = nullptr;  // [d] device
+    // captured Lanczos graphs, keyed by (m, reorth)
+    struct GraphEntry { int m, reorth; cudaGraphExec_t exec; int64_t delta[8]; };
+    std::vector<GraphEntry> graphs;
+    int64_t graph_delta[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int step_col = 0;           // column the step-wise Lanczos API is working on
+    // NCCL
+    void *comm = nullptr;
+    int rank = 0, world = 1;
+    int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+namespace kcrn {
+
+// ----------------------------------------------------------------------------- kcrn_transpose.cu
+int build_csc(const SegMat &csr, int64_t n_cols, SegMat *csc, cudaStream_t s);
+int exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t len, cudaStream_t s);
+
+// ----------------------------------------------------------------------------- kcrn_sweep.cu
+int build_tiles(SegMat *A, cudaStream_t s);
+void free_segmat(SegMat *A);
+int launch_forward(kcrn_problem *h, const double *x);                 // A x and everything derived
+int launch_rows_weighted(kcrn_problem *h, const double *v);           // t = D .* (A v)
+int launch_rows_lanczos(kcrn_problem *h);                             // same, source picked by ctl
+int launch_cols_raw(kcrn_problem *h, const double *src, double *out); // out = A' src
+int launch_cols_scaled(kcrn_problem *h, const double *src, const double *u, double *out);  // A' src / n + l2 u
+int launch_cols_lanczos(kcrn_problem *h);                             // w, alpha fused
+int launch_derive_from_Ax(kcrn_problem *h);
+
+// ----------------------------------------------------------------------------- kcrn_lanczos.cu
+int lanczos_alloc(kcrn_problem *h, int m);
+int launch_lanczos_init(kcrn_problem *h, int m);      // ctl, alphas, bet reset; bet[0] = |g|
+int launch_lanczos_post(kcrn_problem *h, const double *hv_or_raw, int raw);  // epilogue after allreduce / generic feed
+int launch_lanczos_update(kcrn_problem *h, int reorth);
+int launch_normalise_current(kcrn_problem *h);        // V[col] = src / bet[col] outside the fused sweep
+int launch_sum(kcrn_problem *h, const double *a, int64_t len, double scale, double *out);  // deterministic sum
+int launch_axpy_basis(const double *x, const double *V, const double *s, int m, const int32_t *info,
+                      int64_t d, double *out, cudaStream_t st, double *partials = nullptr,
+                      unsigned *ticket = nullptr, double *step_norm = nullptr);
+
+// ----------------------------------------------------------------------------- kcrn_cubic.cu
+int launch_cubic(const double *alphas, const double *betas, int m, const int32_t *info,
+                 const double *gnorm_dev, double gnorm, double M, double r0, double eps, int it_max,
+                 double *s_out, double *scal_out, cudaStream_t st);
+
+// ----------------------------------------------------------------------------- kcrn_nccl.cu
+int nccl_unique_id(void *out128);
+int nccl_init(kcrn_problem *h, const void *id128, int rank, int world);
+int nccl_allreduce_sum(kcrn_problem *h, double *buf, int64_t count);
+void nccl_destroy(kcrn_problem *h);
+
+}  // namespace kcrn

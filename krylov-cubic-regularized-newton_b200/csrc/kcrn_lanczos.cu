@@ -1,0 +1,449 @@
+// K5 / K6 / K8 and the small reductions: everything on d- or n-length vectors around the sweeps.
+//
+// Lanczos (optimizer/cubic.py:77-111) is advanced entirely on the device: a control block in global
+// memory (LanczosCtl) carries the column index, the breakdown state and the bookkeeping the reference
+// does in Python (:98-99 break, :105-108 truncation, :109 last alpha), so a whole m-step recurrence is
+// one CUDA graph with no host round trip.  Every reduction is two-level with a fixed grid and a
+// self-resetting arrival ticket: CTA partials are written to global memory and the last CTA to arrive
+// adds them in index order -- deterministic, no floating-point atomics.
+//
+//   update stage 0 : w' = w - alpha v              ; beta = |w'|            (cubic.py:95-97)
+//   update stage 1 : w' = w - alpha v              ; c  = V[:, :j+1]' w'    (re-orthogonalisation, K6;
+//   update stage 2 : w' = w' - V[:, :j+1] c        ; c2 = V[:, :j+1]' w'     not in the reference,
+//   update stage 3 : w' = w' - V[:, :j+1] c2       ; beta = |w'|             SURVEY.md section 8(c))
+//   post           : w = hv - beta_prev v_prev     ; alpha = v . w          (cubic.py:93-94, :109)
+//                    used after the allreduce of row-sharded runs and by the step-wise API
+#include <algorithm>
+
+#include "kcrn_device.cuh"
+#include "kcrn_internal.cuh"
+
+namespace kcrn {
+
+namespace {
+
+struct VecParams {
+    LanczosCtl *ctl;
+    double *V;
+    const double *w_in;
+    double *w_out;
+    double *wp;
+    const double *g;
+    int64_t d;
+    double *alphas, *bet;
+    const double *coef_in;
+    double *coef_out;
+    double *red_partials;
+    unsigned *red_ticket;
+    int stage, m, raw;
+    double n_samples, l2;
+    int32_t *info;
+};
+
+// Sum `v` over the whole grid.  Returns true in every thread of the CTA that arrived last; in that
+// CTA thread 0 receives the total.  `sh` holds blockDim.x / 32 doubles.
+__device__ __forceinline__ bool grid_sum(double v, double *partials, unsigned *ticket, double *sh, int *s_last,
+                                         double *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double cta = 0.0;
+        for (int w = 0; w < nwarp; ++w) cta += sh[w];
+        partials[blockIdx.x] = cta;
+        __threadfence();
+        *s_last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!*s_last) return false;
+    __threadfence();
+    double t = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += __ldcg(partials + i);
+    t = warp_sum(t);
+    if (lane == 0) sh[warp] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < nwarp; ++w) tot += sh[w];
+        *total = tot;
+    }
+    return true;
+}
+
+// |g| into bet[0]; reset of alphas, betas and the control block for an m-step run
+__global__ void __launch_bounds__(kVecThreads) lanczos_init_kernel(VecParams P) {
+    __shared__ double sh[kVecThreads / 32];
+    __shared__ int s_last;
+    double loc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.d; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = P.g[i];
+        loc = fma(x, x, loc);
+    }
+    double tot = 0.0;
+    if (!grid_sum(loc, P.red_partials, P.red_ticket, sh, &s_last, &tot)) return;
+    for (int i = threadIdx.x; i < P.m; i += blockDim.x) {
+        P.alphas[i] = 0.0;
+        P.bet[i + 1] = 0.0;
+    }
+    if (threadIdx.x == 0) {
+        P.bet[0] = sqrt(tot);
+        LanczosCtl c;
+        c.col = 0; c.redo = 0; c.final_ = (P.m == 1); c.done = 0; c.m_eff = P.m; c.nvalid = 1;
+        c.store_idx = P.m - 1; c.m = P.m; c.broke = 0; c.hvps = 0; c.pad0 = c.pad1 = 0; c.last_beta = 0.0;
+        *P.ctl = c;
+    }
+}
+
+// V[col] = source / bet[col] outside the fused row sweep (step-wise API)
+__global__ void __launch_bounds__(kVecThreads) normalise_kernel(VecParams P) {
+    if (P.ctl->done || P.ctl->redo) return;
+    const int col = P.ctl->col;
+    const double *src = col == 0 ? P.g : P.wp;
+    const double beta = P.bet[col], rinv = 1.0 / beta;
+    double *vout = P.V + (size_t)col * P.d;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.d; i += (int64_t)gridDim.x * blockDim.x)
+        vout[i] = quotient(src[i], beta, rinv);
+}
+
+template <int E>
+__global__ void __launch_bounds__(kVecThreads) lanczos_post_kernel(VecParams P) {
+    __shared__ double sh[kVecThreads / 32];
+    __shared__ int s_last;
+    if (P.ctl->done) return;
+    const int col = P.ctl->col, store_idx = P.ctl->store_idx;
+    const bool final_ = P.ctl->final_ != 0;
+    const double *v = P.V + (size_t)col * P.d;
+    const bool subtract = col > 0 && !final_;
+    const double *vpre = subtract ? P.V + (size_t)(col - 1) * P.d : nullptr;
+    const double beta_prev = subtract ? P.bet[col] : 0.0;
+    const int64_t base = (int64_t)blockIdx.x * (kVecThreads * E) + threadIdx.x;
+    double loc = 0.0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int64_t c = base + (int64_t)e * kVecThreads;
+        if (c < P.d) {
+            const double vc = v[c];
+            double hv = P.w_in[c];
+            if (P.raw) hv = __dadd_rn(hv / P.n_samples, __dmul_rn(P.l2, vc));
+            if (subtract) hv = __dsub_rn(hv, __dmul_rn(beta_prev, vpre[c]));
+            P.w_out[c] = hv;
+            loc = __dadd_rn(loc, __dmul_rn(vc, hv));
+        }
+    }
+    double tot = 0.0;
+    if (!grid_sum(loc, P.red_partials, P.red_ticket, sh, &s_last, &tot)) return;
+    if (threadIdx.x == 0) {
+        P.alphas[final_ ? store_idx : col] = tot;
+        P.ctl->hvps += 1;
+        if (final_) P.ctl->done = 1;
+    }
+}
+
+template <int E>
+__global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P) {
+    __shared__ double sh[kVecThreads / 32];
+    __shared__ int s_last;
+    __shared__ double sdots[kVecThreads / 32][kMaxM];
+    if (P.ctl->done) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = P.ctl->col;
+    const int nv = col + 1;  // basis columns built so far
+    const int64_t base = (int64_t)blockIdx.x * (kVecThreads * E) + threadIdx.x;
+    double x[E];
+    if (P.stage <= 1) {
+        const double alpha = P.alphas[col];
+        const double *v = P.V + (size_t)col * P.d;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int64_t c = base + (int64_t)e * kVecThreads;
+            x[e] = c < P.d ? __dsub_rn(P.w_in[c], __dmul_rn(alpha, v[c])) : 0.0;
+        }
+    } else {
+        double s[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int64_t c = base + (int64_t)e * kVecThreads;
+            x[e] = c < P.d ? P.wp[c] : 0.0;
+            s[e] = 0.0;
+        }
+        for (int i = 0; i < nv; ++i) {
+            const double ci = P.coef_in[i];
+            const double *vi = P.V + (size_t)i * P.d;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int64_t c = base + (int64_t)e * kVecThreads;
+                if (c < P.d) s[e] = fma(ci, vi[c], s[e]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) x[e] -= s[e];
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int64_t c = base + (int64_t)e * kVecThreads;
+        if (c < P.d) P.wp[c] = x[e];
+    }
+
+    if (P.stage == 0 || P.stage == 3) {
+        double loc = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) loc = fma(x[e], x[e], loc);
+        double tot = 0.0;
+        if (!grid_sum(loc, P.red_partials, P.red_ticket, sh, &s_last, &tot)) return;
+        if (threadIdx.x == 0) {
+            LanczosCtl *c = P.ctl;
+            const double beta = sqrt(tot);
+            const int m = c->m;
+            c->last_beta = beta;
+            if (fabs(beta) < 1e-6) {       // cubic.py:98 -- absolute test
+                c->broke = 1;
+                if (col < m - 2) { c->m_eff = col + 1; c->store_idx = col; }   // cubic.py:105-108
+                else { c->m_eff = m; c->store_idx = m - 1; }
+                c->redo = 1;               // cubic.py:109 re-applies the operator to the same v
+                c->final_ = 1;
+            } else {
+                P.bet[col + 1] = beta;
+                c->col = col + 1;
+                c->nvalid = col + 2;
+                if (col + 1 == m - 1) { c->final_ = 1; c->store_idx = m - 1; }
+            }
+        }
+        return;
+    }
+
+    // stages 1, 2: dots of the updated vector with every basis column built so far
+    for (int i = 0; i < nv; ++i) {
+        const double *vi = P.V + (size_t)i * P.d;
+        double loc = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int64_t c = base + (int64_t)e * kVecThreads;
+            if (c < P.d) loc = fma(vi[c], x[e], loc);
+        }
+        loc = warp_sum(loc);
+        if (lane == 0) sdots[warp][i] = loc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        double cta = 0.0;
+        for (int wv = 0; wv < kVecThreads / 32; ++wv) cta += sdots[wv][i];
+        P.red_partials[(size_t)blockIdx.x * nv + i] = cta;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicInc(P.red_ticket, gridDim.x - 1) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        double tot = 0.0;
+        for (int b = 0; b < (int)gridDim.x; ++b) tot += __ldcg(P.red_partials + (size_t)b * nv + i);
+        P.coef_out[i] = tot;
+    }
+}
+
+__global__ void lanczos_finish_kernel(const LanczosCtl *ctl, int32_t *info, double *bet) {
+    if (threadIdx.x == 0) {
+        bet[ctl->m] = ctl->last_beta;   // slot m is free: bet[j + 1] = beta_j only for j <= m - 2
+        info[0] = ctl->m_eff; info[1] = ctl->nvalid; info[2] = ctl->broke; info[3] = ctl->hvps;
+        info[4] = ctl->col; info[5] = ctl->done; info[6] = ctl->redo; info[7] = ctl->final_;
+    }
+}
+
+// mode 0: sum a[i];  mode 1: sum a[i]^2.   out[0] = total * scale
+__global__ void __launch_bounds__(kVecThreads) reduce_kernel(const double *__restrict__ a, int64_t len, int mode,
+                                                             double scale, double *partials, unsigned *ticket,
+                                                             double *out) {
+    __shared__ double sh[kVecThreads / 32];
+    __shared__ int s_last;
+    double loc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = a[i];
+        loc = mode ? fma(x, x, loc) : loc + x;
+    }
+    double tot = 0.0;
+    if (!grid_sum(loc, partials, ticket, sh, &s_last, &tot)) return;
+    if (threadIdx.x == 0) out[0] = tot * scale;
+}
+
+// value = (sum of loss terms) / n + l2 / 2 * |x|^2   (optimizer/loss.py:215-220)
+__global__ void value_combine_kernel(const double *scal, double n_samples, double l2, double *out) {
+    if (threadIdx.x == 0) {
+        double v = scal[1] / n_samples;
+        if (l2 != 0.0) {
+            const double nx = sqrt(scal[2]);
+            v = __dadd_rn(v, __dmul_rn(l2 / 2.0, __dmul_rn(nx, nx)));
+        }
+        out[0] = v;
+    }
+}
+
+// out = y / n + l2 u   (after the allreduce of a row-sharded transpose sweep)
+__global__ void scale_kernel(const double *__restrict__ y, const double *__restrict__ u, int64_t d,
+                             double n_samples, double l2, double *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = y[i] / n_samples;
+        if (u) v = __dadd_rn(v, __dmul_rn(l2, u[i]));
+        out[i] = v;
+    }
+}
+
+// out = x + sum_{i < cols} s[i] V[i]     (cubic.py:291,301); optionally |out - x| for the stopping rule
+// of the step loop (optimizer.py:110)
+__global__ void __launch_bounds__(kVecThreads) axpy_basis_kernel(const double *__restrict__ x,
+                                                                 const double *__restrict__ V,
+                                                                 const double *__restrict__ s, int m,
+                                                                 const int32_t *__restrict__ info, int64_t d,
+                                                                 double *__restrict__ out, double *partials,
+                                                                 unsigned *ticket, double *step_norm) {
+    __shared__ double ss[kMaxM];
+    __shared__ double sh[kVecThreads / 32];
+    __shared__ int s_last;
+    int cols = m;
+    if (info) cols = min(info[0], info[1]);
+    for (int i = threadIdx.x; i < cols; i += blockDim.x) ss[i] = s[i];
+    __syncthreads();
+    double loc = 0.0;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < d; c += (int64_t)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int i = 0; i < cols; ++i) acc = fma(V[(size_t)i * d + c], ss[i], acc);
+        const double xc = x[c];
+        const double xn = xc + acc;
+        out[c] = xn;
+        const double df = xn - xc;
+        loc = fma(df, df, loc);
+    }
+    if (!step_norm) return;
+    double tot = 0.0;
+    if (!grid_sum(loc, partials, ticket, sh, &s_last, &tot)) return;
+    if (threadIdx.x == 0) step_norm[0] = sqrt(tot);
+}
+
+VecParams base_params(kcrn_problem *h) {
+    VecParams P{};
+    P.ctl = h->ctl; P.V = h->V; P.wp = h->wp; P.g = h->g; P.d = h->d; P.alphas = h->alphas; P.bet = h->bet;
+    P.red_partials = h->red_partials; P.n_samples = (double)h->n_global; P.l2 = h->l2; P.info = h->info;
+    return P;
+}
+
+int grid_stride_blocks(int64_t len) {
+    int64_t b = (len + kVecThreads - 1) / kVecThreads;
+    if (b < 1) b = 1;
+    if (b > kNumSm * 8) b = kNumSm * 8;
+    return (int)b;
+}
+
+}  // namespace
+
+int lanczos_alloc(kcrn_problem *h, int m) {
+    if (m <= h->m_cap) return KCRN_OK;
+    KCRN_CUDA(cudaStreamSynchronize(h->stream));
+    for (auto &ge : h->graphs) cudaGraphExecDestroy(ge.exec);
+    h->graphs.clear();
+    cudaFree(h->V);
+    cudaFree(h->red_partials);
+    h->V = nullptr;
+    h->red_partials = nullptr;
+    KCRN_CUDA(cudaMalloc(&h->V, sizeof(double) * (size_t)m * (size_t)h->d));
+    const size_t width = (size_t)m + 1;
+    const size_t rows = (size_t)std::max(std::max(h->vec_grid, kNumSm * 8), std::max(h->csc.grid, h->csr.grid));
+    KCRN_CUDA(cudaMalloc(&h->red_partials, sizeof(double) * rows * width));
+    h->m_cap = m;
+    return KCRN_OK;
+}
+
+int launch_lanczos_init(kcrn_problem *h, int m) {
+    VecParams P = base_params(h);
+    P.m = m;
+    P.red_ticket = h->red_ticket + 4;
+    lanczos_init_kernel<<<grid_stride_blocks(h->d), kVecThreads, 0, h->stream>>>(P);
+    KCRN_LAUNCH_CHECK();
+    h->counters[0] += 1;
+    return KCRN_OK;
+}
+
+int launch_normalise_current(kcrn_problem *h) {
+    VecParams P = base_params(h);
+    normalise_kernel<<<grid_stride_blocks(h->d), kVecThreads, 0, h->stream>>>(P);
+    KCRN_LAUNCH_CHECK();
+    h->counters[0] += 1;
+    return KCRN_OK;
+}
+
+int launch_lanczos_post(kcrn_problem *h, const double *hv_or_raw, int raw) {
+    VecParams P = base_params(h);
+    P.w_in = hv_or_raw; P.w_out = h->w; P.raw = raw;
+    P.red_ticket = h->red_ticket + 2;
+    if (h->vec_elems == 4) lanczos_post_kernel<4><<<h->vec_grid, kVecThreads, 0, h->stream>>>(P);
+    else lanczos_post_kernel<1><<<h->vec_grid, kVecThreads, 0, h->stream>>>(P);
+    KCRN_LAUNCH_CHECK();
+    h->counters[0] += 1;
+    return KCRN_OK;
+}
+
+int launch_lanczos_update(kcrn_problem *h, int reorth) {
+    const int first = reorth ? 1 : 0, last = reorth ? 3 : 0;
+    for (int stage = first; stage <= last; ++stage) {
+        VecParams P = base_params(h);
+        P.w_in = h->w; P.stage = stage;
+        P.coef_in = stage == 2 ? h->coef : h->coef2;
+        P.coef_out = stage == 1 ? h->coef : h->coef2;
+        P.red_ticket = h->red_ticket + 1;
+        if (h->vec_elems == 4) lanczos_update_kernel<4><<<h->vec_grid, kVecThreads, 0, h->stream>>>(P);
+        else lanczos_update_kernel<1><<<h->vec_grid, kVecThreads, 0, h->stream>>>(P);
+        KCRN_LAUNCH_CHECK();
+        h->counters[0] += 1;
+    }
+    return KCRN_OK;
+}
+
+int launch_lanczos_finish(kcrn_problem *h) {
+    lanczos_finish_kernel<<<1, 32, 0, h->stream>>>(h->ctl, h->info, h->bet);
+    KCRN_LAUNCH_CHECK();
+    h->counters[0] += 1;
+    return KCRN_OK;
+}
+
+int launch_sum(kcrn_problem *h, const double *a, int64_t len, double scale, double *out) {
+    reduce_kernel<<<grid_stride_blocks(len), kVecThreads, 0, h->stream>>>(a, len, 0, scale, h->red_partials,
+                                                                           h->red_ticket + 3, out);
+    KCRN_LAUNCH_CHECK();
+    h->counters[0] += 1;
+    return KCRN_OK;
+}
+
+int launch_sumsq(kcrn_problem *h, const double *a, int64_t len, double *out) {
+    reduce_kernel<<<grid_stride_blocks(len), kVecThreads, 0, h->stream>>>(a, len, 1, 1.0, h->red_partials,
+                                                                           h->red_ticket + 3, out);
+    KCRN_LAUNCH_CHECK();
+    h->counters[0] += 1;
+    return KCRN_OK;
+}
+
+int launch_value_combine(kcrn_problem *h, double *out) {
+    value_combine_kernel<<<1, 32, 0, h->stream>>>(h->scal, (double)h->n_global, h->l2, out);
+    KCRN_LAUNCH_CHECK();
+    h->counters[0] += 1;
+    return KCRN_OK;
+}
+
+int launch_scale(kcrn_problem *h, const double *y, const double *u, double *out) {
+    scale_kernel<<<grid_stride_blocks(h->d), kVecThreads, 0, h->stream>>>(y, u, h->d, (double)h->n_global, h->l2, out);
+    KCRN_LAUNCH_CHECK();
+    h->counters[0] += 1;
+    return KCRN_OK;
+}
+
+int launch_axpy_basis(const double *x, const double *V, const double *s, int m, const int32_t *info, int64_t d,
+                      double *out, cudaStream_t st, double *partials, unsigned *ticket, double *step_norm) {
+    axpy_basis_kernel<<<grid_stride_blocks(d), kVecThreads, 0, st>>>(x, V, s, m, info, d, out, partials, ticket,
+                                                                     step_norm);
+    KCRN_LAUNCH_CHECK();
+    return KCRN_OK;
+}
+
+}  // namespace kcrn

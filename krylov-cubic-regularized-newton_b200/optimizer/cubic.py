@@ -1,0 +1,178 @@
+"""Krylov cubic-regularised Newton on the GPU (mirror of the reference's optimizer/cubic.py).
+
+Public names and call signatures follow the reference:
+
+    cubic_solver_root(g, H, M, it_max=100, epsilon=1e-8, r0=0.1) -> (s, iterations, r, model_decrease)   cubic.py:40-75
+    Lanczos(A, v, m=10)                                          -> (V, alphas, betas, beta)             cubic.py:77-111
+    Cubic_Krylov_LS(loss, reg_coef, subspace_dim, solver_eps, beta, ...)                                 cubic.py:238-319
+
+``Cubic_Krylov_LS.step`` enqueues one outer iteration on the device -- gradient sweep, the whole m-step
+Lanczos recurrence as one CUDA graph, the single-CTA sub-problem solve, the trial point, the forward
+sweep and the value reduction -- and reads all of its scalars back with ONE device-to-host copy; the
+backtracking loop on the regulariser M (cubic.py:294-303) stays on the host, as in the reference.
+``reorth=True`` (not in the reference) switches the recurrence to full re-orthogonalisation.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from kcrn_b200 import engine as _engine
+from kcrn_b200._lib import KCRN_E_NOTPD
+from optimizer.optimizer import Optimizer
+
+
+def _is_tensor(x) -> bool:
+    return hasattr(x, "data_ptr")
+
+
+def _host(a):
+    return a.detach().cpu().numpy() if _is_tensor(a) else np.asarray(a)
+
+
+# --------------------------------------------------------------------------------- sub-problem
+def cubic_solver_root(g, H, M, it_max=100, epsilon=1e-8, r0=0.1):
+    """Solve  min_s <g, s> + 1/2 <s, H s> + M/3 |s|^3  by Newton's method on the secular equation.
+
+    H must be (numerically) tridiagonal and g a multiple of e1 -- the form the Krylov method produces
+    (cubic.py:278-283); that system is solved by the single-CTA kernel of libkcrn.  Dense blocks
+    (SSCN, full CRN) go through ``optimizer.dense.cubic_solver_dense``.
+    """
+    import scipy.sparse as sp
+
+    g_host = _host(g).astype(np.float64).ravel()
+    m = g_host.size
+    Hh = H.toarray() if sp.issparse(H) else _host(H)
+    Hh = np.asarray(Hh, np.float64).reshape(m, m)
+    off = Hh - np.diag(np.diag(Hh)) - np.diag(np.diag(Hh, 1), 1) - np.diag(np.diag(Hh, -1), -1)
+    if np.any(off != 0.0) or np.any(g_host[1:] != 0.0) or not np.array_equal(np.diag(Hh, 1), np.diag(Hh, -1)):
+        raise NotImplementedError("cubic_solver_root on the device needs a symmetric tridiagonal H and g = c*e1")
+    s, r, dec, its, status = _engine.cubic_tridiag(np.diag(Hh).copy(), np.diag(Hh, 1).copy(), g_host[0], M,
+                                                   r0=r0, eps=epsilon, it_max=it_max)
+    if status == KCRN_E_NOTPD:
+        raise np.linalg.LinAlgError("H + r I is not positive definite")
+    s = s if _is_tensor(g) else s.cpu().numpy()
+    return s, its, r, dec
+
+
+# --------------------------------------------------------------------------------- Lanczos
+_workspaces = {}
+
+
+def _workspace(d: int):
+    """A matrix-free libkcrn handle (1 x d, no entries) that owns the basis and the recurrence state."""
+    import torch
+
+    key = (d, torch.cuda.current_device())
+    if key not in _workspaces:
+        _workspaces[key] = _engine.Engine(np.zeros(2, np.int32), np.zeros(0, np.int32), np.zeros(0), np.zeros(1),
+                                          (1, d))
+    return _workspaces[key]
+
+
+def Lanczos(A, v, m=10, reorth=False):
+    """m-step Lanczos for the symmetric operator ``A`` (a callable) started from v.
+
+    The recurrence, its breakdown test (beta < 1e-6, absolute), the truncation on early breakdown and
+    the final alpha follow cubic.py:77-111; the d-length arithmetic runs in libkcrn kernels.  Returns
+    V (d x m_eff), alphas (m_eff), betas (m_eff - 1) and the last beta, as numpy arrays when v is numpy
+    and as CUDA tensors otherwise.
+    """
+    import torch
+
+    as_numpy = not _is_tensor(v)
+    d = int(v.shape[0])
+    ws = _workspace(d)
+    g = torch.as_tensor(np.ascontiguousarray(v, np.float64), device=ws.device) if as_numpy else v.contiguous()
+    ws.lanczos_begin(g, m, reorth)
+    finished = False
+    while not finished:
+        cur = ws.lanczos_current()
+        hv = A(cur.cpu().numpy()) if as_numpy else A(cur)
+        hv = torch.as_tensor(np.ascontiguousarray(hv, np.float64), device=ws.device) if not _is_tensor(hv) else hv
+        finished = ws.lanczos_feed(hv.contiguous())
+    Vrows, alphas, bet, info = ws.lanczos_view()
+    info_h = info.cpu().numpy()
+    m_eff, nvalid = int(info_h[0]), int(info_h[1])
+    V = Vrows[:m_eff].clone()
+    if nvalid < m_eff:
+        V[nvalid:] = 0.0            # breakdown at the last step: that column is never built (cubic.py:99)
+    V = V.t()
+    al = alphas[:m_eff].clone()
+    be = bet[1:m_eff].clone()
+    last_beta = float(bet[m].item())   # 4th return value of the reference: the last beta computed (cubic.py:111)
+    if as_numpy:
+        return np.ascontiguousarray(V.cpu().numpy()), al.cpu().numpy(), be.cpu().numpy(), last_beta
+    return V, al, be, last_beta
+
+
+# --------------------------------------------------------------------------------- the optimizer
+class Cubic_Krylov_LS(Optimizer):
+    """Krylov cubic regularized Newton method with line search.
+
+    Arguments:
+        reg_coef (float): estimate of the Hessian's Lipschitz constant (the regulariser M)
+        subspace_dim (int): dimension m of the Krylov subspace
+        solver_eps (float): accuracy of the Newton solve of the cubic sub-problem
+        beta (float): backtracking factor for M
+        reorth (bool): full re-orthogonalisation inside Lanczos (extension; default False = reference)
+    """
+
+    def __init__(self, reg_coef=None, subspace_dim=100, solver_eps=1e-8, beta=0.5, reorth=False, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.solver_it = 0
+        self.subspace_dim = subspace_dim
+        self.solver_eps = solver_eps
+        self.beta = beta
+        self.reorth = reorth
+        self.r0 = 0.1
+        self.value = None
+        self.reg_coef = self.loss.hessian_lipschitz if reg_coef is None else reg_coef
+        self.history = []       # per outer iteration: f, M, solver_it, m_eff, backtracks, r, hvps
+        self._dx = None
+
+    def step(self):
+        loss, eng = self.loss, self.loss.engine
+        if self.value is None:
+            self.value = loss.value(self.x)
+        else:
+            loss._forward(self.x)                       # no-op when the caches already belong to x
+        eng.gradient(keep_internal=True)                # loss.gradient(x)                       cubic.py:270
+        loss.calls["gradient"] += 1
+        eng.lanczos(self.subspace_dim, self.reorth)     # Lanczos(hess_vec_prod, grad, m)        cubic.py:273-275
+        loss.calls["hess_vec_prod"] += self.subspace_dim
+        M = self.reg_coef * self.beta                   # try a smaller M first                  cubic.py:286
+        tries = 0
+        while True:
+            eng.cubic(M, self.r0, self.solver_eps, 100)  # cubic_solver_root(...)                cubic.py:289-290
+            x_new = eng.trial_point(self.x)              # x + V @ s                             cubic.py:291
+            eng.set_x(x_new)                             # loss.value(x_new)                     cubic.py:292
+            value_new, decrease, r, its, status, m_eff, gnorm, hvps, dx = eng.step_record(True)
+            loss.calls["value"] += 1
+            loss.calls["forward"] += 1
+            if status == KCRN_E_NOTPD:
+                raise np.linalg.LinAlgError("T + r I is not positive definite in the cubic sub-problem")
+            loss.adopt_iterate(x_new)
+            loss._note_value(value_new, x_new)
+            if not (value_new > self.value - decrease and tries < 20):   # cubic.py:297
+                break
+            M = M / self.beta
+            tries += 1
+        self.x, self.reg_coef, self.value, self.r0 = x_new, M, value_new, r
+        self.solver_it += its
+        self._dx = dx
+        self.history.append(dict(f=value_new, M=M, solver_it=self.solver_it, m_eff=m_eff, backtracks=tries, r=r,
+                                 hvps=hvps, gnorm=gnorm, dx=dx))
+
+    def step_length(self):
+        return self._dx if self._dx is not None else super().step_length()
+
+    def init_run(self, x0, *args, **kwargs):
+        x0 = self.loss.to_device(x0)
+        super().init_run(x0, *args, **kwargs)
+        self.trace.solver_its = [0]
+        self.loss.reset()
+        self._dx = None
+
+    def update_trace(self):
+        super().update_trace()
+        self.trace.solver_its.append(self.solver_it)

@@ -1,0 +1,356 @@
+"""GPU parity: libkcrn (through the C ABI / the host mirror) against the CPU oracle and the golden
+fixtures written from the unmodified reference (tests/golden/make_golden.py).
+
+Bars (BASELINE.json north_star): index work bit-exact; value / gradient / HVP <= 1e-12 relative;
+trajectories <= 1e-8 relative per outer iteration where the reference's own rounding-noise envelope
+(reference vs row-reversed reference) allows it -- the envelope is asserted next to every trajectory.
+"""
+import numpy as np
+import pytest
+
+import functools
+
+from conftest import rel_err
+from kcrn_b200.synth import make_problem as _make_problem
+from oracle import oracle as O
+
+
+@functools.lru_cache(maxsize=None)
+def make_problem(name, seed=0):
+    return _make_problem(name, seed=seed)
+
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as t
+    if not t.cuda.is_available():
+        pytest.fail("gpu-marked test on a machine without CUDA")
+    return t
+
+
+def _engine(P, l2=0.0):
+    from kcrn_b200.engine import Engine
+    return Engine(P.indptr, P.indices, P.data, O.map_labels(P.b), (P.n, P.d), l2=l2)
+
+
+def _oracle(P, l2=0.0):
+    return O.OracleLogistic(P.indptr, P.indices, P.data, (P.n, P.d), P.b, l2=l2, threads=4)
+
+
+def _dev(torch, a):
+    return torch.as_tensor(np.ascontiguousarray(a, np.float64), device="cuda")
+
+
+# ------------------------------------------------------------------------------- K2: CSR -> CSC
+def test_csc_bitexact_duplicates_unsorted_empty(torch, golden):
+    from kcrn_b200.engine import Engine
+    g = golden("oracle_methods")
+    n, d = (int(v) for v in g["dup_shape"])
+    eng = Engine(g["dup_indptr"], g["dup_indices"], g["dup_data"], np.zeros(n), (n, d))
+    cp, ci, cx = eng.csc()
+    assert np.array_equal(cp, g["dup_csc_indptr"]) and np.array_equal(ci, g["dup_csc_indices"])
+    assert np.array_equal(cx, g["dup_csc_data"])
+    # the sweeps on the same awkward matrix (unsorted columns, duplicates, empty rows and columns)
+    eng.set_x(_dev(torch, g["dup_x"]))
+    assert rel_err(eng.cached_Ax().cpu().numpy(), g["dup_Ax"]) <= TOL
+
+
+@pytest.mark.parametrize("name,seed", [("tiny", 3), ("small", 3), ("w8a", 0), ("rcv1", 0)])
+def test_csc_bitexact_vs_oracle(torch, golden, name, seed):
+    P = make_problem(name, seed=seed)
+    eng = _engine(P)
+    cp, ci, cx = eng.csc()
+    op, oi, ox = O.csr_tocsc(P.n, P.d, P.indptr, P.indices, P.data)
+    assert np.array_equal(cp, op) and np.array_equal(ci, oi) and np.array_equal(cx, ox)
+    if name in ("tiny", "small"):
+        g = golden("oracle_methods")
+        assert np.array_equal(cp, g[f"{name}_csc_indptr"]) and np.array_equal(ci, g[f"{name}_csc_indices"])
+        assert np.array_equal(cx, g[f"{name}_csc_data"])
+
+
+def test_csc_wide_matrix_three_radix_passes(torch):
+    # d > 2^16 forces a third 8-bit digit; a dense column and many empty ones exercise the long-segment path
+    rng = np.random.default_rng(4)
+    n, d = 3000, 70_000
+    rows = []
+    for i in range(n):
+        c = np.unique(np.concatenate(([65_537], rng.integers(0, d, rng.integers(0, 12)))))
+        rows.append(c)
+    indptr = np.concatenate(([0], np.cumsum([len(r) for r in rows]))).astype(np.int32)
+    indices = np.concatenate(rows).astype(np.int32)
+    data = rng.standard_normal(indices.size)
+    from kcrn_b200.engine import Engine
+    eng = Engine(indptr, indices, data, (rng.random(n) > 0.5).astype(np.float64), (n, d))
+    cp, ci, cx = eng.csc()
+    op, oi, ox = O.csr_tocsc(n, d, indptr, indices, data)
+    assert np.array_equal(cp, op) and np.array_equal(ci, oi) and np.array_equal(cx, ox)
+    L = O.OracleLogistic(indptr, indices, data, (n, d), (rng.random(n) > 0.5).astype(np.float64))
+    x, v = rng.standard_normal(d), rng.standard_normal(d)
+    eng.set_x(_dev(torch, x))
+    # same labels are not needed for the HVP: it only depends on A, x, v
+    assert rel_err(eng.hvp(_dev(torch, v)).cpu().numpy(), L.hess_vec_prod(x, v)) <= TOL
+
+
+# ------------------------------------------------------------------------------- K1/K3/K4: oracle methods
+@pytest.mark.parametrize("tag,name", [("tiny", "tiny"), ("tiny_l2", "tiny"), ("small", "small")])
+def test_value_gradient_hvp_vs_reference_golden(torch, golden, tag, name):
+    g = golden("oracle_methods")
+    P = make_problem(name, seed=3)
+    assert P.fingerprint() == str(g[f"{tag}_fp"])
+    eng = _engine(P, float(g[f"{tag}_l2"]))
+    v = _dev(torch, g[f"{tag}_v"])
+    for xx, sfx in ((g[f"{tag}_x"], ""), (P.x0, "0"), (g[f"{tag}_xsat"], "_sat")):
+        eng.set_x(_dev(torch, xx))
+        if sfx == "":
+            assert rel_err(eng.cached_Ax().cpu().numpy(), g[f"{tag}_Ax"]) <= TOL
+        ref = float(g[f"{tag}_value{sfx}"])
+        assert abs(eng.value() - ref) <= TOL * abs(ref)
+        assert rel_err(eng.gradient().cpu().numpy(), g[f"{tag}_grad{sfx}"]) <= TOL
+        assert rel_err(eng.hvp(v).cpu().numpy(), g[f"{tag}_hvp{sfx}"]) <= TOL
+
+
+@pytest.mark.parametrize("name,l2", [("w8a", 0.0), ("rcv1", 0.0), ("rcv1", 1e-4), ("news20", 0.0)])
+def test_value_gradient_hvp_vs_oracle_full_size(torch, name, l2):
+    P = make_problem(name, seed=0)
+    eng, L = _engine(P, l2), _oracle(P, l2)
+    rng = np.random.default_rng(1)
+    for x in (P.x0, rng.standard_normal(P.d), 30.0 * rng.standard_normal(P.d)):
+        v = rng.standard_normal(P.d)
+        eng.set_x(_dev(torch, x))
+        fo = L.value(x)
+        assert abs(eng.value() - fo) <= TOL * abs(fo)
+        assert rel_err(eng.gradient().cpu().numpy(), L.gradient(x)) <= TOL
+        assert rel_err(eng.hvp(_dev(torch, v)).cpu().numpy(), L.hess_vec_prod(x, v)) <= TOL
+    # host-buffer entry points (numpy in / numpy out) give the same numbers
+    val, grad = eng.value_grad_host(P.x0)
+    assert abs(val - L.value(P.x0)) <= TOL * abs(val) and rel_err(grad, L.gradient(P.x0)) <= TOL
+    assert rel_err(eng.hvp_host(None, v), L.hess_vec_prod(P.x0, v)) <= TOL
+
+
+def test_hvp_is_linear_symmetric_and_run_to_run_identical(torch):
+    P = make_problem("rcv1", seed=0)
+    eng = _engine(P)
+    rng = np.random.default_rng(2)
+    u, v = _dev(torch, rng.standard_normal(P.d)), _dev(torch, rng.standard_normal(P.d))
+    eng.set_x(_dev(torch, P.x0))
+    Hu, Hv = eng.hvp(u), eng.hvp(v)
+    assert torch.equal(Hu, eng.hvp(u))                                   # deterministic reductions
+    assert rel_err((eng.hvp(2.0 * u - 3.0 * v)).cpu().numpy(), (2.0 * Hu - 3.0 * Hv).cpu().numpy()) <= 1e-13
+    a, b = float(u @ Hv), float(v @ Hu)
+    assert abs(a - b) <= 1e-12 * max(abs(a), abs(b))                     # H = A' D A is symmetric
+
+
+def test_long_segments_and_empty_rows(torch):
+    # one column present in every row (a 20k-entry CSC segment -> 79 pieces), rows of very uneven length,
+    # empty rows, a long row (> 256 entries -> multi-piece CSR segment)
+    rng = np.random.default_rng(6)
+    n, d = 20_000, 4_000
+    rows = []
+    for i in range(n):
+        if i % 97 == 0:
+            rows.append(np.zeros(0, np.int64))
+        elif i == 5:
+            rows.append(np.arange(0, 3000, 1))
+        else:
+            rows.append(np.unique(np.concatenate(([7], rng.integers(0, d, rng.integers(0, 40))))))
+    indptr = np.concatenate(([0], np.cumsum([len(r) for r in rows]))).astype(np.int32)
+    indices = np.concatenate(rows).astype(np.int32)
+    data = rng.standard_normal(indices.size)
+    b = (rng.random(n) > 0.5).astype(np.float64)
+    from kcrn_b200.engine import Engine
+    eng = Engine(indptr, indices, data, b, (n, d), l2=0.01)
+    L = O.OracleLogistic(indptr, indices, data, (n, d), b, l2=0.01)
+    x, v = 0.1 * rng.standard_normal(d), rng.standard_normal(d)
+    eng.set_x(_dev(torch, x))
+    fo = L.value(x)
+    assert abs(eng.value() - fo) <= TOL * abs(fo)
+    assert rel_err(eng.cached_Ax().cpu().numpy(), L.mat_vec_product(x)) <= TOL
+    assert rel_err(eng.gradient().cpu().numpy(), L.gradient(x)) <= TOL
+    assert rel_err(eng.hvp(_dev(torch, v)).cpu().numpy(), L.hess_vec_prod(x, v)) <= TOL
+
+
+def test_call_order_and_argument_errors(torch):
+    from kcrn_b200._lib import KcrnError
+    P = make_problem("tiny", seed=3)
+    eng = _engine(P)
+    with pytest.raises(KcrnError):
+        eng.gradient()                      # no current x yet
+    with pytest.raises(ValueError):
+        eng.set_x(torch.zeros(P.d + 1, dtype=torch.float64, device="cuda"))
+    with pytest.raises(ValueError):
+        _engine(P, l2=-1.0)
+
+
+# ------------------------------------------------------------------------------- K5: Lanczos
+@pytest.mark.parametrize("tag", ["m1", "m2", "m6", "m12", "brk_early_m8", "brk_last_m4", "brk_m3"])
+@pytest.mark.parametrize("as_numpy", [False, True])
+def test_lanczos_stepwise_vs_reference_golden(torch, golden, tag, as_numpy):
+    from optimizer.cubic import Lanczos
+    g = golden("lanczos")
+    S, g0, m = g[f"{tag}_S"], g[f"{tag}_g"], int(g[f"{tag}_m"])
+    if as_numpy:
+        V, al, be, beta = Lanczos(lambda v: S @ v, g0.copy(), m=m)
+    else:
+        Sd = _dev(torch, S)
+        V, al, be, beta = Lanczos(lambda v: Sd @ v, _dev(torch, g0), m=m)
+        V, al, be = V.cpu().numpy(), al.cpu().numpy(), be.cpu().numpy()
+    assert V.shape == g[f"{tag}_V"].shape and al.shape == g[f"{tag}_alphas"].shape
+    assert be.shape == g[f"{tag}_betas"].shape
+    # well-conditioned operator, small m: the recurrence is stable, so only summation order differs
+    assert rel_err(al, g[f"{tag}_alphas"]) <= 1e-10 and rel_err(V, g[f"{tag}_V"]) <= 1e-8
+    if be.size:
+        assert rel_err(be, g[f"{tag}_betas"]) <= 1e-8
+    assert abs(beta - float(g[f"{tag}_beta"])) <= 1e-8 * max(1.0, abs(float(g[f"{tag}_beta"])))
+
+
+@pytest.mark.parametrize("reorth", [False, True])
+def test_lanczos_fused_graph_vs_oracle(torch, reorth):
+    P = make_problem("small", seed=0)
+    eng, L = _engine(P), _oracle(P)
+    x = P.x0
+    eng.set_x(_dev(torch, x))
+    eng.gradient(keep_internal=True)
+    m = 6
+    eng.lanczos(m, reorth)
+    V, al, bet, info = eng.lanczos_view()
+    Vo, alo, beo, _ = O.lanczos(lambda v: L.hess_vec_prod(x, v), L.gradient(x), m, reorth=reorth)
+    info = info.cpu().numpy()
+    assert info[0] == alo.size and info[3] == m
+    assert abs(float(bet[0]) - np.linalg.norm(L.gradient(x))) <= TOL * float(bet[0])
+    assert rel_err(al.cpu().numpy(), alo) <= 1e-9
+    assert rel_err(bet[1:m].cpu().numpy(), beo) <= 1e-7
+    assert rel_err(V.cpu().numpy().T, Vo) <= 1e-6
+    if reorth:
+        G = (V @ V.T).cpu().numpy()
+        assert np.max(np.abs(G - np.eye(m))) <= 1e-12
+
+
+def test_lanczos_fused_equals_stepwise(torch):
+    from optimizer.cubic import Lanczos
+    P = make_problem("small", seed=0)
+    eng = _engine(P)
+    eng.set_x(_dev(torch, P.x0))
+    g = eng.gradient()
+    eng.lanczos(8, False, g=g)
+    V, al, bet, _ = eng.lanczos_view()
+    V2, al2, be2, _ = Lanczos(lambda v: eng.hvp(v), g, m=8)
+    # same kernels for the vector work; the fused sweep folds w and alpha into the CSC pass
+    assert rel_err(al.cpu().numpy(), al2.cpu().numpy()) <= 1e-10
+    assert rel_err(V.cpu().numpy().T, V2.cpu().numpy()) <= 1e-7
+
+
+# ------------------------------------------------------------------------------- K7: sub-problem
+def test_cubic_subproblem_vs_reference_golden(torch, golden):
+    from kcrn_b200.engine import cubic_tridiag
+    g = golden("cubic")
+    worst = 0.0
+    for i in range(int(g["count"])):
+        al, be = g[f"c{i}_alphas"], g[f"c{i}_betas"]
+        g0, M, r0, r_ref, dec_ref = g[f"c{i}_scal"]
+        s, r, dec, its, status = cubic_tridiag(al, be, g0, M, r0=r0, eps=1e-8, it_max=100)
+        assert status == 0
+        assert its == int(g[f"c{i}_its"]), f"case {i}: Newton iteration count"
+        assert abs(r - r_ref) <= 1e-9 * abs(r_ref) + 1e-16
+        assert abs(dec - dec_ref) <= 1e-9 * abs(dec_ref) + 1e-300
+        worst = max(worst, rel_err(s.cpu().numpy(), g[f"c{i}_s"]))
+    assert worst <= 1e-8   # tridiagonal Cholesky vs LAPACK dposv on T + r I with cond up to ~1e9
+
+
+def test_cubic_solver_root_surface(torch, golden):
+    from optimizer.cubic import cubic_solver_root
+    g = golden("cubic")
+    i = 40
+    al, be = g[f"c{i}_alphas"], g[f"c{i}_betas"]
+    g0, M, r0, r_ref, dec_ref = g[f"c{i}_scal"]
+    T = np.diag(al) + np.diag(be, 1) + np.diag(be, -1)
+    gv = np.zeros(al.size)
+    gv[0] = g0
+    s, its, r, dec = cubic_solver_root(gv, T, M, epsilon=1e-8, r0=r0)
+    assert isinstance(s, np.ndarray) and its == int(g[f"c{i}_its"]) and abs(r - r_ref) <= 1e-9 * abs(r_ref)
+    with pytest.raises(np.linalg.LinAlgError):
+        cubic_solver_root(np.array([1.0, 0.0]), np.array([[-5.0, 0.0], [0.0, 1.0]]), 1e-3, r0=0.1)
+
+
+# ------------------------------------------------------------------------------- K8 + the outer step
+def _make_opt(P, m, reorth=False, **kw):
+    from optimizer.cubic import Cubic_Krylov_LS
+    from optimizer.loss import LogisticRegression
+    loss = LogisticRegression(P.scipy_csr(), P.b, l1=0, l2=0, store_mat_vec_prod=True)
+    return Cubic_Krylov_LS(loss=loss, reg_coef=1e-3, subspace_dim=m, tolerance=1e-9, reorth=reorth, label="k",
+                           tqdm=False, **kw)
+
+
+@pytest.mark.parametrize("name,states", [("small", (0, 3, 8)), ("rcv1", (0, 6))])
+def test_teacher_forced_step_vs_reference(torch, golden, name, states):
+    """Restore the reference's state (x_k, value_k, M_k, r0_k), take ONE step, compare with the reference's."""
+    g = golden(f"traj_{name}")
+    P = make_problem(name, seed=0)
+    assert P.fingerprint() == str(g["fp"])
+    for k in states:
+        opt = _make_opt(P, 10)
+        val, M, r0 = g[f"m10_state{k}_scal"]
+        opt.reg_coef = float(M)
+        opt.init_run(g[f"m10_state{k}_x"])
+        opt.value = None if np.isnan(val) else float(val)
+        opt.r0 = float(r0)
+        opt.step()
+        f_ref, M_ref, r_ref, its_ref = g[f"m10_state{k}_next"]
+        assert opt.reg_coef == M_ref and opt.solver_it == int(its_ref)
+        assert abs(opt.value - f_ref) <= 1e-9 * abs(f_ref)
+        assert abs(opt.r0 - r_ref) <= 1e-6 * abs(r_ref)
+        x = opt.x.cpu().numpy()
+        if f"m10_state{k}_xnext" in g:
+            assert rel_err(x, g[f"m10_state{k}_xnext"]) <= 1e-7
+        else:
+            nx, ndx = g[f"m10_state{k}_xnext_norm"]
+            assert abs(np.linalg.norm(x) - nx) <= 1e-8 * nx
+            assert abs(np.linalg.norm(x - g[f"m10_state{k}_x"]) - ndx) <= 1e-6 * ndx
+
+
+@pytest.mark.parametrize("name,m,iters", [("small", 10, 30), ("w8a", 10, 30), ("rcv1", 10, 40), ("rcv1", 50, 40)])
+@pytest.mark.parametrize("reorth", [False, True])
+def test_free_running_trajectory_vs_reference(torch, golden, name, m, iters, reorth):
+    """f(x_k) of the engine vs the reference (reorth=False) / the reorth-patched reference (reorth=True),
+    with the reference's own self-noise envelope beside it."""
+    g = golden(f"traj_{name}")
+    P = make_problem(name, seed=0)
+    assert P.fingerprint() == str(g["fp"])
+    tag, rev = ("ro", "rorev") if reorth else ("ref", "refrev")
+    ref, refrev = g[f"m{m}_{tag}_f"], g[f"m{m}_{rev}_f"]
+    opt = _make_opt(P, m, reorth)
+    opt.run(P.x0, it_max=min(iters, len(ref)))
+    f = np.array([h["f"] for h in opt.history])
+    k = min(len(f), len(ref), len(refrev))
+    f, ref, refrev = f[:k], ref[:k], refrev[:k]
+    envelope = np.maximum.accumulate(np.abs(refrev - ref) / np.abs(ref))
+    dev = np.abs(f - ref) / np.abs(ref)
+    print(f"\n{name} m={m} reorth={reorth}: max dev {dev.max():.3e}, max envelope {envelope.max():.3e}, "
+          f"iterations with envelope <= 1e-8: {int((envelope <= 1e-8).sum())}/{k}")
+    assert np.all(dev <= np.maximum(1e-8, 10 * envelope)), (dev, envelope)
+    # the iteration stays a descent method and ends where the reference ends (loose, chaos-proof)
+    assert np.all(np.diff(f) <= 1e-12)
+    assert f[-1] <= ref[0]
+
+
+def test_drop_in_driver_flow_with_numpy_iterates(torch):
+    """What cubic_newton.py does (:58-68, :94-111, :140): numpy x0, run, compute_loss_of_iterates, f_opt."""
+    P = make_problem("small", seed=0)
+    opt = _make_opt(P, 10)
+    trace = opt.run(x0=P.x0, it_max=12)
+    opt.compute_loss_of_iterates()
+    assert len(trace.loss_vals) == len(trace.xs) == len(trace.its) == len(trace.ts)
+    assert trace.its[-1] == 12 and np.all(np.diff(trace.ts) > 0)
+    assert np.all(np.diff(trace.loss_vals) <= 1e-12)
+    assert abs(opt.loss.f_opt - trace.loss_vals.min()) <= 1e-15
+    assert trace.solver_its[-1] == opt.solver_it > 0
+    # numpy in -> numpy out on the oracle surface
+    L = _oracle(P)
+    x = P.x0 + 0.01
+    assert rel_err(opt.loss.gradient(x), L.gradient(x)) <= TOL
+    assert rel_err(opt.loss.hess_vec_prod(x, P.x0), L.hess_vec_prod(x, P.x0)) <= TOL
+    assert abs(opt.loss.value(x) - L.value(x)) <= TOL * abs(L.value(x))
