@@ -13,7 +13,10 @@
 // dposv's info > 0 (status = KCRN_E_NOTPD).
 //
 // m <= 512 and a handful of Newton iterations: the work is a chain of dependent divisions and square
-// roots, so one thread walks it while the rest of the warp only helps to load and store.
+// roots, so one thread walks it while the rest of the warp only helps to load and store.  The
+// divisions by the Cholesky diagonal use its precomputed IEEE reciprocal plus one fused correction of
+// the quotient (kcrn_device.cuh: quotient), which cuts the dependent chain of every solve step from a
+// full software division to three fused operations.
 #include "kcrn_device.cuh"
 #include "kcrn_internal.cuh"
 
@@ -24,6 +27,7 @@ namespace {
 struct Tri {
     double *a, *b;      // diagonal, off-diagonal
     double *l, *e;      // Cholesky factor: diagonal, sub-diagonal
+    double *li;         // 1 / l (IEEE), so that the solves divide with three fused operations
     double *s, *q;      // s_lam and (T + lam I)^-1 s_lam
     int m;
 };
@@ -36,9 +40,11 @@ __device__ bool factor(const Tri &t, double lam) {
         piv = __dsub_rn(piv, __dmul_rn(prev_e, prev_e));
         if (!(piv > 0.0)) return false;
         const double lj = sqrt(piv);
+        const double rj = 1.0 / lj;
         t.l[j] = lj;
+        t.li[j] = rj;
         if (j + 1 < t.m) {
-            prev_e = t.b[j] / lj;
+            prev_e = quotient(t.b[j], lj, rj);
             t.e[j] = prev_e;
         }
     }
@@ -51,14 +57,14 @@ __device__ void solve(const Tri &t, const double *rhs, double *out) {
     for (int j = 0; j < t.m; ++j) {
         double v = rhs[j];
         if (j > 0) v = __dsub_rn(v, __dmul_rn(t.e[j - 1], prev));
-        prev = v / t.l[j];
+        prev = quotient(v, t.l[j], t.li[j]);
         out[j] = prev;
     }
     prev = 0.0;
     for (int j = t.m - 1; j >= 0; --j) {
         double v = out[j];
         if (j + 1 < t.m) v = __dsub_rn(v, __dmul_rn(t.e[j], prev));
-        prev = v / t.l[j];
+        prev = quotient(v, t.l[j], t.li[j]);
         out[j] = prev;
     }
 }
@@ -75,7 +81,7 @@ __global__ void __launch_bounds__(32) cubic_kernel(const double *__restrict__ al
                                                    const double *__restrict__ gnorm_dev, double gnorm_arg,
                                                    double M, double r0, double eps, int it_max,
                                                    double *__restrict__ s_out, double *__restrict__ scal_out) {
-    __shared__ double sa[kMaxM], sb[kMaxM], sl[kMaxM], se[kMaxM], ss[kMaxM], sq[kMaxM];
+    __shared__ double sa[kMaxM], sb[kMaxM], sl[kMaxM], se[kMaxM], ss[kMaxM], sq[kMaxM], sli[kMaxM];
     const int m = info ? info[0] : m_arg;
     const double gnorm = gnorm_dev ? gnorm_dev[0] : gnorm_arg;
     for (int j = threadIdx.x; j < m; j += 32) {
@@ -86,7 +92,7 @@ __global__ void __launch_bounds__(32) cubic_kernel(const double *__restrict__ al
     double r = r0, dec = 0.0;
     int its = 0, status = 0;
     if (threadIdx.x == 0) {
-        Tri t{sa, sb, sl, se, ss, sq, m};
+        Tri t{sa, sb, sl, se, sli, ss, sq, m};
         double p0 = r0, p = r0;
         bool finished = false;
         for (int itr = 0; itr < it_max && !finished; ++itr) {

@@ -25,6 +25,13 @@ __device__ __forceinline__ double ld_stream(const double *p) {
     return v;
 }
 
+// 4-byte asynchronous copy global -> shared (LDGSTS); completion with cp_async_wait_all()
+__device__ __forceinline__ void cp_async_4(void *smem_dst, const void *gmem_src) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // x / b with b fixed for the whole kernel: rinv = 1/b (IEEE) is formed once per thread, then one
 // Newton correction on the quotient (Markstein).  Bit-identical for every reader of the same x, so
 // the stored basis vector and the values gathered on the fly agree exactly.

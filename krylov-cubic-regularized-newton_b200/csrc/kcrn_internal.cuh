@@ -30,7 +30,7 @@ void set_error(const char *fmt, ...);
 
 // ----------------------------------------------------------------------------- geometry
 constexpr int kTileNnz = 256;      // non-zeros staged per warp tile (8 per lane)
-constexpr int kTileSegs = 256;     // at most this many segments (rows / columns) per tile
+constexpr int kTileSegs = 128;     // at most this many segments (rows / columns) per tile
 constexpr int kSweepWarps = 8;     // warps per CTA of the sweep kernels
 constexpr int kSweepThreads = kSweepWarps * 32;
 constexpr int kVecThreads = 256;   // CTA size of the d-length vector kernels

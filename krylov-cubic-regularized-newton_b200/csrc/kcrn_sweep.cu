@@ -133,39 +133,57 @@ struct SweepParams {
     unsigned *red_ticket;
 };
 
+// Epilogue of one finished segment.  op0 / op1 are the pass's per-segment operands, already in registers:
+//   rows forward: label b            rows weighted: Hessian weight D
+//   cols scaled : u (l2 term)        cols Lanczos : v[col], v[col-1]
 template <int MODE>
-__device__ __forceinline__ void finish_segment(const SweepParams &P, int seg, double sum, int lseg,
-                                               const double *vcol, const double *vpre, double beta_prev,
-                                               bool subtract, double &acc) {
+__device__ __forceinline__ void finish_segment(const SweepParams &P, int seg, double sum, int lseg, double op0,
+                                               double op1, double beta_prev, bool subtract, double &acc) {
     if constexpr (MODE == kRowsForward) {
-        const double bi = P.b[seg];
         const double a = sigmoid(sum);
         P.Ax[seg] = sum;
         P.D[seg] = __dmul_rn(a, 1.0 - a);
-        P.resid[seg] = a - bi;
-        P.ell[seg] = __dsub_rn(__dmul_rn(1.0 - bi, sum), log_sigmoid(sum));
+        P.resid[seg] = a - op0;
+        P.ell[seg] = __dsub_rn(__dmul_rn(1.0 - op0, sum), log_sigmoid(sum));
     } else if constexpr (MODE == kRowsWeighted || MODE == kRowsLanczos) {
-        P.out[seg] = __dmul_rn(__ldg(P.D + seg), sum);
+        P.out[seg] = __dmul_rn(op0, sum);
     } else if constexpr (MODE == kColsRaw) {
         P.out[seg] = sum;
     } else if constexpr (MODE == kColsScaled) {
         double y = sum / P.n_samples;
-        if (P.add_l2) y = __dadd_rn(y, __dmul_rn(P.l2, __ldg(P.u + seg)));
+        if (P.add_l2) y = __dadd_rn(y, __dmul_rn(P.l2, op0));
         P.out[seg] = y;
     } else {  // kColsLanczos
-        const double vc = __ldg(vcol + seg);
-        double hv = __dadd_rn(sum / P.n_samples, __dmul_rn(P.l2, vc));
-        if (subtract) hv = __dsub_rn(hv, __dmul_rn(beta_prev, __ldg(vpre + seg)));
+        double hv = __dadd_rn(sum / P.n_samples, __dmul_rn(P.l2, op0));
+        if (subtract) hv = __dsub_rn(hv, __dmul_rn(beta_prev, op1));
         P.w[seg] = hv;
-        const double prod = __dmul_rn(vc, hv);
+        const double prod = __dmul_rn(op0, hv);
         if (lseg >= 0) P.longdot[lseg] = prod;  // long segments finish on whichever warp arrives last:
         else acc += prod;                       // keep their share out of the per-warp running sums
     }
 }
 
 template <int MODE>
+__device__ __forceinline__ void load_operands(const SweepParams &P, int seg, const double *vcol, const double *vpre,
+                                              bool subtract, double &op0, double &op1) {
+    op0 = 0.0;
+    op1 = 0.0;
+    if constexpr (MODE == kRowsForward) op0 = __ldg(P.b + seg);
+    if constexpr (MODE == kRowsWeighted || MODE == kRowsLanczos) op0 = __ldg(P.D + seg);
+    if constexpr (MODE == kColsScaled) { if (P.add_l2) op0 = __ldg(P.u + seg); }
+    if constexpr (MODE == kColsLanczos) {
+        op0 = __ldg(vcol + seg);
+        if (subtract) op1 = __ldg(vpre + seg);
+    }
+}
+
+__host__ __device__ constexpr int kOperands(int mode) { return mode == kColsRaw ? 0 : (mode == kColsLanczos ? 2 : 1); }
+
+template <int MODE>
 __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepParams P) {
-    __shared__ double sprod[kSweepWarps][kTileNnz];
+    __shared__ double sprod[kSweepWarps][kTileNnz];       // products of the tile
+    __shared__ double ssum[kSweepWarps][kTileSegs];       // per-segment sums of the tile
+    __shared__ int sptr[kSweepWarps][kTileSegs + 8];      // segment pointers of the tile
     __shared__ double sred[kSweepWarps];
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -185,10 +203,6 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
             src = col == 0 ? P.g : P.wp;
             beta = P.bet[col];
             rinv = 1.0 / beta;
-            double *vout = P.V + (size_t)col * P.d;
-            for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < P.d;
-                 c += (int64_t)gridDim.x * blockDim.x)
-                vout[c] = quotient(__ldg(src + c), beta, rinv);
         }
     }
     if constexpr (MODE == kColsLanczos) {
@@ -205,12 +219,15 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
     }
 
     double acc = 0.0;
+    double *sp = sprod[warp], *sm = ssum[warp];
+    int *sq = sptr[warp];
     const int gw = blockIdx.x * kSweepWarps + warp, tw = gridDim.x * kSweepWarps;
     for (int tile = gw; tile < P.ntiles; tile += tw) {
         const int4 td = __ldg(P.tiles + tile);
         const int seg0 = td.x, k0 = td.y, z = td.z, nk = td.w & 0xffff, logG = td.w >> 16;
         const int32_t *ip = P.idx + k0;
         const double *vp = P.val + k0;
+        // everything that only depends on the descriptor is requested before anything is consumed
         int ci[8];
         double av[8];
 #pragma unroll
@@ -218,6 +235,18 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
             const int i = r * 32 + lane;
             ci[r] = i < nk ? ld_stream(ip + i) : -1;
             av[r] = i < nk ? ld_stream(vp + i) : 0.0;
+        }
+        int4 lt = make_int4(0, 1, 0, 0);
+        constexpr int SR = kTileSegs / 32;   // segment rounds per lane
+        if (z < 0) {
+            lt = __ldg(P.longtab + (-z - 1));
+        } else {
+            // segment pointers go straight to shared memory (cp.async: no registers held while in flight)
+#pragma unroll
+            for (int r = 0; r < SR + 1; ++r) {
+                const int i = r * 32 + lane;
+                if (i <= z) cp_async_4(sq + i, P.ptr + seg0 + i);
+            }
         }
         double p[8];
 #pragma unroll
@@ -228,10 +257,12 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
             p[r] = av[r] * xv;
         }
         if (z < 0) {
+            // one 256-entry piece of a long segment: tree-reduce, publish, the last piece to arrive finishes
+            double op0, op1;
+            load_operands<MODE>(P, seg0, vcol, vpre, subtract, op0, op1);
             double s = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
             s = warp_sum(s);
             const int lseg = -z - 1;
-            const int4 lt = __ldg(P.longtab + lseg);
             const int slot = lt.x + ((k0 - lt.z) >> 8);
             int last = 0;
             if (lane == 0) {
@@ -245,32 +276,60 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
                 double tot = 0.0;
                 for (int i = lane; i < lt.y; i += 32) tot += __ldcg(P.partial + lt.x + i);
                 tot = warp_sum(tot);
-                if (lane == 0) finish_segment<MODE>(P, seg0, tot, lseg, vcol, vpre, beta_prev, subtract, acc);
+                if (lane == 0) finish_segment<MODE>(P, seg0, tot, lseg, op0, op1, beta_prev, subtract, acc);
             }
         } else {
-            double *sp = sprod[warp];
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 const int i = r * 32 + lane;
                 if (i < nk) sp[i] = p[r];
             }
+            // operands of the epilogue: requested now, consumed after the shared-memory reduction
+            constexpr int NOP = kOperands(MODE);
+            double o0[NOP > 0 ? SR : 1], o1[NOP > 1 ? SR : 1];
+#pragma unroll
+            for (int r = 0; r < SR; ++r) {
+                const int sg = r * 32 + lane;
+                if (sg < z) {
+                    double a0, a1;
+                    load_operands<MODE>(P, seg0 + sg, vcol, vpre, subtract, a0, a1);
+                    if constexpr (NOP > 0) o0[r] = a0;
+                    if constexpr (NOP > 1) o1[r] = a1;
+                }
+            }
+            cp_async_wait_all();
             __syncwarp();
+            // phase A: every group of G lanes sums one segment from shared memory
             const int G = 1 << logG, groups = 32 >> logG, gid = lane >> logG, gl = lane & (G - 1);
             for (int sb = 0; sb < z; sb += groups) {
                 const int sg = sb + gid;
-                const bool active = sg < z;
                 int a = 0, b = 0;
-                if (active) {
-                    a = __ldg(P.ptr + seg0 + sg) - k0;
-                    b = __ldg(P.ptr + seg0 + sg + 1) - k0;
-                }
+                if (sg < z) { a = sq[sg] - k0; b = sq[sg + 1] - k0; }
                 double sum = 0.0;
                 for (int i = a + gl; i < b; i += G) sum += sp[i];
                 for (int o = G >> 1; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                if (active && gl == 0)
-                    finish_segment<MODE>(P, seg0 + sg, sum, -1, vcol, vpre, beta_prev, subtract, acc);
+                if (sg < z && gl == 0) sm[sg] = sum;
             }
             __syncwarp();
+            // phase B: coalesced epilogue over the segments of the tile
+#pragma unroll
+            for (int r = 0; r < SR; ++r) {
+                const int sg = r * 32 + lane;
+                if (sg < z)
+                    finish_segment<MODE>(P, seg0 + sg, sm[sg], -1, NOP > 0 ? o0[r] : 0.0, NOP > 1 ? o1[r] : 0.0,
+                                         beta_prev, subtract, acc);
+            }
+            __syncwarp();
+        }
+    }
+
+    if constexpr (MODE == kRowsLanczos) {
+        // side job: store the normalised vector as basis column `col` (the sweep above divided on the fly)
+        if (!P.ctl->redo) {
+            double *vout = P.V + (size_t)col * P.d;
+            for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < P.d;
+                 c += (int64_t)gridDim.x * blockDim.x)
+                vout[c] = quotient(__ldg(src + c), beta, rinv);
         }
     }
 

@@ -1,0 +1,75 @@
+"""Worker for the row-sharded (multi-GPU) parity check; launched by torchrun, one rank per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 \
+        tests/mgpu_worker.py
+
+Every rank holds a contiguous, nnz-balanced row block of ONE problem; results must match the CPU oracle on
+the whole matrix (value / gradient / HVP <= 1e-12) and the reference trajectory prefix (<= 1e-8)."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import conftest  # noqa: E402,F401  (import paths)
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from kcrn_b200.dist import join_communicator, shard_rows  # noqa: E402
+from kcrn_b200.synth import make_problem  # noqa: E402
+from optimizer.cubic import Cubic_Krylov_LS  # noqa: E402
+from optimizer.loss import LogisticRegression  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    name = sys.argv[1] if len(sys.argv) > 1 else "rcv1"
+    P = make_problem(name, seed=0)
+    S = shard_rows(P, rank, world)
+    loss = LogisticRegression(S.scipy_csr(), P_labels(S), l1=0, l2=0, store_mat_vec_prod=True, n_global=P.n)
+    join_communicator(loss.engine, rank, world)
+    L = O.OracleLogistic(P.indptr, P.indices, P.data, (P.n, P.d), P.b, threads=4)
+    rng = np.random.default_rng(5)
+    x, v = rng.standard_normal(P.d), rng.standard_normal(P.d)
+    xd, vd = torch.as_tensor(x, device="cuda"), torch.as_tensor(v, device="cuda")
+    errs = {
+        "value": abs(loss.value(xd) - L.value(x)) / abs(L.value(x)),
+        "gradient": rel(loss.gradient(xd).cpu().numpy(), L.gradient(x)),
+        "hvp": rel(loss.hess_vec_prod(xd, vd).cpu().numpy(), L.hess_vec_prod(x, v)),
+    }
+    # replicas must hold identical bits after the allreduce
+    h = loss.hess_vec_prod(xd, vd)
+    ref = h.clone()
+    dist.broadcast(ref, 0)
+    errs["replica_bits_equal"] = 0.0 if torch.equal(ref, h) else 1.0
+    opt = Cubic_Krylov_LS(loss=loss, reg_coef=1e-3, subspace_dim=10, tolerance=1e-9, label="mg", tqdm=False)
+    opt.run(P.x0, it_max=8)
+    g = np.load(os.path.join(HERE, "golden", f"traj_{name}.npz"))
+    f = np.array([hh["f"] for hh in opt.history])
+    errs["trajectory_prefix"] = float(np.max(np.abs(f - g["m10_ref_f"][:len(f)]) / np.abs(g["m10_ref_f"][:len(f)])))
+    ok = (errs["value"] <= 1e-12 and errs["gradient"] <= 1e-12 and errs["hvp"] <= 1e-12
+          and errs["replica_bits_equal"] == 0.0 and errs["trajectory_prefix"] <= 1e-8)
+    cnt = loss.engine.counters()
+    print(f"rank {rank}/{world}: rows {S.n} nnz {S.nnz} errs {errs} allreduces {cnt['allreduces']} -> {'OK' if ok else 'FAIL'}",
+          flush=True)
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(int(flag.item() != 0))
+
+
+def P_labels(S):
+    return S.b
+
+
+if __name__ == "__main__":
+    main()
