@@ -302,6 +302,7 @@ def main():
                                           f"(oracle/, OpenMP sweeps)"}
     if rank == 0:
         print(json.dumps(line), flush=True)
+    eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

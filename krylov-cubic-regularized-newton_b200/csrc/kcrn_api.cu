@@ -184,8 +184,11 @@ int kcrn_create(kcrn_handle *out, int64_t n_rows, int64_t n_cols, int64_t nnz, c
 int kcrn_destroy(kcrn_handle h) {
     if (!h) return KCRN_OK;
     cudaStreamSynchronize(h->stream);
-    nccl_destroy(h);
+    // captured graphs hold NCCL work: they must be gone before the communicator is torn down
     for (auto &ge : h->graphs) cudaGraphExecDestroy(ge.exec);
+    h->graphs.clear();
+    cudaDeviceSynchronize();
+    nccl_destroy(h);
     free_segmat(&h->csr);
     free_segmat(&h->csc);
     double *bufs[] = {h->b, h->x_cur, h->Ax, h->D, h->resid, h->ell, h->t, h->ypart, h->V, h->w, h->wp, h->g,

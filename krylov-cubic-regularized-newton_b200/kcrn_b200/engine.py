@@ -5,7 +5,9 @@ only: every number is produced by the CUDA kernels behind the C ABI (include/kcr
 """
 from __future__ import annotations
 
+import atexit
 import ctypes
+import weakref
 from ctypes import byref, c_double, c_int, c_int64, c_void_p
 
 import numpy as np
@@ -14,6 +16,19 @@ from . import _lib
 from ._lib import check
 
 MAX_SUBSPACE = 512
+
+
+_live = weakref.WeakSet()
+
+
+@atexit.register
+def _close_all():
+    """Release every handle (graphs, NCCL communicator, device memory) while the interpreter is still whole."""
+    for eng in list(_live):
+        try:
+            eng.close()
+        except Exception:
+            pass
 
 
 class _DeviceView:
@@ -72,6 +87,7 @@ class Engine:
         self._rec = (c_double * 12)()
         self._cnt = (c_int64 * 8)()
         self.world = 1
+        _live.add(self)
 
     # ------------------------------------------------------------------ plumbing
     def close(self):

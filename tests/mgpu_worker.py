@@ -28,6 +28,8 @@ def rel(a, b):
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(75, exit=True)      # a hang prints where, instead of eating the box time
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
@@ -37,6 +39,7 @@ def main():
     loss = LogisticRegression(S.scipy_csr(), P_labels(S), l1=0, l2=0, store_mat_vec_prod=True, n_global=P.n)
     join_communicator(loss.engine, rank, world)
     L = O.OracleLogistic(P.indptr, P.indices, P.data, (P.n, P.d), P.b, threads=4)
+    print(f"rank {rank}: shard ready, communicator joined", flush=True)
     rng = np.random.default_rng(5)
     x, v = rng.standard_normal(P.d), rng.standard_normal(P.d)
     xd, vd = torch.as_tensor(x, device="cuda"), torch.as_tensor(v, device="cuda")
@@ -45,6 +48,7 @@ def main():
         "gradient": rel(loss.gradient(xd).cpu().numpy(), L.gradient(x)),
         "hvp": rel(loss.hess_vec_prod(xd, vd).cpu().numpy(), L.hess_vec_prod(x, v)),
     }
+    print(f"rank {rank}: oracle methods {errs}", flush=True)
     # replicas must hold identical bits after the allreduce
     h = loss.hess_vec_prod(xd, vd)
     ref = h.clone()
@@ -62,6 +66,7 @@ def main():
           flush=True)
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
+    loss.engine.close()            # graphs and the NCCL communicator go first
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(int(flag.item() != 0))
