@@ -45,7 +45,8 @@ def cubic_solver_root(g, H, M, it_max=100, epsilon=1e-8, r0=0.1):
     Hh = np.asarray(Hh, np.float64).reshape(m, m)
     off = Hh - np.diag(np.diag(Hh)) - np.diag(np.diag(Hh, 1), 1) - np.diag(np.diag(Hh, -1), -1)
     if np.any(off != 0.0) or np.any(g_host[1:] != 0.0) or not np.array_equal(np.diag(Hh, 1), np.diag(Hh, -1)):
-        raise NotImplementedError("cubic_solver_root on the device needs a symmetric tridiagonal H and g = c*e1")
+        from optimizer.dense import cubic_solver_dense          # SSCN / full-CRN form: dense H, general g
+        return cubic_solver_dense(g, Hh if not _is_tensor(H) else H, M, it_max=it_max, epsilon=epsilon, r0=r0)
     s, r, dec, its, status = _engine.cubic_tridiag(np.diag(Hh).copy(), np.diag(Hh, 1).copy(), g_host[0], M,
                                                    r0=r0, eps=epsilon, it_max=it_max)
     if status == KCRN_E_NOTPD:
@@ -172,6 +173,109 @@ class Cubic_Krylov_LS(Optimizer):
         self.trace.solver_its = [0]
         self.loss.reset()
         self._dx = None
+
+    def update_trace(self):
+        super().update_trace()
+        self.trace.solver_its.append(self.solver_it)
+
+
+# --------------------------------------------------------------------------------- config-4 baselines
+class Cubic_LS(Optimizer):
+    """Cubic regularized Newton with line search on the full space (reference cubic.py:115-235).
+
+    ``cubic_solver="full"``: dense Hessian A' D A / n formed on the FP64 tensor cores (kcrn_hessian_dense) and the
+    dense secular-equation solve of ``optimizer.dense``.  The matrix-free "CG" variant of the reference is not
+    part of this round."""
+
+    def __init__(self, reg_coef=None, cubic_solver="CG", solver_it_max=100, solver_eps=1e-8, beta=0.5, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if cubic_solver != "full":
+            raise NotImplementedError('only cubic_solver="full" is built on the device in this round')
+        self.solver_it = 0
+        self.solver_it_max = solver_it_max
+        self.solver_eps = solver_eps
+        self.beta = beta
+        self.r0 = 0.1
+        self.value = None
+        self.reg_coef = self.loss.hessian_lipschitz if reg_coef is None else reg_coef
+
+    def step(self):
+        from optimizer.dense import cubic_solver_dense
+
+        loss = self.loss
+        if self.value is None:
+            self.value = loss.value(self.x)
+        self.grad = loss.gradient(self.x)
+        self.hess = loss.hessian(self.x)
+        if loss.norm(self.grad) < self.tolerance:        # cubic.py:201-202
+            return
+        M = self.reg_coef * self.beta
+        while True:
+            s, its, r, decrease = cubic_solver_dense(self.grad, self.hess, M, self.solver_it_max, self.solver_eps,
+                                                     r0=self.r0)
+            x_new = self.x + s
+            value_new = loss.value(x_new)
+            if not value_new > self.value - decrease:    # unbounded backtracking, cubic.py:214
+                break
+            M = M / self.beta
+        self.x, self.reg_coef, self.value, self.r0 = x_new, M, value_new, r
+        self.solver_it += its
+
+    def init_run(self, x0, *args, **kwargs):
+        super().init_run(self.loss.to_device(x0), *args, **kwargs)
+        self.trace.solver_its = [0]
+        self.loss.reset()
+
+    def update_trace(self):
+        super().update_trace()
+        self.trace.solver_its.append(self.solver_it)
+
+
+class SSCN(Optimizer):
+    """Stochastic subspace cubic Newton, coordinate version (reference cubic.py:321-408): a random coordinate
+    block I per step (same numpy Generator stream as the reference), block gradient / Hessian from the device,
+    dense m x m cubic solve, incremental update of the cached A x."""
+
+    def __init__(self, reg_coef=None, subspace_dim=100, solver_eps=1e-8, beta=0.5, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.solver_it = 0
+        self.subspace_dim = subspace_dim
+        self.solver_eps = solver_eps
+        self.beta = beta
+        self.r0 = 0.1
+        self.value = None
+        self.tolerance = 0                                # cubic.py:345
+        self.reg_coef = self.loss.hessian_lipschitz if reg_coef is None else reg_coef
+
+    def step(self):
+        from optimizer.dense import cubic_solver_dense
+
+        loss = self.loss
+        if self.value is None:
+            self.value = loss.value(self.x)
+        I = self.rng.choice(self.dim, size=self.subspace_dim, replace=False)
+        I_dev = loss._index_tensor(I)
+        self.grad = loss.partial_gradient(self.x, I)
+        self.hess = loss.partial_hessian(self.x, I)
+        M = max(self.reg_coef * self.beta, np.finfo(float).eps)
+        x_new = self.x.clone()
+        Ax = loss._mat_vec_prod.clone()
+        eps = np.finfo(float).eps
+        while True:
+            s, its, r, decrease = cubic_solver_dense(self.grad, self.hess, M, r0=self.r0, epsilon=eps)
+            x_new[I_dev] = self.x[I_dev] + s
+            loss.update_mat_vec_product(Ax, s, I)
+            value_new = loss.value(x_new)
+            if not value_new > self.value - decrease:
+                break
+            M = M / self.beta
+        self.x, self.reg_coef, self.value, self.r0 = x_new, M, value_new, r
+        self.solver_it += its
+
+    def init_run(self, x0, *args, **kwargs):
+        super().init_run(self.loss.to_device(x0), *args, **kwargs)
+        self.trace.solver_its = [0]
+        self.loss.reset()
 
     def update_trace(self):
         super().update_trace()

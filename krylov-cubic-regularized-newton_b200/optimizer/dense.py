@@ -1,0 +1,66 @@
+"""Dense cubic sub-problem for the config-4 baselines (SSCN blocks, full-Hessian CRN).
+
+Same Newton iteration on the secular equation as ``cubic_solver_root`` (reference optimizer/cubic.py:40-75,
+scipy's scalar ``newton`` loop, scipy/optimize/_zeros_py.py:319-358), with the dense SPD solves
+(``scipy.linalg.solve(assume_a='pos')`` = LAPACK dposv in the reference) done by cuSOLVER's Cholesky through
+torch.linalg on the device.  This is library code on a baseline-only path: the hot path's sub-problem is the
+tridiagonal single-CTA kernel (csrc/kcrn_cubic.cu); what config 4 accelerates by hand is the formation of
+A' D A (csrc/kcrn_config4.cu).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def cubic_solver_dense(g, H, M, it_max=100, epsilon=1e-8, r0=0.1):
+    """argmin_s <g, s> + 1/2 <s, H s> + M/3 |s|^3 for a dense symmetric H (CUDA tensors or numpy).
+    Returns (s, newton_iterations, r, model_decrease); s is a CUDA tensor if g was one."""
+    import torch
+
+    as_numpy = not hasattr(g, "data_ptr")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    gt = torch.as_tensor(np.ascontiguousarray(g, np.float64), device=dev) if as_numpy else g.to(torch.float64)
+    Ht = torch.as_tensor(np.ascontiguousarray(H, np.float64), device=dev) if not hasattr(H, "data_ptr") else H
+    m = gt.numel()
+    Ht = Ht.reshape(m, m)
+    diag0 = Ht.diagonal().clone()
+    work = Ht if not as_numpy and Ht.numel() > (1 << 26) else Ht.clone()   # huge H: shift its diagonal in place
+
+    def factor(lam):
+        work.diagonal().copy_(diag0 + lam)
+        L, info = torch.linalg.cholesky_ex(work)
+        if int(info.item()) != 0:
+            if work is Ht:
+                work.diagonal().copy_(diag0)
+            raise np.linalg.LinAlgError("H + r I is not positive definite")
+        return L
+
+    def solve(L, rhs):
+        return torch.cholesky_solve(rhs[:, None], L)[:, 0]
+
+    M = float(M)
+    p0 = p = float(r0)
+    its, done = it_max, False
+    for itr in range(it_max):
+        L = factor(p0)
+        s = -solve(L, gt)
+        fval = p0 ** 2 - M ** 2 * float(s.norm().item()) ** 2
+        if fval == 0:
+            p, its, done = p0, itr, True
+            break
+        fder = 2 * p0 + 2 * M ** 2 * float((s @ solve(L, s)).item())
+        if fder == 0:
+            p, its, done = p0, itr + 1, True
+            break
+        p = p0 - fval / fder
+        if abs(p - p0) <= epsilon:
+            its, done = itr + 1, True
+            break
+        p0 = p
+    r = p
+    s = -solve(factor(r), gt)
+    if work is Ht:
+        work.diagonal().copy_(diag0)
+    ns = float(s.norm().item())
+    dec = r / 2 * ns ** 2 - M / 3 * ns ** 3 - float((gt @ s).item()) / 2
+    return (s.cpu().numpy() if as_numpy else s), its, r, dec

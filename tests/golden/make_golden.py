@@ -17,7 +17,15 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-sys.path.insert(0, os.path.join(ROOT, "krylov-cubic-regularized-newton_b200"))
+# only the synthetic generator comes from this repository (loaded by file path: the package directory also
+# holds OUR ``optimizer`` mirror, which must not shadow the reference's ``optimizer`` package imported below)
+import importlib.util  # noqa: E402
+
+_spec = importlib.util.spec_from_file_location(
+    "kcrn_synth", os.path.join(ROOT, "krylov-cubic-regularized-newton_b200", "kcrn_b200", "synth.py"))
+_synth = importlib.util.module_from_spec(_spec)
+sys.modules["kcrn_synth"] = _synth
+_spec.loader.exec_module(_synth)
 
 _mpl, _plt = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
 _mpl.pyplot = _plt
@@ -29,7 +37,7 @@ import optimizer.cubic as ref_cubic  # noqa: E402  (the reference's package)
 from optimizer.loss import LogisticRegression, logsig  # noqa: E402
 import scipy.special  # noqa: E402
 
-from kcrn_b200.synth import make_problem  # noqa: E402
+make_problem = _synth.make_problem
 
 assert ref_cubic.__file__.startswith("/root/reference"), ref_cubic.__file__
 warnings.filterwarnings("ignore")
@@ -275,8 +283,43 @@ def trajectories():
         save(f"traj_{name}", **out)
 
 
+# ------------------------------------------------------------------ 6. config-4 baselines (cubic.py:115-235, 321-408)
+def config4():
+    """SSCN (m = 10, 50) and full-Hessian CRN on the 'small' problem, plus the same runs on row-reversed data
+    (the reference's own rounding-noise envelope)."""
+    P = make_problem("small", seed=0)
+    out = {"fp": np.array(P.fingerprint())}
+
+    def run(kind, m, iters, reverse):
+        A, b = P.scipy_csr(), P.b
+        if reverse:
+            A, b = A[::-1].tocsr(), b[::-1].copy()
+        if kind == "sscn":
+            loss = LogisticRegression(A.tocsc(), b, l1=0, l2=0, store_mat_vec_prod=True)
+            opt = ref_cubic.SSCN(loss=loss, reg_coef=1e-3, subspace_dim=m, tolerance=1e-9, label="s")
+        else:
+            loss = LogisticRegression(A, b, l1=0, l2=0, store_mat_vec_prod=True)
+            opt = ref_cubic.Cubic_LS(loss=loss, reg_coef=1e-3, cubic_solver="full", tolerance=1e-8, label="c")
+        opt.rng = np.random.default_rng(42)
+        opt.init_run(P.x0)
+        f, M, sit = [], [], []
+        for _ in range(iters):
+            opt.step()
+            f.append(opt.value); M.append(opt.reg_coef); sit.append(opt.solver_it)
+        return np.array(f), np.array(M), np.array(sit, dtype=np.int64), opt.x.copy()
+
+    for kind, m, iters in (("sscn", 10, 40), ("sscn", 50, 40), ("full", 0, 12)):
+        tag = f"{kind}{m}" if kind == "sscn" else "full"
+        f, M, sit, x = run(kind, m, iters, False)
+        fr, _, _, _ = run(kind, m, iters, True)
+        out.update({f"{tag}_f": f, f"{tag}_M": M, f"{tag}_solver_it": sit, f"{tag}_x_final": x, f"{tag}_rev_f": fr})
+        print(tag, "f[-1] = %.6e" % f[-1], "self-noise max rel = %.2e" % np.max(np.abs(f - fr) / np.abs(f)))
+    save("traj_config4", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["prims", "oracle_methods", "lanczos", "cubic", "traj"]
+    which = sys.argv[1:] or ["prims", "oracle_methods", "lanczos", "cubic", "traj", "config4"]
+    if "config4" in which: config4()
     if "prims" in which: prims()
     if "oracle_methods" in which: oracle_methods()
     if "lanczos" in which: lanczos_cases()
