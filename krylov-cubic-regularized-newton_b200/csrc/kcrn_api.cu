@@ -1,6 +1,7 @@
 // C ABI of libkcrn.so (see include/kcrn.h for the contract of every entry point).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -135,8 +136,9 @@ int kcrn_create(kcrn_handle *out, int64_t n_rows, int64_t n_cols, int64_t nnz, c
         KCRN_TRY(upload(&h->b, labels01, (size_t)n_rows, arrays_on_device, s));
         h->counters[6] += arrays_on_device ? 0 : (int64_t)(sizeof(int32_t) * (n_rows + 1 + nnz) + sizeof(double) * (nnz + n_rows));
         KCRN_TRY(build_csc(h->csr, n_cols, &h->csc, s));
-        KCRN_TRY(build_tiles(&h->csr, s));
-        KCRN_TRY(build_tiles(&h->csc, s));
+        KCRN_TRY(build_tiles(&h->csr, n_cols, s));   // row sweeps gather a d-vector
+        KCRN_TRY(build_tiles(&h->csc, n_rows, s));   // column sweeps gather an n-vector
+        h->allow_pdl = getenv("KCRN_PDL") != nullptr;   // opt-in: measured slower inside the Lanczos graph
         const size_t n = (size_t)n_rows, d = (size_t)n_cols;
         KCRN_CUDA(cudaMalloc(&h->x_cur, sizeof(double) * d));
         KCRN_CUDA(cudaMalloc(&h->Ax, sizeof(double) * n));
@@ -334,11 +336,13 @@ int kcrn_lanczos(kcrn_handle h, const double *g_dev, int m, int reorth) {
         int64_t saved[8];
         memcpy(saved, h->counters, sizeof(saved));
         h->stream = cap;
+        h->pdl = h->allow_pdl;
         cudaGraph_t graph = nullptr;
         cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed);
         int rc = e == cudaSuccess ? enqueue_lanczos(h, m, reorth) : KCRN_E_CUDA;
         cudaError_t e2 = cudaStreamEndCapture(cap, &graph);
         h->stream = user;
+        h->pdl = false;
         for (int i = 0; i < 8; ++i) h->graph_delta[i] = h->counters[i] - saved[i];
         memcpy(h->counters, saved, sizeof(saved));
         if (e != cudaSuccess || e2 != cudaSuccess || rc != KCRN_OK || !graph) {

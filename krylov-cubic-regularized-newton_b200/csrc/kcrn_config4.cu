@@ -23,10 +23,6 @@ constexpr int BM = 128, BN = 128, BK = 16, LDT = BM + 4, STAGES = 3;
 constexpr int GEMM_THREADS = 256;
 constexpr size_t GEMM_SMEM = (size_t)STAGES * 2 * BK * LDT * sizeof(double);
 
-__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src) {
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }

@@ -30,6 +30,11 @@ __device__ __forceinline__ void cp_async_4(void *smem_dst, const void *gmem_src)
     const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gmem_src) : "memory");
 }
+// 16-byte variant, cached in L2 only (.cg)
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // x / b with b fixed for the whole kernel: rinv = 1/b (IEEE) is formed once per thread, then one
@@ -40,6 +45,14 @@ __device__ __forceinline__ double quotient(double x, double b, double rinv) {
     const double r = fma(-b, q, x);
     return fma(r, rinv, q);
 }
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialisation attribute may
+// become resident while its predecessor in the stream is still running.  pdl_wait() blocks until that
+// predecessor has completed and its writes are visible (no-op for ordinary launches); pdl_trigger() lets the
+// successor start.  Every kernel of this library waits before it touches anything a previous kernel wrote and
+// only triggers afterwards, so completion stays transitive along the stream.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // scipy.special.expit as the reference calls it (optimizer/loss.py:225,296): 1 / (1 + exp(-x))
 __device__ __forceinline__ double sigmoid(double x) { return 1.0 / (1.0 + exp(-x)); }

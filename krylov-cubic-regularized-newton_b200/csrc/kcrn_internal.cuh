@@ -28,9 +28,28 @@ void set_error(const char *fmt, ...);
     } while (0)
 #define KCRN_LAUNCH_CHECK() KCRN_CUDA(cudaGetLastError())
 
+// Kernel launch with (pdl = true) or without the programmatic-dependent-launch attribute.
+template <class... KArgs, class... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ----------------------------------------------------------------------------- geometry
-constexpr int kTileNnz = 256;      // non-zeros staged per warp tile (8 per lane)
-constexpr int kTileSegs = 128;     // at most this many segments (rows / columns) per tile
+constexpr int kTileNnz = 2048;     // non-zeros per CTA tile (8 per thread)
+constexpr int kTileSegs = 1024;    // at most this many segments (rows / columns) per stream tile
+constexpr int kShortSeg = 512;     // longest segment that shares a stream tile with others
+constexpr int kSingleTag = 15;     // descriptor tag of a tile that holds one medium segment
 constexpr int kSweepWarps = 8;     // warps per CTA of the sweep kernels
 constexpr int kSweepThreads = kSweepWarps * 32;
 constexpr int kVecThreads = 256;   // CTA size of the d-length vector kernels
@@ -38,10 +57,11 @@ constexpr int kMaxM = 512;         // largest Lanczos subspace the single-CTA so
 constexpr int kNumSm = 148;        // B200
 
 // One sparse matrix stored by segments: rows (CSR) or columns (CSC).
-//   tiles[i] = {seg0, k0, z, nk | logG << 16}:
-//     z > 0 : "stream" tile -- z whole segments seg0..seg0+z whose non-zeros are [k0, k0+nk);
-//             every group of 2^logG lanes reduces one segment
-//     z < 0 : one 256-non-zero piece [k0, k0+nk) of the long segment seg0; -z-1 indexes longtab
+//   tiles[i] = {seg0, k0, z, nk | tag << 16}  (one CTA per tile):
+//     z > 0, tag = g < 6 : "stream" tile -- z whole short segments seg0..seg0+z whose non-zeros are
+//             [k0, k0+nk); every group of 2^g threads reduces one segment
+//     z = 1, tag = 15    : one medium segment, reduced by the whole CTA
+//     z < 0 : one 2048-non-zero piece [k0, k0+nk) of the long segment seg0; -z-1 indexes longtab
 //   longtab[l] = {first partial slot, number of pieces, ptr[seg], seg}
 struct SegMat {
     int64_t nseg = 0, nnz = 0;
@@ -55,6 +75,7 @@ struct SegMat {
     double *longdot = nullptr;   // [nlong]    v.w contribution of each long segment (Lanczos)
     unsigned *ticket = nullptr;  // [nlong]    self-resetting arrival counters
     int grid = 0;                // CTAs of the sweep kernels over this matrix (fixed -> deterministic sums)
+    int64_t gather_len = 0;      // length of the vector this matrix gathers from (d for CSR, n for CSC)
 };
 
 // Device-resident control block of the Lanczos recurrence (written by single threads on the device,
@@ -124,6 +145,8 @@ struct kcrn_problem {
     void *comm = nullptr;
     int rank = 0, world = 1;
     int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool pdl = false;              // launch with programmatic dependent launch (set while the Lanczos graph is built)
+    bool allow_pdl = false;        // KCRN_PDL=1 switches it on
 };
 
 namespace kcrn {
@@ -133,7 +156,7 @@ int build_csc(const SegMat &csr, int64_t n_cols, SegMat *csc, cudaStream_t s);
 int exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t len, cudaStream_t s);
 
 // ----------------------------------------------------------------------------- kcrn_sweep.cu
-int build_tiles(SegMat *A, cudaStream_t s);
+int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s);
 void free_segmat(SegMat *A);
 int launch_forward(kcrn_problem *h, const double *x);                 // A x and everything derived
 int launch_rows_weighted(kcrn_problem *h, const double *v);           // t = D .* (A v)

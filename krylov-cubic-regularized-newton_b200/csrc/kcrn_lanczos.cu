@@ -73,6 +73,8 @@ __device__ __forceinline__ bool grid_sum(double v, double *partials, unsigned *t
 
 // |g| into bet[0]; reset of alphas, betas and the control block for an m-step run
 __global__ void __launch_bounds__(kVecThreads) lanczos_init_kernel(VecParams P) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ double sh[kVecThreads / 32];
     __shared__ int s_last;
     double loc = 0.0;
@@ -97,6 +99,8 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_init_kernel(VecParams P) 
 
 // V[col] = source / bet[col] outside the fused row sweep (step-wise API)
 __global__ void __launch_bounds__(kVecThreads) normalise_kernel(VecParams P) {
+    pdl_wait();
+    pdl_trigger();
     if (P.ctl->done || P.ctl->redo) return;
     const int col = P.ctl->col;
     const double *src = col == 0 ? P.g : P.wp;
@@ -108,6 +112,8 @@ __global__ void __launch_bounds__(kVecThreads) normalise_kernel(VecParams P) {
 
 template <int E>
 __global__ void __launch_bounds__(kVecThreads) lanczos_post_kernel(VecParams P) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ double sh[kVecThreads / 32];
     __shared__ int s_last;
     if (P.ctl->done) return;
@@ -142,6 +148,8 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_post_kernel(VecParams P) 
 
 template <int E>
 __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ double sh[kVecThreads / 32];
     __shared__ int s_last;
     __shared__ double sdots[kVecThreads / 32][kMaxM];
@@ -247,6 +255,8 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P
 }
 
 __global__ void lanczos_finish_kernel(const LanczosCtl *ctl, int32_t *info, double *bet) {
+    pdl_wait();
+    pdl_trigger();
     if (threadIdx.x == 0) {
         bet[ctl->m] = ctl->last_beta;   // slot m is free: bet[j + 1] = beta_j only for j <= m - 2
         info[0] = ctl->m_eff; info[1] = ctl->nvalid; info[2] = ctl->broke; info[3] = ctl->hvps;
@@ -285,6 +295,8 @@ __global__ void value_combine_kernel(const double *scal, double n_samples, doubl
 // out = y / n + l2 u   (after the allreduce of a row-sharded transpose sweep)
 __global__ void scale_kernel(const double *__restrict__ y, const double *__restrict__ u, int64_t d,
                              double n_samples, double l2, double *__restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d; i += (int64_t)gridDim.x * blockDim.x) {
         double v = y[i] / n_samples;
         if (u) v = __dadd_rn(v, __dmul_rn(l2, u[i]));
@@ -360,8 +372,7 @@ int launch_lanczos_init(kcrn_problem *h, int m) {
     VecParams P = base_params(h);
     P.m = m;
     P.red_ticket = h->red_ticket + 4;
-    lanczos_init_kernel<<<grid_stride_blocks(h->d), kVecThreads, 0, h->stream>>>(P);
-    KCRN_LAUNCH_CHECK();
+    KCRN_CUDA(launch_kernel(lanczos_init_kernel, dim3(grid_stride_blocks(h->d)), dim3(kVecThreads), 0, h->stream, h->pdl, P));
     h->counters[0] += 1;
     return KCRN_OK;
 }
@@ -378,9 +389,8 @@ int launch_lanczos_post(kcrn_problem *h, const double *hv_or_raw, int raw) {
     VecParams P = base_params(h);
     P.w_in = hv_or_raw; P.w_out = h->w; P.raw = raw;
     P.red_ticket = h->red_ticket + 2;
-    if (h->vec_elems == 4) lanczos_post_kernel<4><<<h->vec_grid, kVecThreads, 0, h->stream>>>(P);
-    else lanczos_post_kernel<1><<<h->vec_grid, kVecThreads, 0, h->stream>>>(P);
-    KCRN_LAUNCH_CHECK();
+    if (h->vec_elems == 4) KCRN_CUDA(launch_kernel(lanczos_post_kernel<4>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
+    else KCRN_CUDA(launch_kernel(lanczos_post_kernel<1>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
     h->counters[0] += 1;
     return KCRN_OK;
 }
@@ -393,17 +403,15 @@ int launch_lanczos_update(kcrn_problem *h, int reorth) {
         P.coef_in = stage == 2 ? h->coef : h->coef2;
         P.coef_out = stage == 1 ? h->coef : h->coef2;
         P.red_ticket = h->red_ticket + 1;
-        if (h->vec_elems == 4) lanczos_update_kernel<4><<<h->vec_grid, kVecThreads, 0, h->stream>>>(P);
-        else lanczos_update_kernel<1><<<h->vec_grid, kVecThreads, 0, h->stream>>>(P);
-        KCRN_LAUNCH_CHECK();
+        if (h->vec_elems == 4) KCRN_CUDA(launch_kernel(lanczos_update_kernel<4>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
+        else KCRN_CUDA(launch_kernel(lanczos_update_kernel<1>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
         h->counters[0] += 1;
     }
     return KCRN_OK;
 }
 
 int launch_lanczos_finish(kcrn_problem *h) {
-    lanczos_finish_kernel<<<1, 32, 0, h->stream>>>(h->ctl, h->info, h->bet);
-    KCRN_LAUNCH_CHECK();
+    KCRN_CUDA(launch_kernel(lanczos_finish_kernel, dim3(1), dim3(32), 0, h->stream, h->pdl, (const LanczosCtl *)h->ctl, h->info, h->bet));
     h->counters[0] += 1;
     return KCRN_OK;
 }
@@ -432,8 +440,7 @@ int launch_value_combine(kcrn_problem *h, double *out) {
 }
 
 int launch_scale(kcrn_problem *h, const double *y, const double *u, double *out) {
-    scale_kernel<<<grid_stride_blocks(h->d), kVecThreads, 0, h->stream>>>(y, u, h->d, (double)h->n_global, h->l2, out);
-    KCRN_LAUNCH_CHECK();
+    KCRN_CUDA(launch_kernel(scale_kernel, dim3(grid_stride_blocks(h->d)), dim3(kVecThreads), 0, h->stream, h->pdl, y, u, h->d, (double)h->n_global, h->l2, out));
     h->counters[0] += 1;
     return KCRN_OK;
 }

@@ -1,20 +1,34 @@
 // K1 / K3 / K4: the sweeps over the sparse data matrix.
 //
-// One kernel template serves both storage orders.  The matrix is a list of segments (rows of the CSR
-// copy, columns of the CSC copy); a host-built, static tile list cuts the non-zeros into pieces of at
-// most 256 so that every warp gets the same amount of work whatever the row / column length
-// distribution is (power-law columns put a third of the non-zeros of an rcv1-shaped matrix into 100
-// columns).  A warp
-//   1. loads its (index, value) pairs with fully coalesced loads, 8 in flight per lane,
-//   2. gathers the dense vector through the read-only path and multiplies,
-//   3. either tree-reduces the 256 products (one piece of a long segment; the piece sums are added in
-//      a fixed order by the last piece to arrive -- no floating-point atomics, run-to-run identical),
-//      or stages them in shared memory and lets groups of 2^logG lanes sum whole short segments,
-//   4. applies the epilogue of the pass in registers (sigmoid weights, 1/n + l2, the Lanczos
-//      three-term update and its dot product) so no extra pass over n- or d-vectors is needed.
+// One kernel template serves both storage orders.  The matrix is a list of segments (rows of the CSR copy,
+// columns of the CSC copy).  A host-built, static tile list gives every CTA (256 threads) the same amount of
+// work whatever the segment-length distribution is (power-law columns put a third of the non-zeros of an
+// rcv1-shaped matrix into 100 columns):
+//
+//   stream tile : up to 2048 non-zeros made of whole short segments (each <= 512 entries, <= 1024 segments)
+//   single tile : one segment of 513 .. 2048 entries
+//   piece       : 2048 consecutive entries of a segment longer than 2048
+//
+// One CTA per tile (the hardware scheduler balances the tiles; nothing depends on which SM runs what):
+//   1. 8 coalesced (index, value) loads per thread, the tile's segment pointers (cp.async straight to shared
+//      memory) and the epilogue operands are all requested before anything is consumed;
+//   2. the dense vector is gathered through the read-only path and multiplied;
+//   3. stream tile: products -> shared memory; groups of 2^g threads (g chosen per tile on the host) sum whole
+//      segments, left to right; then one thread per segment applies the epilogue, coalesced.
+//      single / piece: fixed-order CTA reduction; the piece sums of a long segment are added in index order by
+//      the CTA that arrives last (self-resetting ticket) -- no floating-point atomics anywhere;
+//   4. the epilogue of the pass runs in registers (sigmoid weights, 1/n + l2, the Lanczos three-term update and
+//      its dot product), so no extra pass over n- or d-vectors is needed.
+// Every sum has a fixed order: results are run-to-run bit-identical.
+//
+// Warp-sized tiles were tried first (profiles/r1a_*): a lone warp walks a ~6 000-cycle dependent chain per 256
+// non-zeros and an SM only holds 16-32 of them; CTA-wide tiles put 8x more non-zeros behind each chain and
+// spread the per-segment work over 256 threads.
 //
 // Reference arithmetic being replaced: optimizer/loss.py:266-277 (A x), :215-232 (value, gradient),
 // :289-302 (Hessian-vector product) and the v / w bookkeeping of optimizer/cubic.py:92-97.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "kcrn_device.cuh"
@@ -29,27 +43,35 @@ void free_segmat(SegMat *A) {
     *A = SegMat();
 }
 
-int build_tiles(SegMat *A, cudaStream_t s) {
+int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s) {
+    A->gather_len = gather_len;
     const int64_t nseg = A->nseg;
     std::vector<int32_t> ptr((size_t)nseg + 1);
     KCRN_CUDA(cudaMemcpyAsync(ptr.data(), A->ptr, sizeof(int32_t) * (nseg + 1), cudaMemcpyDeviceToHost, s));
     KCRN_CUDA(cudaStreamSynchronize(s));
     std::vector<int4> tiles, longtab;
-    tiles.reserve((size_t)(A->nnz / kTileNnz + nseg / kTileSegs + 16));
+    const char *env_short = getenv("KCRN_SHORT_SEG");       // tuning knob: longest segment that shares a tile
+    const int short_seg = env_short ? std::max(1, std::min(kTileNnz, atoi(env_short))) : kShortSeg;
+    tiles.reserve((size_t)(A->nnz / kTileNnz * 2 + nseg / kTileSegs + 16));
     int npartial = 0;
     int64_t sg = 0;
     while (sg < nseg) {
         const int len = ptr[sg + 1] - ptr[sg];
-        if (len > kTileNnz) {
+        if (len > kTileNnz) {                                   // long segment: pieces + ordered combine
             const int pieces = (len + kTileNnz - 1) / kTileNnz;
             const int lid = (int)longtab.size();
             longtab.push_back(make_int4(npartial, pieces, ptr[sg], (int)sg));
             for (int p = 0; p < pieces; ++p) {
                 const int k0 = ptr[sg] + p * kTileNnz;
                 const int nk = std::min(kTileNnz, ptr[sg + 1] - k0);
-                tiles.push_back(make_int4((int)sg, k0, -(lid + 1), nk | (5 << 16)));
+                tiles.push_back(make_int4((int)sg, k0, -(lid + 1), nk));
             }
             npartial += pieces;
+            ++sg;
+            continue;
+        }
+        if (len > short_seg) {                                  // one medium segment: CTA-wide reduction
+            tiles.push_back(make_int4((int)sg, ptr[sg], 1, len | (kSingleTag << 16)));
             ++sg;
             continue;
         }
@@ -58,7 +80,7 @@ int build_tiles(SegMat *A, cudaStream_t s) {
         int nk = 0, maxlen = 0;
         while (sg < nseg && sg - s0 < kTileSegs) {
             const int l = ptr[sg + 1] - ptr[sg];
-            if (l > kTileNnz || nk + l > kTileNnz) break;
+            if (l > short_seg || nk + l > kTileNnz) break;
             nk += l;
             maxlen = std::max(maxlen, l);
             ++sg;
@@ -67,9 +89,9 @@ int build_tiles(SegMat *A, cudaStream_t s) {
         int best = 0;
         long best_cost = -1;
         for (int lg = 0; lg <= 5; ++lg) {
-            const int G = 1 << lg, groups = 32 >> lg;
+            const int G = 1 << lg, groups = kSweepThreads >> lg;
             const long rounds = (ns + groups - 1) / groups;
-            const long cost = rounds * ((maxlen + G - 1) / G + lg + 2);
+            const long cost = rounds * ((maxlen + G - 1) / G + 2 * lg + 3);
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = lg; }
         }
         tiles.push_back(make_int4((int)s0, k0, ns, nk | (best << 16)));
@@ -77,7 +99,7 @@ int build_tiles(SegMat *A, cudaStream_t s) {
     A->ntiles = (int)tiles.size();
     A->nlong = (int)longtab.size();
     A->npartial = npartial;
-    A->grid = std::max(1, std::min((A->ntiles + kSweepWarps - 1) / kSweepWarps, kNumSm * 8));
+    A->grid = std::max(1, A->ntiles);
     KCRN_CUDA(cudaMalloc(&A->tiles, sizeof(int4) * std::max<size_t>(tiles.size(), 1)));
     KCRN_CUDA(cudaMalloc(&A->longtab, sizeof(int4) * std::max<size_t>(longtab.size(), 1)));
     KCRN_CUDA(cudaMalloc(&A->partial, sizeof(double) * std::max(npartial, 1)));
@@ -121,7 +143,7 @@ struct SweepParams {
     double *Ax, *D, *resid, *ell;
     // scaled columns
     const double *u;
-    double n_samples, l2;
+    double n_samples, inv_n, l2;   // inv_n = 1 / n_samples (IEEE), for the three-operation exact quotient
     int add_l2;
     // Lanczos
     LanczosCtl *ctl;
@@ -129,16 +151,28 @@ struct SweepParams {
     const double *g, *wp, *bet;
     double *w, *alphas;
     int64_t d;
-    double *red_partials;
+    double *red_partials;          // [ntiles] alpha contribution of every tile
     unsigned *red_ticket;
 };
+
+struct SweepState {
+    const double *src = nullptr;
+    double beta = 1.0, rinv = 1.0;        // gathered values are divided by beta (rows-Lanczos)
+    const double *vcol = nullptr, *vpre = nullptr;
+    double beta_prev = 0.0;
+    bool subtract = false;
+};
+
+constexpr int kItems = kTileNnz / kSweepThreads;       // non-zeros per thread
+constexpr int kSegRounds = kTileSegs / kSweepThreads;  // segments per thread in the epilogue
+__host__ __device__ constexpr int sweep_operands(int mode) { return mode == kColsRaw ? 0 : (mode == kColsLanczos ? 2 : 1); }
 
 // Epilogue of one finished segment.  op0 / op1 are the pass's per-segment operands, already in registers:
 //   rows forward: label b            rows weighted: Hessian weight D
 //   cols scaled : u (l2 term)        cols Lanczos : v[col], v[col-1]
 template <int MODE>
-__device__ __forceinline__ void finish_segment(const SweepParams &P, int seg, double sum, int lseg, double op0,
-                                               double op1, double beta_prev, bool subtract, double &acc) {
+__device__ __forceinline__ void finish_segment(const SweepParams &P, const SweepState &S, int seg, double sum,
+                                               int lseg, double op0, double op1, double &acc) {
     if constexpr (MODE == kRowsForward) {
         const double a = sigmoid(sum);
         P.Ax[seg] = sum;
@@ -150,59 +184,98 @@ __device__ __forceinline__ void finish_segment(const SweepParams &P, int seg, do
     } else if constexpr (MODE == kColsRaw) {
         P.out[seg] = sum;
     } else if constexpr (MODE == kColsScaled) {
-        double y = sum / P.n_samples;
+        double y = quotient(sum, P.n_samples, P.inv_n);
         if (P.add_l2) y = __dadd_rn(y, __dmul_rn(P.l2, op0));
         P.out[seg] = y;
     } else {  // kColsLanczos
-        double hv = __dadd_rn(sum / P.n_samples, __dmul_rn(P.l2, op0));
-        if (subtract) hv = __dsub_rn(hv, __dmul_rn(beta_prev, op1));
+        double hv = __dadd_rn(quotient(sum, P.n_samples, P.inv_n), __dmul_rn(P.l2, op0));
+        if (S.subtract) hv = __dsub_rn(hv, __dmul_rn(S.beta_prev, op1));
         P.w[seg] = hv;
         const double prod = __dmul_rn(op0, hv);
-        if (lseg >= 0) P.longdot[lseg] = prod;  // long segments finish on whichever warp arrives last:
-        else acc += prod;                       // keep their share out of the per-warp running sums
+        if (lseg >= 0) P.longdot[lseg] = prod;  // long segments finish on whichever CTA arrives last:
+        else acc += prod;                       // keep their share out of the per-tile sums
     }
 }
 
 template <int MODE>
-__device__ __forceinline__ void load_operands(const SweepParams &P, int seg, const double *vcol, const double *vpre,
-                                              bool subtract, double &op0, double &op1) {
+__device__ __forceinline__ void load_operands(const SweepParams &P, const SweepState &S, int seg, double &op0,
+                                              double &op1) {
     op0 = 0.0;
     op1 = 0.0;
     if constexpr (MODE == kRowsForward) op0 = __ldg(P.b + seg);
     if constexpr (MODE == kRowsWeighted || MODE == kRowsLanczos) op0 = __ldg(P.D + seg);
     if constexpr (MODE == kColsScaled) { if (P.add_l2) op0 = __ldg(P.u + seg); }
     if constexpr (MODE == kColsLanczos) {
-        op0 = __ldg(vcol + seg);
-        if (subtract) op1 = __ldg(vpre + seg);
+        op0 = __ldg(S.vcol + seg);
+        if (S.subtract) op1 = __ldg(S.vpre + seg);
     }
 }
 
-__host__ __device__ constexpr int kOperands(int mode) { return mode == kColsRaw ? 0 : (mode == kColsLanczos ? 2 : 1); }
+// fixed-order CTA sum: warp butterflies, then the warps in index order (thread 0 returns the total)
+__device__ __forceinline__ double cta_sum_to_thread0(double v, double *sred) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) sred[warp] = v;
+    __syncthreads();
+    double tot = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < kSweepWarps; ++w) tot += sred[w];
+    return tot;
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepParams P) {
-    __shared__ double sprod[kSweepWarps][kTileNnz];       // products of the tile
-    __shared__ double ssum[kSweepWarps][kTileSegs];       // per-segment sums of the tile
-    __shared__ int sptr[kSweepWarps][kTileSegs + 8];      // segment pointers of the tile
+    __shared__ double sprod[kTileNnz];           // products of the tile
+    __shared__ double ssum[kTileSegs];           // per-segment sums of the tile
+    __shared__ int sptr[kTileSegs + 8];          // segment pointers of the tile
     __shared__ double sred[kSweepWarps];
     __shared__ int s_last;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    constexpr int NOP = sweep_operands(MODE);
 
-    const double *src = P.src;
-    double beta = 1.0, rinv = 1.0;
-    const double *vcol = nullptr, *vpre = nullptr;
-    double beta_prev = 0.0;
-    bool subtract = false, final_ = false;
-    int col = 0, store_idx = 0;
+    // Everything that only depends on the (constant) matrix is requested BEFORE waiting for the previous kernel
+    // of the stream: with programmatic dependent launch this CTA may already be resident while that kernel is
+    // still finishing, so the descriptor -> (index, value) part of the latency chain overlaps with its tail.
+    const int tile = blockIdx.x;
+    int4 td = make_int4(0, 0, 0, 0);
+    int ci[kItems];
+    double av[kItems];
+    if (tile < P.ntiles) {
+        td = __ldg(P.tiles + tile);
+        const int32_t *ip = P.idx + td.y;
+        const double *vp = P.val + td.y;
+        const int nk0 = td.w & 0xffff;
+#pragma unroll
+        for (int r = 0; r < kItems; ++r) {
+            const int i = r * kSweepThreads + tid;
+            ci[r] = i < nk0 ? ld_stream(ip + i) : -1;
+            av[r] = i < nk0 ? ld_stream(vp + i) : 0.0;
+        }
+        if (td.z > 0 && (td.w >> 16) != kSingleTag) {
+#pragma unroll
+            for (int r = 0; r < kSegRounds + 1; ++r) {
+                const int i = r * kSweepThreads + tid;
+                if (i <= td.z) cp_async_4(sptr + i, P.ptr + td.x + i);
+            }
+        }
+    }
+    pdl_wait();      // the previous kernel's results (control block, vectors) are complete and visible from here on
+    pdl_trigger();   // let the next kernel of the stream start its own matrix loads
+
+    SweepState S;
+    S.src = P.src;
+    bool final_ = false;
+    int col = 0, store_idx = 0, redo = 0;
     if constexpr (MODE == kRowsLanczos) {
         if (P.ctl->done) return;
         col = P.ctl->col;
-        if (P.ctl->redo) {
-            src = P.V + (size_t)col * P.d;
+        redo = P.ctl->redo;
+        if (redo) {
+            S.src = P.V + (size_t)col * P.d;
         } else {
-            src = col == 0 ? P.g : P.wp;
-            beta = P.bet[col];
-            rinv = 1.0 / beta;
+            S.src = col == 0 ? P.g : P.wp;
+            S.beta = P.bet[col];
+            S.rinv = 1.0 / S.beta;
         }
     }
     if constexpr (MODE == kColsLanczos) {
@@ -210,138 +283,119 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         col = P.ctl->col;
         final_ = P.ctl->final_ != 0;
         store_idx = P.ctl->store_idx;
-        vcol = P.V + (size_t)col * P.d;
+        S.vcol = P.V + (size_t)col * P.d;
         if (col > 0 && !final_) {
-            subtract = true;
-            vpre = P.V + (size_t)(col - 1) * P.d;
-            beta_prev = P.bet[col];
+            S.subtract = true;
+            S.vpre = P.V + (size_t)(col - 1) * P.d;
+            S.beta_prev = P.bet[col];
         }
     }
 
     double acc = 0.0;
-    double *sp = sprod[warp], *sm = ssum[warp];
-    int *sq = sptr[warp];
-    const int gw = blockIdx.x * kSweepWarps + warp, tw = gridDim.x * kSweepWarps;
-    for (int tile = gw; tile < P.ntiles; tile += tw) {
-        const int4 td = __ldg(P.tiles + tile);
-        const int seg0 = td.x, k0 = td.y, z = td.z, nk = td.w & 0xffff, logG = td.w >> 16;
-        const int32_t *ip = P.idx + k0;
-        const double *vp = P.val + k0;
-        // everything that only depends on the descriptor is requested before anything is consumed
-        int ci[8];
-        double av[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int i = r * 32 + lane;
-            ci[r] = i < nk ? ld_stream(ip + i) : -1;
-            av[r] = i < nk ? ld_stream(vp + i) : 0.0;
-        }
+    if (tile < P.ntiles) {
+        const int seg0 = td.x, k0 = td.y, z = td.z, nk = td.w & 0xffff, tag = td.w >> 16;
+        const bool stream = z > 0 && tag != kSingleTag;
         int4 lt = make_int4(0, 1, 0, 0);
-        constexpr int SR = kTileSegs / 32;   // segment rounds per lane
-        if (z < 0) {
-            lt = __ldg(P.longtab + (-z - 1));
-        } else {
-            // segment pointers go straight to shared memory (cp.async: no registers held while in flight)
+        double o0[NOP > 0 ? kSegRounds : 1], o1[NOP > 1 ? kSegRounds : 1];
+        if (stream) {
+            // epilogue operands to registers: in flight while the gathers run
 #pragma unroll
-            for (int r = 0; r < SR + 1; ++r) {
-                const int i = r * 32 + lane;
-                if (i <= z) cp_async_4(sq + i, P.ptr + seg0 + i);
-            }
-        }
-        double p[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            double xv = 0.0;
-            if (ci[r] >= 0) xv = __ldg(src + ci[r]);
-            if constexpr (MODE == kRowsLanczos) xv = quotient(xv, beta, rinv);
-            p[r] = av[r] * xv;
-        }
-        if (z < 0) {
-            // one 256-entry piece of a long segment: tree-reduce, publish, the last piece to arrive finishes
-            double op0, op1;
-            load_operands<MODE>(P, seg0, vcol, vpre, subtract, op0, op1);
-            double s = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
-            s = warp_sum(s);
-            const int lseg = -z - 1;
-            const int slot = lt.x + ((k0 - lt.z) >> 8);
-            int last = 0;
-            if (lane == 0) {
-                P.partial[slot] = s;
-                __threadfence();
-                last = atomicInc(P.ticket + lseg, (unsigned)(lt.y - 1)) == (unsigned)(lt.y - 1);
-            }
-            last = __shfl_sync(0xffffffffu, last, 0);
-            if (last) {
-                __threadfence();
-                double tot = 0.0;
-                for (int i = lane; i < lt.y; i += 32) tot += __ldcg(P.partial + lt.x + i);
-                tot = warp_sum(tot);
-                if (lane == 0) finish_segment<MODE>(P, seg0, tot, lseg, op0, op1, beta_prev, subtract, acc);
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int i = r * 32 + lane;
-                if (i < nk) sp[i] = p[r];
-            }
-            // operands of the epilogue: requested now, consumed after the shared-memory reduction
-            constexpr int NOP = kOperands(MODE);
-            double o0[NOP > 0 ? SR : 1], o1[NOP > 1 ? SR : 1];
-#pragma unroll
-            for (int r = 0; r < SR; ++r) {
-                const int sg = r * 32 + lane;
+            for (int r = 0; r < kSegRounds; ++r) {
+                const int sg = r * kSweepThreads + tid;
                 if (sg < z) {
                     double a0, a1;
-                    load_operands<MODE>(P, seg0 + sg, vcol, vpre, subtract, a0, a1);
+                    load_operands<MODE>(P, S, seg0 + sg, a0, a1);
                     if constexpr (NOP > 0) o0[r] = a0;
                     if constexpr (NOP > 1) o1[r] = a1;
                 }
             }
+        } else {
+            if (z < 0) lt = __ldg(P.longtab + (-z - 1));
+            if (tid == 0) {
+                double a0, a1;
+                load_operands<MODE>(P, S, seg0, a0, a1);
+                if constexpr (NOP > 0) o0[0] = a0;
+                if constexpr (NOP > 1) o1[0] = a1;
+            }
+        }
+        double p[kItems];
+#pragma unroll
+        for (int r = 0; r < kItems; ++r) {
+            double xv = 0.0;
+            if (ci[r] >= 0) xv = __ldg(S.src + ci[r]);
+            if constexpr (MODE == kRowsLanczos) xv = quotient(xv, S.beta, S.rinv);
+            p[r] = av[r] * xv;
+        }
+        if (!stream) {
+            // one segment (or one piece of a long one) spread over the whole CTA
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < kItems; ++r) s += p[r];
+            const double tot = cta_sum_to_thread0(s, sred);
+            if (z > 0) {
+                if (tid == 0) finish_segment<MODE>(P, S, seg0, tot, -1, NOP > 0 ? o0[0] : 0.0, NOP > 1 ? o1[0] : 0.0, acc);
+            } else {
+                const int lseg = -z - 1;
+                if (tid == 0) {
+                    P.partial[lt.x + (k0 - lt.z) / kTileNnz] = tot;
+                    __threadfence();
+                    s_last = atomicInc(P.ticket + lseg, (unsigned)(lt.y - 1)) == (unsigned)(lt.y - 1);
+                }
+                __syncthreads();
+                if (s_last && tid < 32) {
+                    __threadfence();
+                    double all = 0.0;
+                    for (int i = lane; i < lt.y; i += 32) all += __ldcg(P.partial + lt.x + i);
+                    all = warp_sum(all);
+                    // thread 0 holds the operands
+                    if (tid == 0) finish_segment<MODE>(P, S, seg0, all, lseg, NOP > 0 ? o0[0] : 0.0, NOP > 1 ? o1[0] : 0.0, acc);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < kItems; ++r) {
+                const int i = r * kSweepThreads + tid;
+                if (i < nk) sprod[i] = p[r];
+            }
             cp_async_wait_all();
-            __syncwarp();
-            // phase A: every group of G lanes sums one segment from shared memory
-            const int G = 1 << logG, groups = 32 >> logG, gid = lane >> logG, gl = lane & (G - 1);
+            __syncthreads();
+            // phase A: every group of G threads sums one segment from shared memory, left to right
+            const int G = 1 << tag, groups = kSweepThreads >> tag, gid = tid >> tag, gl = tid & (G - 1);
             for (int sb = 0; sb < z; sb += groups) {
                 const int sg = sb + gid;
                 int a = 0, b = 0;
-                if (sg < z) { a = sq[sg] - k0; b = sq[sg + 1] - k0; }
+                if (sg < z) { a = sptr[sg] - k0; b = sptr[sg + 1] - k0; }
                 double sum = 0.0;
-                for (int i = a + gl; i < b; i += G) sum += sp[i];
+                for (int i = a + gl; i < b; i += G) sum += sprod[i];
                 for (int o = G >> 1; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                if (sg < z && gl == 0) sm[sg] = sum;
+                if (sg < z && gl == 0) ssum[sg] = sum;
             }
-            __syncwarp();
-            // phase B: coalesced epilogue over the segments of the tile
+            __syncthreads();
+            // phase B: one thread per segment applies the epilogue, coalesced
 #pragma unroll
-            for (int r = 0; r < SR; ++r) {
-                const int sg = r * 32 + lane;
+            for (int r = 0; r < kSegRounds; ++r) {
+                const int sg = r * kSweepThreads + tid;
                 if (sg < z)
-                    finish_segment<MODE>(P, seg0 + sg, sm[sg], -1, NOP > 0 ? o0[r] : 0.0, NOP > 1 ? o1[r] : 0.0,
-                                         beta_prev, subtract, acc);
+                    finish_segment<MODE>(P, S, seg0 + sg, ssum[sg], -1, NOP > 0 ? o0[r] : 0.0, NOP > 1 ? o1[r] : 0.0, acc);
             }
-            __syncwarp();
         }
     }
 
     if constexpr (MODE == kRowsLanczos) {
-        // side job: store the normalised vector as basis column `col` (the sweep above divided on the fly)
-        if (!P.ctl->redo) {
+        // side job: store the normalised vector as basis column `col` (the sweep divided on the fly)
+        if (!redo) {
             double *vout = P.V + (size_t)col * P.d;
-            for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < P.d;
-                 c += (int64_t)gridDim.x * blockDim.x)
-                vout[c] = quotient(__ldg(src + c), beta, rinv);
+            for (int64_t c = (int64_t)blockIdx.x * blockDim.x + tid; c < P.d; c += (int64_t)gridDim.x * blockDim.x)
+                vout[c] = quotient(__ldg(S.src + c), S.beta, S.rinv);
         }
     }
 
     if constexpr (MODE == kColsLanczos) {
-        // alpha = v . w : lanes -> warp -> CTA -> (last CTA) whole grid, every level in a fixed order
-        acc = warp_sum(acc);
-        if (lane == 0) sred[warp] = acc;
+        // alpha = v . w : threads -> tile (fixed order) -> the last CTA adds the tile sums in tile order
         __syncthreads();
-        if (threadIdx.x == 0) {
-            double cta = 0.0;
-            for (int wv = 0; wv < kSweepWarps; ++wv) cta += sred[wv];
-            P.red_partials[blockIdx.x] = cta;
+        const double mine = cta_sum_to_thread0(acc, sred);
+        if (tid == 0) {
+            P.red_partials[blockIdx.x] = mine;
             __threadfence();
             s_last = atomicInc(P.red_ticket, gridDim.x - 1) == gridDim.x - 1;
         }
@@ -349,15 +403,11 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         if (s_last) {
             __threadfence();
             double tot = 0.0;
-            for (int i = threadIdx.x; i < (int)gridDim.x; i += kSweepThreads) tot += __ldcg(P.red_partials + i);
-            for (int i = threadIdx.x; i < P.nlong; i += kSweepThreads) tot += __ldcg(P.longdot + i);
-            tot = warp_sum(tot);
+            for (int i = tid; i < (int)gridDim.x; i += kSweepThreads) tot += __ldcg(P.red_partials + i);
+            for (int i = tid; i < P.nlong; i += kSweepThreads) tot += __ldcg(P.longdot + i);
             __syncthreads();
-            if (lane == 0) sred[warp] = tot;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                double alpha = 0.0;
-                for (int wv = 0; wv < kSweepWarps; ++wv) alpha += sred[wv];
+            const double alpha = cta_sum_to_thread0(tot, sred);
+            if (tid == 0) {
                 P.alphas[final_ ? store_idx : col] = alpha;
                 P.ctl->hvps += 1;
                 if (final_) P.ctl->done = 1;
@@ -375,8 +425,7 @@ void fill_matrix(SweepParams &P, const SegMat &A) {
 template <int MODE>
 int launch(kcrn_problem *h, const SegMat &A, SweepParams &P) {
     fill_matrix(P, A);
-    sweep_kernel<MODE><<<A.grid, kSweepThreads, 0, h->stream>>>(P);
-    KCRN_LAUNCH_CHECK();
+    KCRN_CUDA(launch_kernel(sweep_kernel<MODE>, dim3(A.grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
     h->counters[0] += 1;
     return KCRN_OK;
 }
@@ -394,6 +443,8 @@ __global__ void derive_from_Ax_kernel(const double *__restrict__ Ax, const doubl
 }
 
 }  // namespace
+
+int configure_sweep_kernels() { return KCRN_OK; }
 
 int launch_forward(kcrn_problem *h, const double *x) {
     SweepParams P{};
@@ -425,7 +476,7 @@ int launch_cols_raw(kcrn_problem *h, const double *src, double *out) {
 
 int launch_cols_scaled(kcrn_problem *h, const double *src, const double *u, double *out) {
     SweepParams P{};
-    P.src = src; P.out = out; P.u = u; P.n_samples = (double)h->n_global; P.l2 = h->l2;
+    P.src = src; P.out = out; P.u = u; P.n_samples = (double)h->n_global; P.inv_n = 1.0 / P.n_samples; P.l2 = h->l2;
     P.add_l2 = u != nullptr;
     h->counters[4] += 1;
     return launch<kColsScaled>(h, h->csc, P);
@@ -434,7 +485,7 @@ int launch_cols_scaled(kcrn_problem *h, const double *src, const double *u, doub
 int launch_cols_lanczos(kcrn_problem *h) {
     SweepParams P{};
     P.src = h->t; P.ctl = h->ctl; P.V = h->V; P.bet = h->bet; P.w = h->w; P.alphas = h->alphas; P.d = h->d;
-    P.n_samples = (double)h->n_global; P.l2 = h->l2;
+    P.n_samples = (double)h->n_global; P.inv_n = 1.0 / P.n_samples; P.l2 = h->l2;
     P.red_partials = h->red_partials; P.red_ticket = h->red_ticket + 0;
     h->counters[4] += 1;
     return launch<kColsLanczos>(h, h->csc, P);
