@@ -130,3 +130,40 @@ def balanced_row_cuts(indptr: np.ndarray, parts: int) -> np.ndarray:
     inner = np.searchsorted(indptr, targets, side="left")
     cuts = np.concatenate(([0], inner, [n])).astype(np.int64)
     return np.maximum.accumulate(np.minimum(cuts, n))
+
+
+def make_problem_device(n: int, d: int, nnz_per_row: float, zipf_a: float = 1.0, seed: int = 0, device="cuda"):
+    """Large synthetic problem generated ON the GPU with torch (BASELINE config 5 scale: host generation of 1e9
+    non-zeros is impractical).  Same recipe as ``make_problem`` -- Poisson row lengths, power-law column popularity
+    under a random permutation, distinct sorted columns per row, lognormal values with unit-L2 rows -- but not
+    bit-identical to it.  Returns (indptr int32 [n+1], indices int32 [nnz], data float64 [nnz], labels01 float64 [n])
+    as CUDA tensors."""
+    import torch
+
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    lens = torch.poisson(torch.full((n,), float(nnz_per_row), device=device), generator=gen).clamp_(1, d).to(torch.int64)
+    rows = torch.repeat_interleave(torch.arange(n, device=device, dtype=torch.int64), lens)
+    u = torch.rand(rows.numel(), device=device, generator=gen, dtype=torch.float64)
+    if zipf_a == 1.0:
+        rank = torch.exp(u * float(np.log(d + 1.0))) - 1.0            # P(rank <= r) ~ log(r + 1) / log(d + 1)
+    else:
+        e = 1.0 - zipf_a
+        rank = ((u * ((d + 1.0) ** e - 1.0) + 1.0) ** (1.0 / e)) - 1.0
+    del u
+    rank = rank.to(torch.int64).clamp_(0, d - 1)
+    perm = torch.randperm(d, device=device, generator=gen)
+    key = rows * d + perm[rank]
+    del rows, rank
+    key = torch.unique(key)                                           # sorted, duplicates inside a row removed
+    rows = torch.div(key, d, rounding_mode="floor")
+    indices = (key - rows * d).to(torch.int32)
+    del key
+    counts = torch.bincount(rows, minlength=n)
+    indptr = torch.zeros(n + 1, device=device, dtype=torch.int64)
+    torch.cumsum(counts, 0, out=indptr[1:])
+    data = torch.exp(0.5 * torch.randn(indices.numel(), device=device, generator=gen, dtype=torch.float64))
+    sq = torch.zeros(n, device=device, dtype=torch.float64).index_add_(0, rows, data * data)
+    data /= torch.sqrt(sq)[rows]
+    labels = (torch.rand(n, device=device, generator=gen) > 0.5).to(torch.float64)
+    return indptr.to(torch.int32), indices, data, labels
