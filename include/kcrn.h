@@ -124,6 +124,15 @@ int kcrn_trial_point(kcrn_handle h, const double *x_dev, double *out_dev);
  * the current x (the value reduction is enqueued by this call when with_value != 0). */
 int kcrn_step_record(kcrn_handle h, int with_value, double *rec12_host);
 
+/* One trial of a Krylov-CRN outer iteration as ONE CUDA graph plus one device-to-host copy (cubic.py:265-303
+ * without the host-side compare).  first != 0: keep the current x as the base iterate, gradient, m-step
+ * Lanczos; always: sub-problem with (M, r0, eps, it_max), trial point x_base + V s, forward sweep and value
+ * at the trial point (which becomes the handle's current x).  first == 0 repeats only the second half with a
+ * new M (the backtracking loop of cubic.py:294-303).  x_out_dev (nullable) receives the trial point;
+ * rec12_host as in kcrn_step_record.  Synchronous. */
+int kcrn_krylov_trial(kcrn_handle h, int first, int m, int reorth, double M, double r0, double eps, int it_max,
+                      double *x_out_dev, double *rec12_host);
+
 /* ---- config-4 rows (full-Hessian CRN, SSCN) -------------------------------------------------
  * dense A' D A / n + l2 I, row-major [n_cols x n_cols]  (loss.py:249-255), FP64 tensor cores. */
 int kcrn_hessian_dense(kcrn_handle h, double *out_dev);

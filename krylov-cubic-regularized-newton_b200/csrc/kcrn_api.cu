@@ -23,6 +23,7 @@ int launch_lanczos_finish(kcrn_problem *h);
 int launch_sumsq(kcrn_problem *h, const double *a, int64_t len, double *out);
 int launch_value_combine(kcrn_problem *h, double *out);
 int launch_scale(kcrn_problem *h, const double *y, const double *u, double *out);
+int launch_record(kcrn_problem *h);
 int config4_hessian_dense(kcrn_problem *h, double *out);
 int config4_partial_gradient(kcrn_problem *h, const int64_t *I, int m, double *out);
 int config4_partial_hessian(kcrn_problem *h, const int64_t *I, int m, double *out);
@@ -95,6 +96,60 @@ int enqueue_lanczos(kcrn_problem *h, int m, int reorth) {
     return launch_lanczos_finish(h);
 }
 
+// Capture `enqueue` once per key = (kind, m, reorth) into a CUDA graph and replay it on the handle's stream.
+template <class F>
+int run_graph(kcrn_problem *h, int kind, int m, int reorth, F enqueue) {
+    cudaGraphExec_t exec = nullptr;
+    for (auto &ge : h->graphs)
+        if (ge.kind == kind && ge.m == m && ge.reorth == reorth) exec = ge.exec;
+    if (!exec) {
+        cudaStream_t user = h->stream, cap = nullptr;
+        KCRN_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+        int64_t saved[8];
+        memcpy(saved, h->counters, sizeof(saved));
+        h->stream = cap;
+        h->pdl = h->allow_pdl;
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed);
+        int rc = e == cudaSuccess ? enqueue() : KCRN_E_CUDA;
+        cudaError_t e2 = cudaStreamEndCapture(cap, &graph);
+        h->stream = user;
+        h->pdl = false;
+        for (int i = 0; i < 8; ++i) h->graph_delta[i] = h->counters[i] - saved[i];
+        memcpy(h->counters, saved, sizeof(saved));
+        if (e != cudaSuccess || e2 != cudaSuccess || rc != KCRN_OK || !graph) {
+            if (rc == KCRN_OK) set_error("graph capture failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+            if (graph) cudaGraphDestroy(graph);
+            cudaStreamDestroy(cap);
+            return rc != KCRN_OK ? rc : KCRN_E_CUDA;
+        }
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        cudaStreamDestroy(cap);
+        if (e != cudaSuccess) { set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e)); return KCRN_E_CUDA; }
+        kcrn_problem::GraphEntry ge;
+        ge.kind = kind; ge.m = m; ge.reorth = reorth; ge.exec = exec;
+        memcpy(ge.delta, h->graph_delta, sizeof(ge.delta));
+        h->graphs.push_back(ge);
+    }
+    KCRN_CUDA(cudaGraphLaunch(exec, h->stream));
+    for (auto &ge : h->graphs)
+        if (ge.exec == exec)
+            for (int i = 0; i < 8; ++i) h->counters[i] += ge.delta[i];
+    h->counters[1] += 1;
+    return KCRN_OK;
+}
+
+// one device-to-host copy of the record assembled by record_kernel; synchronous
+int read_step_record(kcrn_problem *h, double *rec12_host) {
+    cudaStream_t s = h->stream;
+    KCRN_CUDA(cudaMemcpyAsync(h->rec_host, h->scal + 4, sizeof(double) * 12, cudaMemcpyDeviceToHost, s));
+    KCRN_CUDA(cudaStreamSynchronize(s));
+    h->counters[7] += (int64_t)sizeof(double) * 12;
+    memcpy(rec12_host, h->rec_host, sizeof(double) * 12);
+    return KCRN_OK;
+}
+
 }  // namespace
 }  // namespace kcrn
 
@@ -141,6 +196,8 @@ int kcrn_create(kcrn_handle *out, int64_t n_rows, int64_t n_cols, int64_t nnz, c
         h->allow_pdl = getenv("KCRN_PDL") != nullptr;   // opt-in: measured slower inside the Lanczos graph
         const size_t n = (size_t)n_rows, d = (size_t)n_cols;
         KCRN_CUDA(cudaMalloc(&h->x_cur, sizeof(double) * d));
+        KCRN_CUDA(cudaMalloc(&h->x_base, sizeof(double) * d));
+        KCRN_CUDA(cudaMalloc(&h->step_params, sizeof(double) * 4));
         KCRN_CUDA(cudaMalloc(&h->Ax, sizeof(double) * n));
         KCRN_CUDA(cudaMalloc(&h->D, sizeof(double) * n));
         KCRN_CUDA(cudaMalloc(&h->resid, sizeof(double) * n));
@@ -193,7 +250,7 @@ int kcrn_destroy(kcrn_handle h) {
     nccl_destroy(h);
     free_segmat(&h->csr);
     free_segmat(&h->csc);
-    double *bufs[] = {h->b, h->x_cur, h->Ax, h->D, h->resid, h->ell, h->t, h->ypart, h->V, h->w, h->wp, h->g,
+    double *bufs[] = {h->b, h->x_base, h->step_params, h->x_cur, h->Ax, h->D, h->resid, h->ell, h->t, h->ypart, h->V, h->w, h->wp, h->g,
                       h->alphas, h->bet, h->coef, h->coef2, h->sub, h->scal, h->red_partials, h->x_stage,
                       h->v_stage, h->o_stage};
     for (double *p : bufs) cudaFree(p);
@@ -246,6 +303,7 @@ int kcrn_set_x(kcrn_handle h, const double *x_dev) {
         KCRN_CUDA(cudaMemcpyAsync(h->x_cur, x_dev, sizeof(double) * h->d, cudaMemcpyDeviceToDevice, h->stream));
     KCRN_TRY(launch_forward(h, h->x_cur));
     h->have_x = true;
+    h->have_base = false;
     return KCRN_OK;
 }
 
@@ -327,48 +385,50 @@ int kcrn_lanczos(kcrn_handle h, const double *g_dev, int m, int reorth) {
     KCRN_TRY(lanczos_alloc(h, m));
     if (g_dev && g_dev != h->g)
         KCRN_CUDA(cudaMemcpyAsync(h->g, g_dev, sizeof(double) * h->d, cudaMemcpyDeviceToDevice, h->stream));
-    cudaGraphExec_t exec = nullptr;
-    for (auto &ge : h->graphs)
-        if (ge.m == m && ge.reorth == reorth) exec = ge.exec;
-    if (!exec) {
-        cudaStream_t user = h->stream, cap = nullptr;
-        KCRN_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
-        int64_t saved[8];
-        memcpy(saved, h->counters, sizeof(saved));
-        h->stream = cap;
-        h->pdl = h->allow_pdl;
-        cudaGraph_t graph = nullptr;
-        cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed);
-        int rc = e == cudaSuccess ? enqueue_lanczos(h, m, reorth) : KCRN_E_CUDA;
-        cudaError_t e2 = cudaStreamEndCapture(cap, &graph);
-        h->stream = user;
-        h->pdl = false;
-        for (int i = 0; i < 8; ++i) h->graph_delta[i] = h->counters[i] - saved[i];
-        memcpy(h->counters, saved, sizeof(saved));
-        if (e != cudaSuccess || e2 != cudaSuccess || rc != KCRN_OK || !graph) {
-            if (rc == KCRN_OK) set_error("kcrn_lanczos: graph capture failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
-            if (graph) cudaGraphDestroy(graph);
-            cudaStreamDestroy(cap);
-            return rc != KCRN_OK ? rc : KCRN_E_CUDA;
-        }
-        e = cudaGraphInstantiate(&exec, graph, 0);
-        cudaGraphDestroy(graph);
-        cudaStreamDestroy(cap);
-        if (e != cudaSuccess) { set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e)); return KCRN_E_CUDA; }
-        kcrn_problem::GraphEntry ge;
-        ge.m = m; ge.reorth = reorth; ge.exec = exec;
-        memcpy(ge.delta, h->graph_delta, sizeof(ge.delta));
-        h->graphs.push_back(ge);
-    }
-    KCRN_CUDA(cudaGraphLaunch(exec, h->stream));
-    for (auto &ge : h->graphs)
-        if (ge.exec == exec)
-            for (int i = 0; i < 8; ++i) h->counters[i] += ge.delta[i];
-    h->counters[1] += 1;
+    KCRN_TRY(run_graph(h, 0, m, reorth, [&]() { return enqueue_lanczos(h, m, reorth); }));
     h->counters[2] += m;
     h->cur_m = m;
     h->cur_reorth = reorth;
     return KCRN_OK;
+}
+
+int kcrn_krylov_trial(kcrn_handle h, int first, int m, int reorth, double M, double r0, double eps, int it_max,
+                      double *x_out_dev, double *rec12_host) {
+    KCRN_TRY(need_x(h, "kcrn_krylov_trial"));
+    if (m < 1 || m > kMaxM) { set_error("kcrn_krylov_trial: m = %d outside [1, %d]", m, kMaxM); return KCRN_E_ARG; }
+    if (!rec12_host) { set_error("kcrn_krylov_trial: null record"); return KCRN_E_ARG; }
+    if (!first && (h->cur_m != m || !h->have_base)) {
+        set_error("kcrn_krylov_trial: a re-trial needs the first trial of the same step before it");
+        return KCRN_E_STATE;
+    }
+    reorth = reorth ? 1 : 0;
+    KCRN_TRY(lanczos_alloc(h, m));
+    cudaStream_t s = h->stream;
+    double *pp = h->rec_host + 12;          // pinned; every trial ends with a stream synchronise, so it is free
+    pp[0] = M; pp[1] = r0; pp[2] = eps; pp[3] = (double)it_max;
+    KCRN_CUDA(cudaMemcpyAsync(h->step_params, pp, sizeof(double) * 4, cudaMemcpyHostToDevice, s));
+    h->cur_m = m;
+    h->cur_reorth = reorth;
+    KCRN_TRY(run_graph(h, first ? 1 : 2, m, reorth, [&]() -> int {
+        if (first) {
+            KCRN_CUDA(cudaMemcpyAsync(h->x_base, h->x_cur, sizeof(double) * h->d, cudaMemcpyDeviceToDevice, h->stream));
+            KCRN_TRY(cols_product(h, h->resid, h->l2 != 0.0 ? h->x_cur : nullptr, h->g));      // gradient
+            KCRN_TRY(enqueue_lanczos(h, m, reorth));
+        }
+        h->counters[0] += 2;
+        KCRN_TRY(launch_cubic(h->alphas, h->bet + 1, m, h->info, h->bet, 0.0, 0.0, 0.0, 0.0, 0, h->sub, h->sub + kMaxM,
+                              h->stream, h->step_params));
+        KCRN_TRY(launch_axpy_basis(h->x_base, h->V, h->sub, m, h->info, h->d, h->x_cur, h->stream, h->red_partials,
+                                   h->red_ticket + 5, h->scal + 3));
+        KCRN_TRY(launch_forward(h, h->x_cur));
+        KCRN_TRY(enqueue_value(h, h->scal + 0));
+        return launch_record(h);
+    }));
+    if (first) h->counters[2] += m;
+    h->have_base = true;
+    if (x_out_dev)
+        KCRN_CUDA(cudaMemcpyAsync(x_out_dev, h->x_cur, sizeof(double) * h->d, cudaMemcpyDeviceToDevice, s));
+    return read_step_record(h, rec12_host);
 }
 
 int kcrn_lanczos_view(kcrn_handle h, const double **V_dev, const double **alphas_dev, const double **bet_dev,
@@ -420,14 +480,14 @@ int kcrn_cubic_tridiag(const double *alphas_dev, const double *betas_dev, int m,
                        double eps, int it_max, double *out_dev, void *stream) {
     if (!alphas_dev || !out_dev || (m > 1 && !betas_dev)) { set_error("kcrn_cubic_tridiag: null argument"); return KCRN_E_ARG; }
     return launch_cubic(alphas_dev, betas_dev, m, nullptr, nullptr, gnorm, M, r0, eps, it_max, out_dev, out_dev + m,
-                        (cudaStream_t)stream);
+                        (cudaStream_t)stream, nullptr);
 }
 
 int kcrn_cubic_from_lanczos(kcrn_handle h, double M, double r0, double eps, int it_max) {
     if (!h || h->cur_m < 1) { set_error("kcrn_cubic_from_lanczos: no Lanczos result in the handle"); return KCRN_E_STATE; }
     h->counters[0] += 1;
     return launch_cubic(h->alphas, h->bet + 1, h->cur_m, h->info, h->bet, 0.0, M, r0, eps, it_max, h->sub,
-                        h->sub + kMaxM, h->stream);
+                        h->sub + kMaxM, h->stream, nullptr);
 }
 
 int kcrn_axpy_basis(const double *x_dev, const double *V_dev, const double *s_dev, int m, int64_t d, double *out_dev,
@@ -447,35 +507,13 @@ int kcrn_trial_point(kcrn_handle h, const double *x_dev, double *out_dev) {
 }
 
 int kcrn_step_record(kcrn_handle h, int with_value, double *rec12_host) {
-    double *rec8_host = rec12_host;
-    if (!h || !rec8_host) { set_error("kcrn_step_record: null argument"); return KCRN_E_ARG; }
-    cudaStream_t s = h->stream;
+    if (!h || !rec12_host) { set_error("kcrn_step_record: null argument"); return KCRN_E_ARG; }
     if (with_value) {
         KCRN_TRY(need_x(h, "kcrn_step_record"));
         KCRN_TRY(enqueue_value(h, h->scal + 0));
     }
-    double *r = h->rec_host;
-    int32_t *ri = reinterpret_cast<int32_t *>(r + 8);
-    KCRN_CUDA(cudaMemcpyAsync(r + 0, h->scal + 0, sizeof(double), cudaMemcpyDeviceToHost, s));
-    KCRN_CUDA(cudaMemcpyAsync(r + 1, h->sub + kMaxM, sizeof(double) * 4, cudaMemcpyDeviceToHost, s));
-    KCRN_CUDA(cudaMemcpyAsync(r + 5, h->bet, sizeof(double), cudaMemcpyDeviceToHost, s));
-    KCRN_CUDA(cudaMemcpyAsync(r + 6, h->scal + 3, sizeof(double), cudaMemcpyDeviceToHost, s));
-    KCRN_CUDA(cudaMemcpyAsync(ri, h->info, sizeof(int32_t) * 8, cudaMemcpyDeviceToHost, s));
-    KCRN_CUDA(cudaStreamSynchronize(s));
-    h->counters[7] += (int64_t)(sizeof(double) * 7 + sizeof(int32_t) * 8);
-    rec8_host[0] = r[0];           // value at the current x
-    rec8_host[1] = r[2];           // model decrease
-    rec8_host[2] = r[1];           // r
-    rec8_host[3] = r[3];           // Newton iterations
-    rec8_host[4] = r[4];           // status
-    rec8_host[5] = (double)ri[0];  // m_eff
-    rec8_host[6] = r[5];           // |g|
-    rec8_host[7] = (double)ri[3];  // operator applications of the last Lanczos run
-    rec12_host[8] = r[6];          // |x_trial - x| of the last kcrn_trial_point
-    rec12_host[9] = (double)ri[1]; // basis columns written
-    rec12_host[10] = (double)ri[2];// breakdown flag
-    rec12_host[11] = 0.0;
-    return KCRN_OK;
+    KCRN_TRY(launch_record(h));
+    return read_step_record(h, rec12_host);
 }
 
 int kcrn_hessian_dense(kcrn_handle h, double *out_dev) {

@@ -80,7 +80,9 @@ __global__ void __launch_bounds__(32) cubic_kernel(const double *__restrict__ al
                                                    const int32_t *__restrict__ info,
                                                    const double *__restrict__ gnorm_dev, double gnorm_arg,
                                                    double M, double r0, double eps, int it_max,
-                                                   double *__restrict__ s_out, double *__restrict__ scal_out) {
+                                                   double *__restrict__ s_out, double *__restrict__ scal_out,
+                                                   const double *__restrict__ params) {
+    if (params) { M = params[0]; r0 = params[1]; eps = params[2]; it_max = (int)params[3]; }   // whole-step graph
     __shared__ double sa[kMaxM], sb[kMaxM], sl[kMaxM], se[kMaxM], ss[kMaxM], sq[kMaxM], sli[kMaxM];
     const int m = info ? info[0] : m_arg;
     const double gnorm = gnorm_dev ? gnorm_dev[0] : gnorm_arg;
@@ -145,12 +147,13 @@ __global__ void __launch_bounds__(32) cubic_kernel(const double *__restrict__ al
 
 int launch_cubic(const double *alphas, const double *betas, int m, const int32_t *info, const double *gnorm_dev,
                  double gnorm, double M, double r0, double eps, int it_max, double *s_out, double *scal_out,
-                 cudaStream_t st) {
+                 cudaStream_t st, const double *params_dev) {
     if (m < 1 || m > kMaxM) {
         set_error("cubic sub-problem: m = %d outside [1, %d]", m, kMaxM);
         return KCRN_E_ARG;
     }
-    cubic_kernel<<<1, 32, 0, st>>>(alphas, betas, m, info, gnorm_dev, gnorm, M, r0, eps, it_max, s_out, scal_out);
+    cubic_kernel<<<1, 32, 0, st>>>(alphas, betas, m, info, gnorm_dev, gnorm, M, r0, eps, it_max, s_out, scal_out,
+                                   params_dev);
     KCRN_LAUNCH_CHECK();
     return KCRN_OK;
 }

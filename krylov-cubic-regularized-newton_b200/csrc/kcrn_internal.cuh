@@ -95,12 +95,6 @@ struct LanczosCtl {
     double last_beta;
 };
 
-struct Reduce {
-    double *partials = nullptr;  // [grid * width]
-    unsigned *ticket = nullptr;
-    int cap = 0;
-};
-
 }  // namespace kcrn
 
 struct kcrn_problem {
@@ -112,6 +106,9 @@ struct kcrn_problem {
     // caches at the current x
     bool have_x = false;
     double *x_cur = nullptr;                       // [d]
+    double *x_base = nullptr;                      // [d] iterate the trial points of the running step start from
+    double *step_params = nullptr;                 // [4] {M, r0, eps, it_max} of the next sub-problem solve (device)
+    bool have_base = false;
     double *Ax = nullptr, *D = nullptr, *resid = nullptr, *ell = nullptr;  // [n]
     // sweep temporaries
     double *t = nullptr;        // [n]   D .* (A v)
@@ -131,13 +128,11 @@ struct kcrn_problem {
     // reductions
     double *red_partials = nullptr;
     unsigned *red_ticket = nullptr;   // [8]
-    int vec_grid = 0, vec_elems = 1, row_grid = 0;
-    // pinned staging for the host-buffer entry points
-    double *stage_host = nullptr;
-    size_t stage_bytes = 0;
+    int vec_grid = 0, vec_elems = 1;
+    // device staging for the host-buffer entry points
     double *x_stage = nullptr, *v_stage = nullptr, *o_stage = nullptr;  // [d] device
     // captured Lanczos graphs, keyed by (m, reorth)
-    struct GraphEntry { int m, reorth; cudaGraphExec_t exec; int64_t delta[8]; };
+    struct GraphEntry { int kind, m, reorth; cudaGraphExec_t exec; int64_t delta[8]; };   // kind 0: Lanczos, 1 / 2: first / repeated trial
     std::vector<GraphEntry> graphs;
     int64_t graph_delta[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int step_col = 0;           // column the step-wise Lanczos API is working on
@@ -180,7 +175,7 @@ int launch_axpy_basis(const double *x, const double *V, const double *s, int m, 
 // ----------------------------------------------------------------------------- kcrn_cubic.cu
 int launch_cubic(const double *alphas, const double *betas, int m, const int32_t *info,
                  const double *gnorm_dev, double gnorm, double M, double r0, double eps, int it_max,
-                 double *s_out, double *scal_out, cudaStream_t st);
+                 double *s_out, double *scal_out, cudaStream_t st, const double *params_dev);
 
 // ----------------------------------------------------------------------------- kcrn_nccl.cu
 int nccl_unique_id(void *out128);

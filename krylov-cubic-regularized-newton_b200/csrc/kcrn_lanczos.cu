@@ -292,6 +292,20 @@ __global__ void value_combine_kernel(const double *scal, double n_samples, doubl
     }
 }
 
+// the scalars of one trial, gathered into 12 consecutive doubles so that the host needs ONE copy:
+// {value, model decrease, r, Newton iterations, status, m_eff, |g|, operator applications, |x_trial - x|,
+//  basis columns written, breakdown flag, 0}
+__global__ void record_kernel(const double *__restrict__ scal, const double *__restrict__ sub_tail,
+                              const double *__restrict__ bet, const int32_t *__restrict__ info,
+                              double *__restrict__ rec) {
+    pdl_wait();
+    if (threadIdx.x == 0) {
+        rec[0] = scal[0]; rec[1] = sub_tail[1]; rec[2] = sub_tail[0]; rec[3] = sub_tail[2]; rec[4] = sub_tail[3];
+        rec[5] = (double)info[0]; rec[6] = bet[0]; rec[7] = (double)info[3]; rec[8] = scal[3];
+        rec[9] = (double)info[1]; rec[10] = (double)info[2]; rec[11] = 0.0;
+    }
+}
+
 // out = y / n + l2 u   (after the allreduce of a row-sharded transpose sweep)
 __global__ void scale_kernel(const double *__restrict__ y, const double *__restrict__ u, int64_t d,
                              double n_samples, double l2, double *__restrict__ out) {
@@ -434,6 +448,13 @@ int launch_sumsq(kcrn_problem *h, const double *a, int64_t len, double *out) {
 
 int launch_value_combine(kcrn_problem *h, double *out) {
     value_combine_kernel<<<1, 32, 0, h->stream>>>(h->scal, (double)h->n_global, h->l2, out);
+    KCRN_LAUNCH_CHECK();
+    h->counters[0] += 1;
+    return KCRN_OK;
+}
+
+int launch_record(kcrn_problem *h) {
+    record_kernel<<<1, 32, 0, h->stream>>>(h->scal, h->sub + kMaxM, h->bet, h->info, h->scal + 4);
     KCRN_LAUNCH_CHECK();
     h->counters[0] += 1;
     return KCRN_OK;

@@ -46,6 +46,8 @@ SIGNATURES = {
     "kcrn_axpy_basis": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "kcrn_trial_point": (c_int, [c_void_p, c_void_p, c_void_p]),
     "kcrn_step_record": (c_int, [c_void_p, c_int, POINTER(c_double)]),
+    "kcrn_krylov_trial": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_double, c_double, c_int, c_void_p,
+                                  POINTER(c_double)]),
     "kcrn_hessian_dense": (c_int, [c_void_p, c_void_p]),
     "kcrn_partial_gradient": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "kcrn_partial_hessian": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),

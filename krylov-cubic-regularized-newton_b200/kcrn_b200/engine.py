@@ -234,6 +234,18 @@ class Engine:
         check(self.lib.kcrn_trial_point(self.h, self._vec(x, self.d, "x").data_ptr(), out.data_ptr()))
         return out
 
+    def krylov_trial(self, first: bool, m: int, reorth: bool, M: float, r0: float, eps: float = 1e-8,
+                     it_max: int = 100, x_out=None):
+        """One trial of a Krylov-CRN step as one CUDA graph + one D2H (kcrn_krylov_trial).  Returns the step record
+        tuple of ``step_record``; ``x_out`` receives the trial point."""
+        self._use_stream()
+        check(self.lib.kcrn_krylov_trial(self.h, int(bool(first)), int(m), int(bool(reorth)), float(M), float(r0),
+                                         float(eps), int(it_max), _ptr(x_out), self._rec))
+        self._m = int(m)
+        self._views = None
+        r = self._rec
+        return r[0], r[1], r[2], int(r[3]), int(r[4]), int(r[5]), r[6], int(r[7]), r[8]
+
     def step_record(self, with_value: bool = True):
         """(value, model_decrease, r, newton_its, status, m_eff, |g|, hvps, |x_trial - x|) -- one D2H, synchronous."""
         self._use_stream()

@@ -137,17 +137,20 @@ class Cubic_Krylov_LS(Optimizer):
             self.value = loss.value(self.x)
         else:
             loss._forward(self.x)                       # no-op when the caches already belong to x
-        eng.gradient(keep_internal=True)                # loss.gradient(x)                       cubic.py:270
-        loss.calls["gradient"] += 1
-        eng.lanczos(self.subspace_dim, self.reorth)     # Lanczos(hess_vec_prod, grad, m)        cubic.py:273-275
-        loss.calls["hess_vec_prod"] += self.subspace_dim
         M = self.reg_coef * self.beta                   # try a smaller M first                  cubic.py:286
         tries = 0
+        first = True
         while True:
-            eng.cubic(M, self.r0, self.solver_eps, 100)  # cubic_solver_root(...)                cubic.py:289-290
-            x_new = eng.trial_point(self.x)              # x + V @ s                             cubic.py:291
-            eng.set_x(x_new)                             # loss.value(x_new)                     cubic.py:292
-            value_new, decrease, r, its, status, m_eff, gnorm, hvps, dx = eng.step_record(True)
+            # first trial: gradient (cubic.py:270), Lanczos (:273-275), sub-problem (:289-290), x + V s (:291),
+            # value at the trial point (:292) -- one CUDA graph and one device-to-host copy; re-trials with a
+            # larger M (:298-302) replay only the second half
+            x_new = eng.new_vector()
+            value_new, decrease, r, its, status, m_eff, gnorm, hvps, dx = eng.krylov_trial(
+                first, self.subspace_dim, self.reorth, M, self.r0, self.solver_eps, 100, x_out=x_new)
+            if first:
+                loss.calls["gradient"] += 1
+                loss.calls["hess_vec_prod"] += self.subspace_dim
+                first = False
             loss.calls["value"] += 1
             loss.calls["forward"] += 1
             if status == KCRN_E_NOTPD:
