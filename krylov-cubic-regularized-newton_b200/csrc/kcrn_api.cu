@@ -83,15 +83,19 @@ int enqueue_value(kcrn_problem *h, double *out) {
 int enqueue_lanczos(kcrn_problem *h, int m, int reorth) {
     KCRN_TRY(launch_lanczos_init(h, m));
     for (int slot = 0; slot < m; ++slot) {
+        // rows sweep: t = D (A v), basis column, and alpha = v'Hv one sweep early (so that the column sweep can
+        // form w' = Hv - beta v_prev - alpha v and beta = |w'| itself: two kernels per Lanczos step)
         KCRN_TRY(launch_rows_lanczos(h));
         if (h->world > 1) {
             KCRN_TRY(launch_cols_raw(h, h->t, h->ypart));
-            KCRN_TRY(nccl_allreduce_sum(h, h->ypart, h->d));
-            KCRN_TRY(launch_lanczos_post(h, h->ypart, 1));
-        } else {
-            KCRN_TRY(launch_cols_lanczos(h));
+            KCRN_CUDA(cudaMemcpyAsync(h->ypart + h->d, h->scal + 16, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+            KCRN_TRY(nccl_allreduce_sum(h, h->ypart, h->d + 1));
+            KCRN_CUDA(cudaMemcpyAsync(h->scal + 16, h->ypart + h->d, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+            KCRN_TRY(launch_lanczos_post_sharded(h, h->ypart, reorth));
+        } else if (slot + 1 < m) {
+            KCRN_TRY(launch_cols_lanczos(h, reorth ? 0 : 1));
         }
-        if (slot + 1 < m) KCRN_TRY(launch_lanczos_update(h, reorth));
+        if (reorth && slot + 1 < m) KCRN_TRY(launch_lanczos_update(h, 1, 1));
     }
     return launch_lanczos_finish(h);
 }
@@ -203,7 +207,7 @@ int kcrn_create(kcrn_handle *out, int64_t n_rows, int64_t n_cols, int64_t nnz, c
         KCRN_CUDA(cudaMalloc(&h->resid, sizeof(double) * n));
         KCRN_CUDA(cudaMalloc(&h->ell, sizeof(double) * n));
         KCRN_CUDA(cudaMalloc(&h->t, sizeof(double) * n));
-        KCRN_CUDA(cudaMalloc(&h->ypart, sizeof(double) * d));
+        KCRN_CUDA(cudaMalloc(&h->ypart, sizeof(double) * (d + 1)));
         KCRN_CUDA(cudaMalloc(&h->w, sizeof(double) * d));
         KCRN_CUDA(cudaMalloc(&h->wp, sizeof(double) * d));
         KCRN_CUDA(cudaMalloc(&h->g, sizeof(double) * d));
@@ -215,12 +219,12 @@ int kcrn_create(kcrn_handle *out, int64_t n_rows, int64_t n_cols, int64_t nnz, c
         KCRN_CUDA(cudaMalloc(&h->coef, sizeof(double) * (kMaxM + 2)));
         KCRN_CUDA(cudaMalloc(&h->coef2, sizeof(double) * (kMaxM + 2)));
         KCRN_CUDA(cudaMalloc(&h->sub, sizeof(double) * (kMaxM + 8)));
-        KCRN_CUDA(cudaMalloc(&h->scal, sizeof(double) * 16));
+        KCRN_CUDA(cudaMalloc(&h->scal, sizeof(double) * 32));
         KCRN_CUDA(cudaMalloc(&h->ctl, sizeof(LanczosCtl)));
         KCRN_CUDA(cudaMalloc(&h->info, sizeof(int32_t) * 8));
         KCRN_CUDA(cudaMalloc(&h->red_ticket, sizeof(unsigned) * 8));
         KCRN_CUDA(cudaMemsetAsync(h->red_ticket, 0, sizeof(unsigned) * 8, s));
-        KCRN_CUDA(cudaMemsetAsync(h->scal, 0, sizeof(double) * 16, s));
+        KCRN_CUDA(cudaMemsetAsync(h->scal, 0, sizeof(double) * 32, s));
         KCRN_CUDA(cudaMemsetAsync(h->sub, 0, sizeof(double) * (kMaxM + 8), s));
         KCRN_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(LanczosCtl), s));
         KCRN_CUDA(cudaMemsetAsync(h->info, 0, sizeof(int32_t) * 8, s));
@@ -465,7 +469,7 @@ int kcrn_lanczos_current(kcrn_handle h, const double **cur_dev) {
 int kcrn_lanczos_feed(kcrn_handle h, const double *hv_dev, int *finished_host) {
     if (!h || !hv_dev || !finished_host) { set_error("kcrn_lanczos_feed: null argument"); return KCRN_E_ARG; }
     KCRN_TRY(launch_lanczos_post(h, hv_dev, 0));
-    KCRN_TRY(launch_lanczos_update(h, h->cur_reorth));   // no-op on the device once the last alpha is in
+    KCRN_TRY(launch_lanczos_update(h, h->cur_reorth, 0));   // no-op on the device once the last alpha is in
     KCRN_TRY(launch_normalise_current(h));
     KCRN_TRY(launch_lanczos_finish(h));
     int32_t info[8];

@@ -95,6 +95,26 @@ struct LanczosCtl {
     double last_beta;
 };
 
+#ifdef __CUDACC__
+// Bookkeeping of cubic.py:98-109 once beta = |w'| of column `col` is known (executed by ONE thread).
+__device__ inline void lanczos_advance(LanczosCtl *c, double *bet, double beta) {
+    const int col = c->col, m = c->m;
+    c->last_beta = beta;
+    if (fabs(beta) < 1e-6) {               // cubic.py:98 -- absolute test
+        c->broke = 1;
+        if (col < m - 2) { c->m_eff = col + 1; c->store_idx = col; }   // cubic.py:105-108
+        else { c->m_eff = m; c->store_idx = m - 1; }
+        c->redo = 1;                       // cubic.py:109 re-applies the operator to the same v
+        c->final_ = 1;
+    } else {
+        bet[col + 1] = beta;
+        c->col = col + 1;
+        c->nvalid = col + 2;
+        if (col + 1 == m - 1) { c->final_ = 1; c->store_idx = m - 1; }
+    }
+}
+#endif
+
 }  // namespace kcrn
 
 struct kcrn_problem {
@@ -158,14 +178,15 @@ int launch_rows_weighted(kcrn_problem *h, const double *v);           // t = D .
 int launch_rows_lanczos(kcrn_problem *h);                             // same, source picked by ctl
 int launch_cols_raw(kcrn_problem *h, const double *src, double *out); // out = A' src
 int launch_cols_scaled(kcrn_problem *h, const double *src, const double *u, double *out);  // A' src / n + l2 u
-int launch_cols_lanczos(kcrn_problem *h);                             // w, alpha fused
+int launch_cols_lanczos(kcrn_problem *h, int update_ctl);             // w' and beta fused
 int launch_derive_from_Ax(kcrn_problem *h);
 
 // ----------------------------------------------------------------------------- kcrn_lanczos.cu
 int lanczos_alloc(kcrn_problem *h, int m);
 int launch_lanczos_init(kcrn_problem *h, int m);      // ctl, alphas, bet reset; bet[0] = |g|
 int launch_lanczos_post(kcrn_problem *h, const double *hv_or_raw, int raw);  // epilogue after allreduce / generic feed
-int launch_lanczos_update(kcrn_problem *h, int reorth);
+int launch_lanczos_update(kcrn_problem *h, int reorth, int fused);
+int launch_lanczos_post_sharded(kcrn_problem *h, const double *y_allreduced, int reorth);
 int launch_normalise_current(kcrn_problem *h);        // V[col] = src / bet[col] outside the fused sweep
 int launch_sum(kcrn_problem *h, const double *a, int64_t len, double scale, double *out);  // deterministic sum
 int launch_axpy_basis(const double *x, const double *V, const double *s, int m, const int32_t *info,

@@ -36,6 +36,9 @@ struct VecParams {
     double *red_partials;
     unsigned *red_ticket;
     int stage, m, raw;
+    int from_wp;               // reorth stage 1 inside the fused loop: w' was already formed by the column sweep
+    const double *alpha_raw;   // row-sharded fused loop: {sum_i t_i (Av)_i (allreduced), |v|^2}
+    double inv_n;
     double n_samples, l2;
     int32_t *info;
 };
@@ -146,6 +149,48 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_post_kernel(VecParams P) 
     }
 }
 
+// Row-sharded fused loop, after the allreduce of {A't, sum_i t_i (Av)_i}: alpha = v'Hv, w' = y/n + l2 v -
+// beta_prev v_prev - alpha v, beta = |w'|, then the bookkeeping of cubic.py:98-109 -- replicated on every rank.
+template <int E>
+__global__ void __launch_bounds__(kVecThreads) lanczos_post_sharded_kernel(VecParams P) {
+    __shared__ double sh[kVecThreads / 32];
+    __shared__ int s_last;
+    pdl_wait();
+    pdl_trigger();
+    if (P.ctl->done) return;
+    const int col = P.ctl->col, store_idx = P.ctl->store_idx;
+    const bool final_ = P.ctl->final_ != 0;
+    const double alpha = __dadd_rn(quotient(P.alpha_raw[0], P.n_samples, P.inv_n), __dmul_rn(P.l2, P.alpha_raw[1]));
+    const double *v = P.V + (size_t)col * P.d;
+    const bool subtract = col > 0;
+    const double *vpre = subtract ? P.V + (size_t)(col - 1) * P.d : nullptr;
+    const double beta_prev = subtract ? P.bet[col] : 0.0;
+    const int64_t base = (int64_t)blockIdx.x * (kVecThreads * E) + threadIdx.x;
+    double loc = 0.0;
+    if (!final_) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int64_t c = base + (int64_t)e * kVecThreads;
+            if (c < P.d) {
+                const double vc = v[c];
+                double hv = __dadd_rn(quotient(P.w_in[c], P.n_samples, P.inv_n), __dmul_rn(P.l2, vc));
+                if (subtract) hv = __dsub_rn(hv, __dmul_rn(beta_prev, vpre[c]));
+                hv = __dsub_rn(hv, __dmul_rn(alpha, vc));
+                P.wp[c] = hv;
+                loc = fma(hv, hv, loc);
+            }
+        }
+    }
+    double tot = 0.0;
+    if (!grid_sum(loc, P.red_partials, P.red_ticket, sh, &s_last, &tot)) return;
+    if (threadIdx.x == 0) {
+        P.alphas[final_ ? store_idx : col] = alpha;
+        P.ctl->hvps += 1;
+        if (final_) P.ctl->done = 1;
+        else if (P.stage == 0) lanczos_advance(P.ctl, P.bet, sqrt(tot));   // stage 1: re-orthogonalisation follows
+    }
+}
+
 template <int E>
 __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P) {
     pdl_wait();
@@ -159,7 +204,13 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P
     const int nv = col + 1;  // basis columns built so far
     const int64_t base = (int64_t)blockIdx.x * (kVecThreads * E) + threadIdx.x;
     double x[E];
-    if (P.stage <= 1) {
+    if (P.stage == 1 && P.from_wp) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int64_t c = base + (int64_t)e * kVecThreads;
+            x[e] = c < P.d ? P.wp[c] : 0.0;
+        }
+    } else if (P.stage <= 1) {
         const double alpha = P.alphas[col];
         const double *v = P.V + (size_t)col * P.d;
 #pragma unroll
@@ -199,24 +250,7 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P
         for (int e = 0; e < E; ++e) loc = fma(x[e], x[e], loc);
         double tot = 0.0;
         if (!grid_sum(loc, P.red_partials, P.red_ticket, sh, &s_last, &tot)) return;
-        if (threadIdx.x == 0) {
-            LanczosCtl *c = P.ctl;
-            const double beta = sqrt(tot);
-            const int m = c->m;
-            c->last_beta = beta;
-            if (fabs(beta) < 1e-6) {       // cubic.py:98 -- absolute test
-                c->broke = 1;
-                if (col < m - 2) { c->m_eff = col + 1; c->store_idx = col; }   // cubic.py:105-108
-                else { c->m_eff = m; c->store_idx = m - 1; }
-                c->redo = 1;               // cubic.py:109 re-applies the operator to the same v
-                c->final_ = 1;
-            } else {
-                P.bet[col + 1] = beta;
-                c->col = col + 1;
-                c->nvalid = col + 2;
-                if (col + 1 == m - 1) { c->final_ = 1; c->store_idx = m - 1; }
-            }
-        }
+        if (threadIdx.x == 0) lanczos_advance(P.ctl, P.bet, sqrt(tot));
         return;
     }
 
@@ -409,11 +443,23 @@ int launch_lanczos_post(kcrn_problem *h, const double *hv_or_raw, int raw) {
     return KCRN_OK;
 }
 
-int launch_lanczos_update(kcrn_problem *h, int reorth) {
+int launch_lanczos_post_sharded(kcrn_problem *h, const double *y_allreduced, int reorth) {
+    VecParams P = base_params(h);
+    P.w_in = y_allreduced; P.alpha_raw = h->scal + 16; P.inv_n = 1.0 / P.n_samples; P.stage = reorth ? 1 : 0;
+    P.red_ticket = h->red_ticket + 2;
+    if (h->vec_elems == 4) KCRN_CUDA(launch_kernel(lanczos_post_sharded_kernel<4>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
+    else KCRN_CUDA(launch_kernel(lanczos_post_sharded_kernel<1>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
+    h->counters[0] += 1;
+    return KCRN_OK;
+}
+
+// reorth = 0: stage 0 (w' = w - alpha v, beta) -- the step-wise API; reorth = 1: the three Gram-Schmidt stages;
+// fused = 1: w' already holds w - alpha v (formed by the column sweep / the sharded post kernel)
+int launch_lanczos_update(kcrn_problem *h, int reorth, int fused) {
     const int first = reorth ? 1 : 0, last = reorth ? 3 : 0;
     for (int stage = first; stage <= last; ++stage) {
         VecParams P = base_params(h);
-        P.w_in = h->w; P.stage = stage;
+        P.w_in = h->w; P.stage = stage; P.from_wp = fused;
         P.coef_in = stage == 2 ? h->coef : h->coef2;
         P.coef_out = stage == 1 ? h->coef : h->coef2;
         P.red_ticket = h->red_ticket + 1;

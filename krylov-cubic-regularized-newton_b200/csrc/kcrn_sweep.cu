@@ -121,10 +121,10 @@ namespace {
 enum SweepMode {
     kRowsForward = 0,   // A x, sigma, weights, residual, loss terms      (loss.py:215-232, 266-277, 296-297)
     kRowsWeighted = 1,  // t = D .* (A v)                                 (loss.py:299-301)
-    kRowsLanczos = 2,   // same; v = source / beta taken from the control block, V[col] written on the side
+    kRowsLanczos = 2,   // same; v = source / beta from the control block, V[col] on the side, alpha = v'Hv (cubic.py:94,109)
     kColsRaw = 3,       // out = A' src                                   (row-sharded runs, before the allreduce)
     kColsScaled = 4,    // out = A' src / n (+ l2 u)                      (loss.py:227-229, :302)
-    kColsLanczos = 5,   // w = A' t / n + l2 v - beta v_prev ; alpha = v . w   (loss.py:302 + cubic.py:93-94,109)
+    kColsLanczos = 5,   // w' = A' t / n + l2 v - beta v_prev - alpha v ; beta = |w'|   (loss.py:302 + cubic.py:93-97)
 };
 
 struct SweepParams {
@@ -148,18 +148,22 @@ struct SweepParams {
     // Lanczos
     LanczosCtl *ctl;
     double *V;
-    const double *g, *wp, *bet;
+    const double *g, *wp;
+    double *bet;
     double *w, *alphas;
     int64_t d;
-    double *red_partials;          // [ntiles] alpha contribution of every tile
+    double *red_partials;          // [2 * ntiles] per-tile contributions to the reduction of the pass
     unsigned *red_ticket;
+    int alpha_mode;                // rows-Lanczos: 0 = finish alpha here, 1 = export the raw sums (row-sharded runs)
+    double *alpha_raw;             // [2] raw sums {sum_i t_i (Av)_i, |v|^2} for alpha_mode 1
+    int update_ctl;                // cols-Lanczos: 1 = finish beta and advance the recurrence here
 };
 
 struct SweepState {
     const double *src = nullptr;
     double beta = 1.0, rinv = 1.0;        // gathered values are divided by beta (rows-Lanczos)
     const double *vcol = nullptr, *vpre = nullptr;
-    double beta_prev = 0.0;
+    double beta_prev = 0.0, alpha = 0.0;
     bool subtract = false;
 };
 
@@ -179,8 +183,15 @@ __device__ __forceinline__ void finish_segment(const SweepParams &P, const Sweep
         P.D[seg] = __dmul_rn(a, 1.0 - a);
         P.resid[seg] = a - op0;
         P.ell[seg] = __dsub_rn(__dmul_rn(1.0 - op0, sum), log_sigmoid(sum));
-    } else if constexpr (MODE == kRowsWeighted || MODE == kRowsLanczos) {
+    } else if constexpr (MODE == kRowsWeighted) {
         P.out[seg] = __dmul_rn(op0, sum);
+    } else if constexpr (MODE == kRowsLanczos) {
+        // t = D (Av); its share of alpha = v'Hv = sum_i D_i (Av)_i^2 / n (+ l2 |v|^2) is taken here, one sweep early
+        const double t = __dmul_rn(op0, sum);
+        P.out[seg] = t;
+        const double prod = __dmul_rn(t, sum);
+        if (lseg >= 0) P.longdot[lseg] = prod;  // long segments finish on whichever CTA arrives last:
+        else acc += prod;                       // keep their share out of the per-tile sums
     } else if constexpr (MODE == kColsRaw) {
         P.out[seg] = sum;
     } else if constexpr (MODE == kColsScaled) {
@@ -190,10 +201,11 @@ __device__ __forceinline__ void finish_segment(const SweepParams &P, const Sweep
     } else {  // kColsLanczos
         double hv = __dadd_rn(quotient(sum, P.n_samples, P.inv_n), __dmul_rn(P.l2, op0));
         if (S.subtract) hv = __dsub_rn(hv, __dmul_rn(S.beta_prev, op1));
+        hv = __dsub_rn(hv, __dmul_rn(S.alpha, op0));          // w' = Hv - beta v_prev - alpha v   (cubic.py:93-96)
         P.w[seg] = hv;
-        const double prod = __dmul_rn(op0, hv);
-        if (lseg >= 0) P.longdot[lseg] = prod;  // long segments finish on whichever CTA arrives last:
-        else acc += prod;                       // keep their share out of the per-tile sums
+        const double prod = __dmul_rn(hv, hv);                // share of beta^2 = |w'|^2            (cubic.py:97)
+        if (lseg >= 0) P.longdot[lseg] = prod;
+        else acc += prod;
     }
 }
 
@@ -270,6 +282,8 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         if (P.ctl->done) return;
         col = P.ctl->col;
         redo = P.ctl->redo;
+        final_ = P.ctl->final_ != 0;
+        store_idx = P.ctl->store_idx;
         if (redo) {
             S.src = P.V + (size_t)col * P.d;
         } else {
@@ -281,10 +295,9 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
     if constexpr (MODE == kColsLanczos) {
         if (P.ctl->done) return;
         col = P.ctl->col;
-        final_ = P.ctl->final_ != 0;
-        store_idx = P.ctl->store_idx;
+        S.alpha = P.alphas[col];
         S.vcol = P.V + (size_t)col * P.d;
-        if (col > 0 && !final_) {
+        if (col > 0) {
             S.subtract = true;
             S.vpre = P.V + (size_t)(col - 1) * P.d;
             S.beta_prev = P.bet[col];
@@ -382,16 +395,57 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
     }
 
     if constexpr (MODE == kRowsLanczos) {
-        // side job: store the normalised vector as basis column `col` (the sweep divided on the fly)
-        if (!redo) {
+        // side job: store the normalised vector as basis column `col` (the sweep divided on the fly); |v|^2 for
+        // the l2 part of alpha
+        double vsq = 0.0;
+        if (!redo || P.l2 != 0.0) {
             double *vout = P.V + (size_t)col * P.d;
-            for (int64_t c = (int64_t)blockIdx.x * blockDim.x + tid; c < P.d; c += (int64_t)gridDim.x * blockDim.x)
-                vout[c] = quotient(__ldg(S.src + c), S.beta, S.rinv);
+            for (int64_t c = (int64_t)blockIdx.x * blockDim.x + tid; c < P.d; c += (int64_t)gridDim.x * blockDim.x) {
+                const double vc = quotient(__ldg(S.src + c), S.beta, S.rinv);
+                if (!redo) vout[c] = vc;
+                vsq = fma(vc, vc, vsq);
+            }
+        }
+        // alpha = v'Hv: threads -> tile (fixed order) -> the last CTA adds the tile sums in tile order
+        __syncthreads();
+        const double mine = cta_sum_to_thread0(acc, sred);
+        __syncthreads();
+        const double mine2 = cta_sum_to_thread0(vsq, sred);
+        if (tid == 0) {
+            P.red_partials[blockIdx.x] = mine;
+            P.red_partials[gridDim.x + blockIdx.x] = mine2;
+            __threadfence();
+            s_last = atomicInc(P.red_ticket, gridDim.x - 1) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            double tot = 0.0, tot2 = 0.0;
+            for (int i = tid; i < (int)gridDim.x; i += kSweepThreads) {
+                tot += __ldcg(P.red_partials + i);
+                tot2 += __ldcg(P.red_partials + gridDim.x + i);
+            }
+            for (int i = tid; i < P.nlong; i += kSweepThreads) tot += __ldcg(P.longdot + i);
+            __syncthreads();
+            const double s1 = cta_sum_to_thread0(tot, sred);
+            __syncthreads();
+            const double s2 = cta_sum_to_thread0(tot2, sred);
+            if (tid == 0) {
+                if (P.alpha_mode == 0) {
+                    const double alpha = __dadd_rn(quotient(s1, P.n_samples, P.inv_n), __dmul_rn(P.l2, s2));
+                    P.alphas[final_ ? store_idx : col] = alpha;
+                    P.ctl->hvps += 1;
+                    if (final_) P.ctl->done = 1;           // cubic.py:109: the last alpha needs no further vector
+                } else {
+                    P.alpha_raw[0] = s1;                   // summed over the ranks together with A't
+                    P.alpha_raw[1] = s2;
+                }
+            }
         }
     }
 
     if constexpr (MODE == kColsLanczos) {
-        // alpha = v . w : threads -> tile (fixed order) -> the last CTA adds the tile sums in tile order
+        // beta^2 = |w'|^2: threads -> tile (fixed order) -> the last CTA adds the tile sums in tile order
         __syncthreads();
         const double mine = cta_sum_to_thread0(acc, sred);
         if (tid == 0) {
@@ -400,18 +454,14 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
             s_last = atomicInc(P.red_ticket, gridDim.x - 1) == gridDim.x - 1;
         }
         __syncthreads();
-        if (s_last) {
+        if (s_last && P.update_ctl) {
             __threadfence();
             double tot = 0.0;
             for (int i = tid; i < (int)gridDim.x; i += kSweepThreads) tot += __ldcg(P.red_partials + i);
             for (int i = tid; i < P.nlong; i += kSweepThreads) tot += __ldcg(P.longdot + i);
             __syncthreads();
-            const double alpha = cta_sum_to_thread0(tot, sred);
-            if (tid == 0) {
-                P.alphas[final_ ? store_idx : col] = alpha;
-                P.ctl->hvps += 1;
-                if (final_) P.ctl->done = 1;
-            }
+            const double bsq = cta_sum_to_thread0(tot, sred);
+            if (tid == 0) lanczos_advance(P.ctl, P.bet, sqrt(bsq));
         }
     }
 }
@@ -463,6 +513,9 @@ int launch_rows_weighted(kcrn_problem *h, const double *v) {
 int launch_rows_lanczos(kcrn_problem *h) {
     SweepParams P{};
     P.D = h->D; P.out = h->t; P.ctl = h->ctl; P.V = h->V; P.g = h->g; P.wp = h->wp; P.bet = h->bet; P.d = h->d;
+    P.alphas = h->alphas; P.n_samples = (double)h->n_global; P.inv_n = 1.0 / P.n_samples; P.l2 = h->l2;
+    P.red_partials = h->red_partials; P.red_ticket = h->red_ticket + 7;
+    P.alpha_mode = h->world > 1 ? 1 : 0; P.alpha_raw = h->scal + 16;
     h->counters[3] += 1;
     return launch<kRowsLanczos>(h, h->csr, P);
 }
@@ -482,9 +535,10 @@ int launch_cols_scaled(kcrn_problem *h, const double *src, const double *u, doub
     return launch<kColsScaled>(h, h->csc, P);
 }
 
-int launch_cols_lanczos(kcrn_problem *h) {
+int launch_cols_lanczos(kcrn_problem *h, int update_ctl) {
     SweepParams P{};
-    P.src = h->t; P.ctl = h->ctl; P.V = h->V; P.bet = h->bet; P.w = h->w; P.alphas = h->alphas; P.d = h->d;
+    P.src = h->t; P.ctl = h->ctl; P.V = h->V; P.bet = h->bet; P.w = h->wp; P.alphas = h->alphas; P.d = h->d;
+    P.update_ctl = update_ctl;
     P.n_samples = (double)h->n_global; P.inv_n = 1.0 / P.n_samples; P.l2 = h->l2;
     P.red_partials = h->red_partials; P.red_ticket = h->red_ticket + 0;
     h->counters[4] += 1;
