@@ -88,9 +88,7 @@ int enqueue_lanczos(kcrn_problem *h, int m, int reorth) {
         KCRN_TRY(launch_rows_lanczos(h));
         if (h->world > 1) {
             KCRN_TRY(launch_cols_raw(h, h->t, h->ypart));
-            KCRN_CUDA(cudaMemcpyAsync(h->ypart + h->d, h->scal + 16, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-            KCRN_TRY(nccl_allreduce_sum(h, h->ypart, h->d + 1));
-            KCRN_CUDA(cudaMemcpyAsync(h->scal + 16, h->ypart + h->d, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+            KCRN_TRY(nccl_allreduce_sum(h, h->ypart, (h->d + 2) & ~(int64_t)1));   // even count: 16-byte multiple
             KCRN_TRY(launch_lanczos_post_sharded(h, h->ypart, reorth));
         } else if (slot + 1 < m) {
             KCRN_TRY(launch_cols_lanczos(h, reorth ? 0 : 1));
@@ -207,7 +205,8 @@ int kcrn_create(kcrn_handle *out, int64_t n_rows, int64_t n_cols, int64_t nnz, c
         KCRN_CUDA(cudaMalloc(&h->resid, sizeof(double) * n));
         KCRN_CUDA(cudaMalloc(&h->ell, sizeof(double) * n));
         KCRN_CUDA(cudaMalloc(&h->t, sizeof(double) * n));
-        KCRN_CUDA(cudaMalloc(&h->ypart, sizeof(double) * (d + 1)));
+        KCRN_CUDA(cudaMalloc(&h->ypart, sizeof(double) * (d + 2)));   // + sum_i t_i (Av)_i of the fused Lanczos step (+ pad)
+        KCRN_CUDA(cudaMemsetAsync(h->ypart, 0, sizeof(double) * (d + 2), s));
         KCRN_CUDA(cudaMalloc(&h->w, sizeof(double) * d));
         KCRN_CUDA(cudaMalloc(&h->wp, sizeof(double) * d));
         KCRN_CUDA(cudaMalloc(&h->g, sizeof(double) * d));

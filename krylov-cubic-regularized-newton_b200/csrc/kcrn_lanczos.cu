@@ -37,7 +37,7 @@ struct VecParams {
     unsigned *red_ticket;
     int stage, m, raw;
     int from_wp;               // reorth stage 1 inside the fused loop: w' was already formed by the column sweep
-    const double *alpha_raw;   // row-sharded fused loop: {sum_i t_i (Av)_i (allreduced), |v|^2}
+    const double *alpha_raw, *alpha_raw2;   // row-sharded fused loop: sum_i t_i (Av)_i (allreduced) and |v|^2
     double inv_n;
     double n_samples, l2;
     int32_t *info;
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_post_sharded_kernel(VecPa
     if (P.ctl->done) return;
     const int col = P.ctl->col, store_idx = P.ctl->store_idx;
     const bool final_ = P.ctl->final_ != 0;
-    const double alpha = __dadd_rn(quotient(P.alpha_raw[0], P.n_samples, P.inv_n), __dmul_rn(P.l2, P.alpha_raw[1]));
+    const double alpha = __dadd_rn(quotient(P.alpha_raw[0], P.n_samples, P.inv_n), __dmul_rn(P.l2, P.alpha_raw2[0]));
     const double *v = P.V + (size_t)col * P.d;
     const bool subtract = col > 0;
     const double *vpre = subtract ? P.V + (size_t)(col - 1) * P.d : nullptr;
@@ -445,7 +445,7 @@ int launch_lanczos_post(kcrn_problem *h, const double *hv_or_raw, int raw) {
 
 int launch_lanczos_post_sharded(kcrn_problem *h, const double *y_allreduced, int reorth) {
     VecParams P = base_params(h);
-    P.w_in = y_allreduced; P.alpha_raw = h->scal + 16; P.inv_n = 1.0 / P.n_samples; P.stage = reorth ? 1 : 0;
+    P.w_in = y_allreduced; P.alpha_raw = h->ypart + h->d; P.alpha_raw2 = h->scal + 17; P.inv_n = 1.0 / P.n_samples; P.stage = reorth ? 1 : 0;
     P.red_ticket = h->red_ticket + 2;
     if (h->vec_elems == 4) KCRN_CUDA(launch_kernel(lanczos_post_sharded_kernel<4>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
     else KCRN_CUDA(launch_kernel(lanczos_post_sharded_kernel<1>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));

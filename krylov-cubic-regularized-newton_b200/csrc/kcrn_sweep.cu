@@ -155,7 +155,7 @@ struct SweepParams {
     double *red_partials;          // [2 * ntiles] per-tile contributions to the reduction of the pass
     unsigned *red_ticket;
     int alpha_mode;                // rows-Lanczos: 0 = finish alpha here, 1 = export the raw sums (row-sharded runs)
-    double *alpha_raw;             // [2] raw sums {sum_i t_i (Av)_i, |v|^2} for alpha_mode 1
+    double *alpha_raw, *alpha_raw2; // raw sums sum_i t_i (Av)_i (allreduced later) and |v|^2 for alpha_mode 1
     int update_ctl;                // cols-Lanczos: 1 = finish beta and advance the recurrence here
 };
 
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
                     if (final_) P.ctl->done = 1;           // cubic.py:109: the last alpha needs no further vector
                 } else {
                     P.alpha_raw[0] = s1;                   // summed over the ranks together with A't
-                    P.alpha_raw[1] = s2;
+                    P.alpha_raw2[0] = s2;
                 }
             }
         }
@@ -515,7 +515,7 @@ int launch_rows_lanczos(kcrn_problem *h) {
     P.D = h->D; P.out = h->t; P.ctl = h->ctl; P.V = h->V; P.g = h->g; P.wp = h->wp; P.bet = h->bet; P.d = h->d;
     P.alphas = h->alphas; P.n_samples = (double)h->n_global; P.inv_n = 1.0 / P.n_samples; P.l2 = h->l2;
     P.red_partials = h->red_partials; P.red_ticket = h->red_ticket + 7;
-    P.alpha_mode = h->world > 1 ? 1 : 0; P.alpha_raw = h->scal + 16;
+    P.alpha_mode = h->world > 1 ? 1 : 0; P.alpha_raw = h->ypart + h->d; P.alpha_raw2 = h->scal + 17;   // the first is allreduced together with A't
     h->counters[3] += 1;
     return launch<kRowsLanczos>(h, h->csr, P);
 }
