@@ -235,12 +235,24 @@ __device__ __forceinline__ double cta_sum_to_thread0(double v, double *sred) {
     return tot;
 }
 
+// two sums at once (same fixed order), one barrier
+__device__ __forceinline__ void cta_sum2_to_thread0(double a, double b, double *sred, double &ra, double &rb) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) { sred[warp] = a; sred[kSweepWarps + warp] = b; }
+    __syncthreads();
+    ra = rb = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < kSweepWarps; ++w) { ra += sred[w]; rb += sred[kSweepWarps + w]; }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepParams P) {
     __shared__ double sprod[kTileNnz];           // products of the tile
     __shared__ double ssum[kTileSegs];           // per-segment sums of the tile
     __shared__ int sptr[kTileSegs + 8];          // segment pointers of the tile
-    __shared__ double sred[kSweepWarps];
+    __shared__ double sred[2 * kSweepWarps];
     __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31;
     constexpr int NOP = sweep_operands(MODE);
@@ -305,6 +317,19 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
     }
 
     double acc = 0.0;
+    double vsq = 0.0;
+    if constexpr (MODE == kRowsLanczos) {
+        // side job, issued before the tile so that its loads overlap the gathers: store the normalised vector as
+        // basis column `col` (the sweep itself divides on the fly); |v|^2 for the l2 part of alpha
+        if (!redo || P.l2 != 0.0) {
+            double *vout = P.V + (size_t)col * P.d;
+            for (int64_t c = (int64_t)blockIdx.x * blockDim.x + tid; c < P.d; c += (int64_t)gridDim.x * blockDim.x) {
+                const double vc = quotient(__ldg(S.src + c), S.beta, S.rinv);
+                if (!redo) vout[c] = vc;
+                vsq = fma(vc, vc, vsq);
+            }
+        }
+    }
     if (tile < P.ntiles) {
         const int seg0 = td.x, k0 = td.y, z = td.z, nk = td.w & 0xffff, tag = td.w >> 16;
         const bool stream = z > 0 && tag != kSingleTag;
@@ -395,22 +420,10 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
     }
 
     if constexpr (MODE == kRowsLanczos) {
-        // side job: store the normalised vector as basis column `col` (the sweep divided on the fly); |v|^2 for
-        // the l2 part of alpha
-        double vsq = 0.0;
-        if (!redo || P.l2 != 0.0) {
-            double *vout = P.V + (size_t)col * P.d;
-            for (int64_t c = (int64_t)blockIdx.x * blockDim.x + tid; c < P.d; c += (int64_t)gridDim.x * blockDim.x) {
-                const double vc = quotient(__ldg(S.src + c), S.beta, S.rinv);
-                if (!redo) vout[c] = vc;
-                vsq = fma(vc, vc, vsq);
-            }
-        }
         // alpha = v'Hv: threads -> tile (fixed order) -> the last CTA adds the tile sums in tile order
         __syncthreads();
-        const double mine = cta_sum_to_thread0(acc, sred);
-        __syncthreads();
-        const double mine2 = cta_sum_to_thread0(vsq, sred);
+        double mine, mine2;
+        cta_sum2_to_thread0(acc, vsq, sred, mine, mine2);
         if (tid == 0) {
             P.red_partials[blockIdx.x] = mine;
             P.red_partials[gridDim.x + blockIdx.x] = mine2;
@@ -427,9 +440,8 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
             }
             for (int i = tid; i < P.nlong; i += kSweepThreads) tot += __ldcg(P.longdot + i);
             __syncthreads();
-            const double s1 = cta_sum_to_thread0(tot, sred);
-            __syncthreads();
-            const double s2 = cta_sum_to_thread0(tot2, sred);
+            double s1, s2;
+            cta_sum2_to_thread0(tot, tot2, sred, s1, s2);
             if (tid == 0) {
                 if (P.alpha_mode == 0) {
                     const double alpha = __dadd_rn(quotient(s1, P.n_samples, P.inv_n), __dmul_rn(P.l2, s2));
