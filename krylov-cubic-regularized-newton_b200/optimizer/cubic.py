@@ -187,39 +187,100 @@ class Cubic_LS(Optimizer):
     """Cubic regularized Newton with line search on the full space (reference cubic.py:115-235).
 
     ``cubic_solver="full"``: dense Hessian A' D A / n formed on the FP64 tensor cores (kcrn_hessian_dense) and the
-    dense secular-equation solve of ``optimizer.dense``.  The matrix-free "CG" variant of the reference is not
-    part of this round."""
+    dense secular-equation solve of ``optimizer.dense``.  ``cubic_solver="CG"`` (what the reference driver uses for
+    dim >= 500, cubic_newton.py:76-82): matrix-free -- every (H + lam I)^-1 application is a conjugate-gradient solve
+    whose operator is the device HVP; the CG recurrence itself follows scipy.sparse.linalg.cg (x0 = 0, atol = 0,
+    rtol = solver_eps, maxiter = 10 n, no preconditioner) with torch vector operations on the device."""
 
     def __init__(self, reg_coef=None, cubic_solver="CG", solver_it_max=100, solver_eps=1e-8, beta=0.5, *args, **kwargs):
         super().__init__(*args, **kwargs)
-        if cubic_solver != "full":
-            raise NotImplementedError('only cubic_solver="full" is built on the device in this round')
+        if cubic_solver not in ("full", "CG"):
+            raise ValueError("cubic_solver must be 'full' or 'CG'")
+        self.cubic_solver = cubic_solver
         self.solver_it = 0
         self.solver_it_max = solver_it_max
         self.solver_eps = solver_eps
         self.beta = beta
         self.r0 = 0.1
         self.value = None
+        self.cg_iterations = 0
         self.reg_coef = self.loss.hessian_lipschitz if reg_coef is None else reg_coef
 
-    def step(self):
+    # -- matrix-free solve of (H + lam I) y = b, as scipy.sparse.linalg.cg iterates it
+    def _cg(self, lam, b, rtol):
+        eng = self.loss.engine
+        bnrm2 = float(b.norm())
+        if bnrm2 == 0:
+            return b.clone()
+        atol = rtol * bnrm2
+        x = b.new_zeros(b.shape)
+        r = b.clone()
+        p, rho_prev = None, None
+        for it in range(10 * b.numel()):
+            if float(r.norm()) < atol:
+                break
+            rho_cur = float(r @ r)
+            if it > 0:
+                p.mul_(rho_cur / rho_prev).add_(r)
+            else:
+                p = r.clone()
+            q = eng.hvp(p).add_(p, alpha=lam)
+            alpha = rho_cur / float(p @ q)
+            x.add_(p, alpha=alpha)
+            r.sub_(q, alpha=alpha)
+            rho_prev = rho_cur
+            self.cg_iterations += 1
+        return x
+
+    def cubic_solver_root_CG(self, M, it_max=100, epsilon=1e-8, r0=0.1):
+        """cubic_solver_root with conjugate-gradient solves (reference cubic.py:152-182)."""
+        from optimizer.dense import newton_scalar
+
+        g = self.grad
+        self.loss._forward(self.x)
+        memo = {}
+
+        def s_of(lam):
+            if lam not in memo:
+                memo.clear()
+                memo[lam] = self._cg(lam, -g, epsilon)
+            return memo[lam]
+
+        def func(lam):
+            return lam ** 2 - M ** 2 * float(s_of(lam).norm()) ** 2
+
+        def grad(lam):
+            s = s_of(lam)
+            return 2 * lam + 2 * M ** 2 * float(s @ self._cg(lam, s, epsilon))
+
+        r, its = newton_scalar(func, grad, r0, epsilon, it_max)
+        s = self._cg(r, -g, epsilon)
+        ns = float(s.norm())
+        return s, its, r, r / 2 * ns ** 2 - M / 3 * ns ** 3 - float(g @ s) / 2
+
+    def cubic_solver_root_full(self, M, it_max=100, epsilon=1e-8, r0=0.1):
         from optimizer.dense import cubic_solver_dense
 
+        return cubic_solver_dense(self.grad, self.hess, M, it_max, epsilon, r0=r0)
+
+    def step(self):
         loss = self.loss
         if self.value is None:
             self.value = loss.value(self.x)
         self.grad = loss.gradient(self.x)
-        self.hess = loss.hessian(self.x)
+        if self.cubic_solver == "full":
+            self.hess = loss.hessian(self.x)
         if loss.norm(self.grad) < self.tolerance:        # cubic.py:201-202
             return
+        solve = self.cubic_solver_root_full if self.cubic_solver == "full" else self.cubic_solver_root_CG
         M = self.reg_coef * self.beta
         while True:
-            s, its, r, decrease = cubic_solver_dense(self.grad, self.hess, M, self.solver_it_max, self.solver_eps,
-                                                     r0=self.r0)
+            s, its, r, decrease = solve(M, self.solver_it_max, self.solver_eps, r0=self.r0)
             x_new = self.x + s
             value_new = loss.value(x_new)
             if not value_new > self.value - decrease:    # unbounded backtracking, cubic.py:214
                 break
+            loss._forward(self.x)                        # the next solve needs the Hessian at x again
             M = M / self.beta
         self.x, self.reg_coef, self.value, self.r0 = x_new, M, value_new, r
         self.solver_it += its

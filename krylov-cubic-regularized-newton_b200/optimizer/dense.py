@@ -12,6 +12,24 @@ from __future__ import annotations
 import numpy as np
 
 
+def newton_scalar(func, fprime, x0, tol, maxiter):
+    """Newton-Raphson as scipy's scalar ``newton`` iterates it for root_scalar(method='newton', xtol=tol)
+    (scipy/optimize/_zeros_py.py:319-358, disp=False, rtol=0).  Returns (root, iterations)."""
+    p0 = p = float(x0)
+    for itr in range(maxiter):
+        fval = func(p0)
+        if fval == 0:
+            return p0, itr
+        fder = fprime(p0)
+        if fder == 0:
+            return p0, itr + 1
+        p = p0 - fval / fder
+        if abs(p - p0) <= tol:
+            return p, itr + 1
+        p0 = p
+    return p, maxiter
+
+
 def cubic_solver_dense(g, H, M, it_max=100, epsilon=1e-8, r0=0.1):
     """argmin_s <g, s> + 1/2 <s, H s> + M/3 |s|^3 for a dense symmetric H (CUDA tensors or numpy).
     Returns (s, newton_iterations, r, model_decrease); s is a CUDA tensor if g was one."""

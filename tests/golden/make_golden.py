@@ -299,7 +299,8 @@ def config4():
             opt = ref_cubic.SSCN(loss=loss, reg_coef=1e-3, subspace_dim=m, tolerance=1e-9, label="s")
         else:
             loss = LogisticRegression(A, b, l1=0, l2=0, store_mat_vec_prod=True)
-            opt = ref_cubic.Cubic_LS(loss=loss, reg_coef=1e-3, cubic_solver="full", tolerance=1e-8, label="c")
+            opt = ref_cubic.Cubic_LS(loss=loss, reg_coef=1e-3, cubic_solver="full" if kind == "full" else "CG",
+                                     tolerance=1e-8, label="c")
         opt.rng = np.random.default_rng(42)
         opt.init_run(P.x0)
         f, M, sit = [], [], []
@@ -308,8 +309,12 @@ def config4():
             f.append(opt.value); M.append(opt.reg_coef); sit.append(opt.solver_it)
         return np.array(f), np.array(M), np.array(sit, dtype=np.int64), opt.x.copy()
 
-    for kind, m, iters in (("sscn", 10, 40), ("sscn", 50, 40), ("full", 0, 12)):
-        tag = f"{kind}{m}" if kind == "sscn" else "full"
+    # cg(..., tol=) of the pinned scipy 1.10.1 is cg(..., rtol=) in the installed one
+    from scipy.sparse.linalg import cg as _scipy_cg
+    ref_cubic.cg = lambda A, b, tol: _scipy_cg(A, b, rtol=tol)
+
+    for kind, m, iters in (("sscn", 10, 40), ("sscn", 50, 40), ("full", 0, 12), ("cg", 0, 12)):
+        tag = f"{kind}{m}" if kind == "sscn" else kind
         f, M, sit, x = run(kind, m, iters, False)
         fr, _, _, _ = run(kind, m, iters, True)
         out.update({f"{tag}_f": f, f"{tag}_M": M, f"{tag}_solver_it": sit, f"{tag}_x_final": x, f"{tag}_rev_f": fr})

@@ -122,3 +122,22 @@ def test_full_hessian_crn_trajectory_vs_reference(torch, golden):
     assert dev.max() <= 1e-8
     assert opt.reg_coef == g["full_M"][-1] and opt.solver_it == int(g["full_solver_it"][-1])
     assert rel_err(opt.x.cpu().numpy(), g["full_x_final"]) <= 1e-8
+
+
+def test_cg_crn_trajectory_vs_reference(torch, golden):
+    """Cubic_LS(cubic_solver="CG") -- the CRN baseline the reference driver actually runs for dim >= 500."""
+    from optimizer.cubic import Cubic_LS
+    g = golden("traj_config4")
+    P = make_problem("small", seed=0)
+    opt = Cubic_LS(loss=_loss(P), reg_coef=1e-3, cubic_solver="CG", tolerance=1e-8, label="c", tqdm=False)
+    opt.init_run(P.x0)
+    ref = g["cg_f"]
+    f = []
+    for _ in range(len(ref)):
+        opt.step()
+        f.append(opt.value)
+    dev = np.abs(np.array(f) - ref) / np.abs(ref)
+    print(f"\nCG CRN: max dev {dev.max():.2e}, {opt.cg_iterations} CG iterations")
+    assert dev.max() <= 1e-8
+    assert opt.reg_coef == g["cg_M"][-1] and opt.solver_it == int(g["cg_solver_it"][-1])
+    assert rel_err(opt.x.cpu().numpy(), g["cg_x_final"]) <= 1e-7

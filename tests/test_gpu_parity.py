@@ -361,3 +361,72 @@ def test_drop_in_driver_flow_with_numpy_iterates(torch):
     assert rel_err(opt.loss.gradient(x), L.gradient(x)) <= TOL
     assert rel_err(opt.loss.hess_vec_prod(x, P.x0), L.hess_vec_prod(x, P.x0)) <= TOL
     assert abs(opt.loss.value(x) - L.value(x)) <= TOL * abs(L.value(x))
+
+
+# ------------------------------------------------------------------------------- API robustness
+def test_krylov_trial_state_errors_and_retrial_consistency(torch):
+    """kcrn_krylov_trial: a re-trial before any first trial is a state error; a re-trial with the same M reproduces
+    the first trial bit for bit; a larger M shortens the step (the backtracking loop of cubic.py:294-303)."""
+    from kcrn_b200._lib import KcrnError
+    P = make_problem("small", seed=0)
+    eng = _engine(P)
+    x = _dev(torch, P.x0)
+    eng.set_x(x)
+    with pytest.raises(KcrnError):
+        eng.krylov_trial(False, 6, False, 1e-3, 0.1)
+    x1 = eng.new_vector()
+    r1 = eng.krylov_trial(True, 6, False, 1e-3, 0.1, x_out=x1)
+    x2 = eng.new_vector()
+    r2 = eng.krylov_trial(False, 6, False, 1e-3, 0.1, x_out=x2)
+    assert torch.equal(x1, x2) and r1[:5] == r2[:5]
+    x3 = eng.new_vector()
+    r3 = eng.krylov_trial(False, 6, False, 1e+3, 0.1, x_out=x3)
+    assert r3[8] < r1[8] and r3[4] == 0                       # |x_trial - x| shrinks with a larger regulariser
+    # a forward sweep at another x invalidates the base iterate
+    eng.set_x(x)
+    with pytest.raises(KcrnError):
+        eng.krylov_trial(False, 6, False, 1e-3, 0.1)
+
+
+@pytest.mark.parametrize("m", [1, 2, 64])
+def test_fused_lanczos_extreme_subspace_sizes(torch, m):
+    P = make_problem("small", seed=0)
+    eng, L = _engine(P), _oracle(P)
+    x = P.x0
+    eng.set_x(_dev(torch, x))
+    eng.gradient(keep_internal=True)
+    eng.lanczos(m, True)
+    V, al, bet, info = eng.lanczos_view()
+    info = info.cpu().numpy()
+    Vo, alo, beo, _ = O.lanczos(lambda v: L.hess_vec_prod(x, v), L.gradient(x), m, reorth=True)
+    assert info[0] == alo.size == m
+    assert rel_err(al.cpu().numpy(), alo) <= 1e-8
+    G = (V @ V.T).cpu().numpy()
+    assert np.max(np.abs(G - np.eye(m))) <= 1e-11
+    with pytest.raises(ValueError):
+        eng.lanczos(513, False)
+
+
+def test_handles_are_independent_and_reusable(torch):
+    """Two handles on one device, interleaved calls, destroy + re-create: no shared state leaks between them."""
+    Pa, Pb = make_problem("tiny", seed=3), make_problem("small", seed=0)
+    ea, eb = _engine(Pa), _engine(Pb, 1e-3)
+    La, Lb = _oracle(Pa), _oracle(Pb, 1e-3)
+    rng = np.random.default_rng(9)
+    for _ in range(3):
+        xa, xb = rng.standard_normal(Pa.d), rng.standard_normal(Pb.d)
+        va, vb = rng.standard_normal(Pa.d), rng.standard_normal(Pb.d)
+        ea.set_x(_dev(torch, xa)); eb.set_x(_dev(torch, xb))
+        ha, hb = ea.hvp(_dev(torch, va)), eb.hvp(_dev(torch, vb))
+        assert rel_err(ha.cpu().numpy(), La.hess_vec_prod(xa, va)) <= TOL
+        assert rel_err(hb.cpu().numpy(), Lb.hess_vec_prod(xb, vb)) <= TOL
+    ea.close()
+    ea = _engine(Pa)
+    ea.set_x(_dev(torch, xa))
+    assert rel_err(ea.gradient().cpu().numpy(), La.gradient(xa)) <= TOL
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):                 # calls follow torch's current stream
+        eb.set_x(_dev(torch, xb))
+        g = eb.gradient()
+    side.synchronize()
+    assert rel_err(g.cpu().numpy(), Lb.gradient(xb)) <= TOL
