@@ -195,7 +195,7 @@ int kcrn_create(kcrn_handle *out, int64_t n_rows, int64_t n_cols, int64_t nnz, c
         KCRN_TRY(build_csc(h->csr, n_cols, &h->csc, s));
         KCRN_TRY(build_tiles(&h->csr, n_cols, s));   // row sweeps gather a d-vector
         KCRN_TRY(build_tiles(&h->csc, n_rows, s));   // column sweeps gather an n-vector
-        h->allow_pdl = getenv("KCRN_PDL") != nullptr;   // opt-in: measured slower inside the Lanczos graph
+        h->allow_pdl = getenv("KCRN_NO_PDL") == nullptr;   // programmatic dependent launch inside the captured graphs
         const size_t n = (size_t)n_rows, d = (size_t)n_cols;
         KCRN_CUDA(cudaMalloc(&h->x_cur, sizeof(double) * d));
         KCRN_CUDA(cudaMalloc(&h->x_base, sizeof(double) * d));

@@ -161,7 +161,7 @@ struct kcrn_problem {
     int rank = 0, world = 1;
     int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool pdl = false;              // launch with programmatic dependent launch (set while the Lanczos graph is built)
-    bool allow_pdl = false;        // KCRN_PDL=1 switches it on
+    bool allow_pdl = true;         // KCRN_NO_PDL=1 switches it off
 };
 
 namespace kcrn {

@@ -284,7 +284,6 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         }
     }
     pdl_wait();      // the previous kernel's results (control block, vectors) are complete and visible from here on
-    pdl_trigger();   // let the next kernel of the stream start its own matrix loads
 
     SweepState S;
     S.src = P.src;
@@ -418,6 +417,10 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
             }
         }
     }
+
+    // The tile is done: from here on only the short reduction tails remain, so the next kernel of the stream may
+    // become resident and start its own (matrix-only) loads while they run -- it still waits for our completion.
+    pdl_trigger();
 
     if constexpr (MODE == kRowsLanczos) {
         // alpha = v'Hv: threads -> tile (fixed order) -> the last CTA adds the tile sums in tile order
