@@ -292,12 +292,7 @@ int kcrn_comm_init(kcrn_handle h, const void *unique_id_128_host, int rank, int 
 
 int kcrn_csc_view(kcrn_handle h, int32_t *indptr_host, int32_t *indices_host, double *data_host) {
     if (!h) { set_error("kcrn_csc_view: null handle"); return KCRN_E_ARG; }
-    cudaStream_t s = h->stream;
-    if (indptr_host) KCRN_CUDA(cudaMemcpyAsync(indptr_host, h->csc.ptr, sizeof(int32_t) * (h->d + 1), cudaMemcpyDeviceToHost, s));
-    if (indices_host && h->nnz) KCRN_CUDA(cudaMemcpyAsync(indices_host, h->csc.idx, sizeof(int32_t) * h->nnz, cudaMemcpyDeviceToHost, s));
-    if (data_host && h->nnz) KCRN_CUDA(cudaMemcpyAsync(data_host, h->csc.val, sizeof(double) * h->nnz, cudaMemcpyDeviceToHost, s));
-    KCRN_CUDA(cudaStreamSynchronize(s));
-    return KCRN_OK;
+    return canonical_csc_to_host(h->csc, indptr_host, indices_host, data_host, h->stream);
 }
 
 int kcrn_set_x(kcrn_handle h, const double *x_dev) {

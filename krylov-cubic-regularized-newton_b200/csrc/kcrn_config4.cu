@@ -142,10 +142,10 @@ __global__ void densify_rows_kernel(const int32_t *__restrict__ ptr, const int32
 __global__ void densify_cols_kernel(const int32_t *__restrict__ cptr, const int32_t *__restrict__ cidx,
                                     const double *__restrict__ cval, const double *__restrict__ w,
                                     const int64_t *__restrict__ I, int m, int ld, double *__restrict__ X,
-                                    double *__restrict__ Y) {
+                                    double *__restrict__ Y, const int32_t *__restrict__ pos) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
-    const int64_t c = I[j];
+    const int64_t c = pos ? pos[I[j]] : I[j];
     for (int k = cptr[c]; k < cptr[c + 1]; ++k) {
         const size_t o = (size_t)cidx[k] * ld + j;
         Y[o] += cval[k];
@@ -157,16 +157,17 @@ __global__ void densify_cols_kernel(const int32_t *__restrict__ cptr, const int3
 __global__ void partial_gradient_kernel(const int32_t *__restrict__ cptr, const int32_t *__restrict__ cidx,
                                         const double *__restrict__ cval, const double *__restrict__ r,
                                         const int64_t *__restrict__ I, int m, double n_samples, double l2,
-                                        const double *__restrict__ x, double *__restrict__ out) {
+                                        const double *__restrict__ x, double *__restrict__ out,
+                                        const int32_t *__restrict__ pos) {
     const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (j >= m) return;
-    const int64_t c = I[j];
+    const int64_t c = pos ? pos[I[j]] : I[j];
     double acc = 0.0;
     for (int k = cptr[c] + lane; k < cptr[c + 1]; k += 32) acc = fma(cval[k], r[cidx[k]], acc);
     acc = warp_sum(acc);
     if (lane == 0) {
         double g = acc / n_samples;
-        if (l2 != 0.0) g = __dadd_rn(g, __dmul_rn(l2, x[c]));
+        if (l2 != 0.0) g = __dadd_rn(g, __dmul_rn(l2, x[I[j]]));
         out[j] = g;
     }
 }
@@ -177,9 +178,10 @@ __global__ void __launch_bounds__(1024) column_update_kernel(const int32_t *__re
                                                              const double *__restrict__ cval,
                                                              const int64_t *__restrict__ I,
                                                              const double *__restrict__ delta, int m,
-                                                             double *__restrict__ tmp) {
+                                                             double *__restrict__ tmp,
+                                                             const int32_t *__restrict__ pos) {
     for (int j = 0; j < m; ++j) {
-        const int64_t c = I[j];
+        const int64_t c = pos ? pos[I[j]] : I[j];
         const double dj = delta[j];
         for (int k = cptr[c] + threadIdx.x; k < cptr[c + 1]; k += blockDim.x)
             tmp[cidx[k]] = fma(cval[k], dj, tmp[cidx[k]]);
@@ -246,7 +248,7 @@ int config4_partial_gradient(kcrn_problem *h, const int64_t *I, int m, double *o
     if (h->world > 1) { set_error("kcrn_partial_gradient: row-sharded handles are not supported"); return KCRN_E_ARG; }
     partial_gradient_kernel<<<(m * 32 + 255) / 256, 256, 0, h->stream>>>(h->csc.ptr, h->csc.idx, h->csc.val, h->resid,
                                                                         I, m, (double)h->n_global, h->l2, h->x_cur,
-                                                                        out);
+                                                                        out, h->csc.pos);
     KCRN_LAUNCH_CHECK();
     h->counters[0] += 1;
     return KCRN_OK;
@@ -265,7 +267,7 @@ int config4_partial_hessian(kcrn_problem *h, const int64_t *I, int m, double *ou
     KCRN_CUDA(cudaMallocAsync(&Y, bytes, s));
     KCRN_CUDA(cudaMemsetAsync(X, 0, bytes, s));
     KCRN_CUDA(cudaMemsetAsync(Y, 0, bytes, s));
-    densify_cols_kernel<<<(m + 127) / 128, 128, 0, s>>>(h->csc.ptr, h->csc.idx, h->csc.val, h->D, I, m, ld, X, Y);
+    densify_cols_kernel<<<(m + 127) / 128, 128, 0, s>>>(h->csc.ptr, h->csc.idx, h->csc.val, h->D, I, m, ld, X, Y, h->csc.pos);
     KCRN_LAUNCH_CHECK();
     KCRN_TRY(run_gemm(X, Y, K, ld, m, (double)h->n_global, h->l2, out, m, s));
     KCRN_CUDA(cudaFreeAsync(X, s));
@@ -279,7 +281,7 @@ int config4_update_Ax(kcrn_problem *h, const int64_t *I, const double *delta, in
     if (h->world > 1) { set_error("kcrn_update_Ax: row-sharded handles are not supported"); return KCRN_E_ARG; }
     cudaStream_t s = h->stream;
     KCRN_CUDA(cudaMemsetAsync(h->t, 0, sizeof(double) * h->n, s));      // t doubles as the A[:, I] delta buffer
-    column_update_kernel<<<1, 1024, 0, s>>>(h->csc.ptr, h->csc.idx, h->csc.val, I, delta, m, h->t);
+    column_update_kernel<<<1, 1024, 0, s>>>(h->csc.ptr, h->csc.idx, h->csc.val, I, delta, m, h->t, h->csc.pos);
     KCRN_LAUNCH_CHECK();
     add_inplace_kernel<<<(unsigned)((h->n + 255) / 256), 256, 0, s>>>(h->Ax, h->t, h->n);
     KCRN_LAUNCH_CHECK();

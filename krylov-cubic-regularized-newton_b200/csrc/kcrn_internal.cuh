@@ -48,7 +48,7 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
 // ----------------------------------------------------------------------------- geometry
 constexpr int kTileNnz = 2048;     // non-zeros per CTA tile (8 per thread)
 constexpr int kTileSegs = 1024;    // at most this many segments (rows / columns) per stream tile
-constexpr int kShortSeg = 512;     // longest segment that shares a stream tile with others
+constexpr int kShortSeg = 1024;    // longest segment that shares a stream tile with others
 constexpr int kSingleTag = 15;     // descriptor tag of a tile that holds one medium segment
 constexpr int kSweepWarps = 8;     // warps per CTA of the sweep kernels
 constexpr int kSweepThreads = kSweepWarps * 32;
@@ -76,6 +76,10 @@ struct SegMat {
     unsigned *ticket = nullptr;  // [nlong]    self-resetting arrival counters
     int grid = 0;                // CTAs of the sweep kernels over this matrix (fixed -> deterministic sums)
     int64_t gather_len = 0;      // length of the vector this matrix gathers from (d for CSR, n for CSC)
+    // CSC copy only: its columns are stored in a length-class order (kcrn_transpose.cu)
+    int32_t *segid = nullptr;    // [nseg] original column of the s-th stored segment (null: natural order)
+    int32_t *pos = nullptr;      // [nseg] where column c is stored
+    std::vector<int32_t> cptr_host;   // canonical column pointer (natural order), for kcrn_csc_view
 };
 
 // Device-resident control block of the Lanczos recurrence (written by single threads on the device,
@@ -169,6 +173,8 @@ namespace kcrn {
 // ----------------------------------------------------------------------------- kcrn_transpose.cu
 int build_csc(const SegMat &csr, int64_t n_cols, SegMat *csc, cudaStream_t s);
 int exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t len, cudaStream_t s);
+int canonical_csc_to_host(const SegMat &csc, int32_t *indptr_host, int32_t *indices_host, double *data_host,
+                          cudaStream_t s);
 
 // ----------------------------------------------------------------------------- kcrn_sweep.cu
 int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s);

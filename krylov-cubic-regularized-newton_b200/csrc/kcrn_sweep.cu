@@ -39,7 +39,7 @@ namespace kcrn {
 // ----------------------------------------------------------------------------- tile lists (host)
 void free_segmat(SegMat *A) {
     cudaFree(A->ptr); cudaFree(A->idx); cudaFree(A->val); cudaFree(A->tiles); cudaFree(A->longtab);
-    cudaFree(A->partial); cudaFree(A->longdot); cudaFree(A->ticket);
+    cudaFree(A->partial); cudaFree(A->longdot); cudaFree(A->ticket); cudaFree(A->segid); cudaFree(A->pos);
     *A = SegMat();
 }
 
@@ -133,6 +133,7 @@ struct SweepParams {
     const int4 *tiles;
     int ntiles;
     const int4 *longtab;
+    const int32_t *segid;          // stored segment -> index of its operands / outputs (null: identity)
     double *partial, *longdot;
     unsigned *ticket;
     int nlong;
@@ -334,6 +335,8 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         const bool stream = z > 0 && tag != kSingleTag;
         int4 lt = make_int4(0, 1, 0, 0);
         double o0[NOP > 0 ? kSegRounds : 1], o1[NOP > 1 ? kSegRounds : 1];
+        int sid[kSegRounds];
+        sid[0] = seg0;
         if (stream) {
             // epilogue operands to registers: in flight while the gathers run
 #pragma unroll
@@ -341,7 +344,8 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
                 const int sg = r * kSweepThreads + tid;
                 if (sg < z) {
                     double a0, a1;
-                    load_operands<MODE>(P, S, seg0 + sg, a0, a1);
+                    sid[r] = P.segid ? __ldg(P.segid + seg0 + sg) : seg0 + sg;
+                    load_operands<MODE>(P, S, sid[r], a0, a1);
                     if constexpr (NOP > 0) o0[r] = a0;
                     if constexpr (NOP > 1) o1[r] = a1;
                 }
@@ -350,7 +354,8 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
             if (z < 0) lt = __ldg(P.longtab + (-z - 1));
             if (tid == 0) {
                 double a0, a1;
-                load_operands<MODE>(P, S, seg0, a0, a1);
+                if (P.segid) sid[0] = __ldg(P.segid + seg0);
+                load_operands<MODE>(P, S, sid[0], a0, a1);
                 if constexpr (NOP > 0) o0[0] = a0;
                 if constexpr (NOP > 1) o1[0] = a1;
             }
@@ -370,7 +375,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
             for (int r = 0; r < kItems; ++r) s += p[r];
             const double tot = cta_sum_to_thread0(s, sred);
             if (z > 0) {
-                if (tid == 0) finish_segment<MODE>(P, S, seg0, tot, -1, NOP > 0 ? o0[0] : 0.0, NOP > 1 ? o1[0] : 0.0, acc);
+                if (tid == 0) finish_segment<MODE>(P, S, sid[0], tot, -1, NOP > 0 ? o0[0] : 0.0, NOP > 1 ? o1[0] : 0.0, acc);
             } else {
                 const int lseg = -z - 1;
                 if (tid == 0) {
@@ -385,7 +390,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
                     for (int i = lane; i < lt.y; i += 32) all += __ldcg(P.partial + lt.x + i);
                     all = warp_sum(all);
                     // thread 0 holds the operands
-                    if (tid == 0) finish_segment<MODE>(P, S, seg0, all, lseg, NOP > 0 ? o0[0] : 0.0, NOP > 1 ? o1[0] : 0.0, acc);
+                    if (tid == 0) finish_segment<MODE>(P, S, sid[0], all, lseg, NOP > 0 ? o0[0] : 0.0, NOP > 1 ? o1[0] : 0.0, acc);
                 }
             }
         } else {
@@ -413,7 +418,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
             for (int r = 0; r < kSegRounds; ++r) {
                 const int sg = r * kSweepThreads + tid;
                 if (sg < z)
-                    finish_segment<MODE>(P, S, seg0 + sg, ssum[sg], -1, NOP > 0 ? o0[r] : 0.0, NOP > 1 ? o1[r] : 0.0, acc);
+                    finish_segment<MODE>(P, S, sid[r], ssum[sg], -1, NOP > 0 ? o0[r] : 0.0, NOP > 1 ? o1[r] : 0.0, acc);
             }
         }
     }
@@ -483,7 +488,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
 
 void fill_matrix(SweepParams &P, const SegMat &A) {
     P.ptr = A.ptr; P.idx = A.idx; P.val = A.val; P.tiles = A.tiles; P.ntiles = A.ntiles;
-    P.longtab = A.longtab; P.partial = A.partial; P.longdot = A.longdot; P.ticket = A.ticket;
+    P.longtab = A.longtab; P.segid = A.segid; P.partial = A.partial; P.longdot = A.longdot; P.ticket = A.ticket;
     P.nlong = A.nlong;
 }
 

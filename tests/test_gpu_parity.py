@@ -330,14 +330,15 @@ def test_free_running_trajectory_vs_reference(torch, golden, name, m, iters, reo
     f, ref, refrev = f[:k], ref[:k], refrev[:k]
     envelope = np.maximum.accumulate(np.abs(refrev - ref) / np.abs(ref))
     dev = np.abs(f - ref) / np.abs(ref)
-    prefix = int(np.argmax(envelope > 1e-8)) if np.any(envelope > 1e-8) else k
-    print(f"\n{name} m={m} reorth={reorth}: envelope <= 1e-8 for the first {prefix}/{k} iterations; on that prefix "
+    prefix = int(np.argmax(envelope > 1e-9)) if np.any(envelope > 1e-9) else k
+    print(f"\n{name} m={m} reorth={reorth}: envelope <= 1e-9 for the first {prefix}/{k} iterations; on that prefix "
           f"max dev {dev[:prefix].max():.3e}; beyond it max dev {dev[prefix:].max() if prefix < k else 0:.3e} vs "
           f"max envelope {envelope.max():.3e}")
-    # (1) where the reference agrees with itself to 1e-8 under a pure re-ordering of its sums, so do we
+    # (1) where the reference agrees with itself to 1e-9 under a pure re-ordering of its sums (a decade of margin:
+    #     one perturbed run is a sample of the noise, not a bound), we agree with it to the 1e-8 bar
     assert np.all(dev[:prefix] <= 1e-8), dev[:prefix]
-    # (2) beyond, rounding noise is amplified chaotically; one perturbed run of the
-    #     reference is a sample of that noise, not a bound, so require agreement within two orders of it
+    # (2) beyond, rounding noise is amplified chaotically: stay within two orders of the
+    #     reference's own self-noise
     assert np.all(dev <= np.maximum(1e-8, 100 * envelope)), (dev, envelope)
     # the iteration stays a descent method and ends where the reference ends (loose, chaos-proof)
     assert np.all(np.diff(f) <= 1e-12)
