@@ -8,6 +8,7 @@
 // Ranks inside a block come from warp match/ballot, so no floating-point or order-dependent atomics
 // are involved and the result does not depend on scheduling.  The column pointer is read off the
 // sorted keys by binary search; row indices and values are gathered through the sorted positions.
+#include <stdlib.h>
 #include <string.h>
 
 #include "kcrn_internal.cuh"
@@ -274,7 +275,8 @@ int build_csc(const SegMat &csr, int64_t n_cols, SegMat *csc, cudaStream_t s) {
         KCRN_CUDA(cudaMemcpyAsync(cnt.data(), counts, sizeof(int32_t) * n_cols, cudaMemcpyDeviceToHost, s));
         KCRN_CUDA(cudaStreamSynchronize(s));
         cudaFree(counts);
-        auto cls = [](int len) { return len <= 8 ? 0 : len <= 32 ? 1 : len <= 128 ? 2 : len <= 512 ? 3 : len <= kTileNnz ? 4 : 5; };
+        const bool natural = getenv("KCRN_NATURAL_CSC") != nullptr;   // A/B switch: keep the scipy column order
+        auto cls = [natural](int len) { return natural ? 0 : len <= 8 ? 0 : len <= 32 ? 1 : len <= 128 ? 2 : len <= 512 ? 3 : len <= kTileNnz ? 4 : 5; };
         int64_t start[7] = {0, 0, 0, 0, 0, 0, 0};
         for (int64_t c = 0; c < n_cols; ++c) start[cls(cnt[c]) + 1] += 1;
         for (int k = 0; k < 6; ++k) start[k + 1] += start[k];
