@@ -85,7 +85,18 @@ int enqueue_lanczos(kcrn_problem *h, int m, int reorth) {
     for (int slot = 0; slot < m; ++slot) {
         // rows sweep: t = D (A v), basis column, and alpha = v'Hv one sweep early (so that the column sweep can
         // form w' = Hv - beta v_prev - alpha v and beta = |w'| itself: two kernels per Lanczos step)
-        KCRN_TRY(launch_rows_lanczos(h));
+        const bool peer = h->world > 1 && h->p2p_ready &&
+                          (int64_t)(h->world - 1) * h->d * (int64_t)sizeof(double) <= (8 << 20);
+        if (peer) {
+            // fused epilogue + allreduce over NVLink peer memory (small d: the collective is latency-bound)
+            double *buf = h->p2p_y + (size_t)(slot & 1) * (size_t)(h->d + 2);
+            KCRN_TRY(launch_rows_lanczos(h, buf + h->d));
+            KCRN_TRY(launch_cols_raw(h, h->t, buf));
+            KCRN_TRY(launch_lanczos_post_peer(h, slot & 1, reorth));
+            if (reorth && slot + 1 < m) KCRN_TRY(launch_lanczos_update(h, 1, 1));
+            continue;
+        }
+        KCRN_TRY(launch_rows_lanczos(h, h->ypart + h->d));
         if (h->world > 1) {
             KCRN_TRY(launch_cols_raw(h, h->t, h->ypart));
             KCRN_TRY(nccl_allreduce_sum(h, h->ypart, (h->d + 2) & ~(int64_t)1));   // even count: 16-byte multiple
@@ -250,6 +261,12 @@ int kcrn_destroy(kcrn_handle h) {
     for (auto &ge : h->graphs) cudaGraphExecDestroy(ge.exec);
     h->graphs.clear();
     cudaDeviceSynchronize();
+    for (int k = 0; k < kMaxPeers; ++k) {
+        if (k != h->rank && h->peer_y[k]) cudaIpcCloseMemHandle(h->peer_y[k]);
+        if (k != h->rank && h->peer_flags[k]) cudaIpcCloseMemHandle(h->peer_flags[k]);
+    }
+    cudaFree(h->p2p_y);
+    cudaFree(h->p2p_flags);
     nccl_destroy(h);
     free_segmat(&h->csr);
     free_segmat(&h->csc);
@@ -288,6 +305,58 @@ int kcrn_comm_init(kcrn_handle h, const void *unique_id_128_host, int rank, int 
     for (auto &ge : h->graphs) cudaGraphExecDestroy(ge.exec);
     h->graphs.clear();
     return nccl_init(h, unique_id_128_host, rank, world);
+}
+
+int kcrn_p2p_export(kcrn_handle h, void *handles_128_host) {
+    if (!h || !handles_128_host) { set_error("kcrn_p2p_export: null argument"); return KCRN_E_ARG; }
+    if (!h->p2p_y) {
+        KCRN_CUDA(cudaMalloc(&h->p2p_y, sizeof(double) * 2 * (size_t)(h->d + 2)));
+        KCRN_CUDA(cudaMalloc(&h->p2p_flags, sizeof(unsigned) * 3 * kMaxPeers));
+        KCRN_CUDA(cudaMemset(h->p2p_y, 0, sizeof(double) * 2 * (size_t)(h->d + 2)));
+        KCRN_CUDA(cudaMemset(h->p2p_flags, 0, sizeof(unsigned) * 3 * kMaxPeers));
+    }
+    cudaIpcMemHandle_t hy, hf;
+    KCRN_CUDA(cudaIpcGetMemHandle(&hy, h->p2p_y));
+    KCRN_CUDA(cudaIpcGetMemHandle(&hf, h->p2p_flags));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handles_128_host, &hy, 64);
+    memcpy((char *)handles_128_host + 64, &hf, 64);
+    return KCRN_OK;
+}
+
+int kcrn_p2p_attach(kcrn_handle h, const void *all_handles_host) {
+    if (!h || !all_handles_host) { set_error("kcrn_p2p_attach: null argument"); return KCRN_E_ARG; }
+    if (h->world < 2 || h->world > kMaxPeers || !h->p2p_y) {
+        set_error("kcrn_p2p_attach: needs kcrn_comm_init (2..%d ranks) and kcrn_p2p_export first", kMaxPeers);
+        return KCRN_E_STATE;
+    }
+    for (auto &ge : h->graphs) cudaGraphExecDestroy(ge.exec);
+    h->graphs.clear();
+    for (int k = 0; k < h->world; ++k) {
+        if (k == h->rank) { h->peer_y[k] = h->p2p_y; h->peer_flags[k] = h->p2p_flags; continue; }
+        cudaIpcMemHandle_t hy, hf;
+        memcpy(&hy, (const char *)all_handles_host + (size_t)k * 128, 64);
+        memcpy(&hf, (const char *)all_handles_host + (size_t)k * 128 + 64, 64);
+        void *py = nullptr, *pf = nullptr;
+        KCRN_CUDA(cudaIpcOpenMemHandle(&py, hy, cudaIpcMemLazyEnablePeerAccess));
+        KCRN_CUDA(cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_y[k] = (double *)py;
+        h->peer_flags[k] = (unsigned *)pf;
+    }
+    h->p2p_ready = getenv("KCRN_NO_P2P") == nullptr;
+    return KCRN_OK;
+}
+
+int kcrn_p2p_enable(kcrn_handle h, int on) {
+    if (!h) { set_error("kcrn_p2p_enable: null handle"); return KCRN_E_ARG; }
+    if (on && !h->peer_y[h->rank]) { set_error("kcrn_p2p_enable: kcrn_p2p_attach first"); return KCRN_E_STATE; }
+    if ((on != 0) != h->p2p_ready) {
+        KCRN_CUDA(cudaStreamSynchronize(h->stream));
+        for (auto &ge : h->graphs) cudaGraphExecDestroy(ge.exec);
+        h->graphs.clear();
+        h->p2p_ready = on != 0;
+    }
+    return KCRN_OK;
 }
 
 int kcrn_csc_view(kcrn_handle h, int32_t *indptr_host, int32_t *indices_host, double *data_host) {

@@ -55,6 +55,7 @@ constexpr int kSweepThreads = kSweepWarps * 32;
 constexpr int kVecThreads = 256;   // CTA size of the d-length vector kernels
 constexpr int kMaxM = 512;         // largest Lanczos subspace the single-CTA solver accepts
 constexpr int kNumSm = 148;        // B200
+constexpr int kMaxPeers = 16;      // ranks of one NVLink domain that can share exchange buffers
 
 // One sparse matrix stored by segments: rows (CSR) or columns (CSC).
 //   tiles[i] = {seg0, k0, z, nk | tag << 16}  (one CTA per tile):
@@ -163,6 +164,13 @@ struct kcrn_problem {
     // NCCL
     void *comm = nullptr;
     int rank = 0, world = 1;
+    // NVLink peer exchange of the fused Lanczos step (kcrn_p2p_export / kcrn_p2p_attach)
+    double *p2p_y = nullptr;            // [2][d + 2] my partial A't (+ alpha partial), double-buffered by step parity
+    unsigned *p2p_flags = nullptr;      // [kMaxPeers] arrival epochs written by the peers, [kMaxPeers] my
+                                        // epoch, [kMaxPeers] read-done acknowledgements written by the peers
+    double *peer_y[kcrn::kMaxPeers] = {};
+    unsigned *peer_flags[kcrn::kMaxPeers] = {};
+    bool p2p_ready = false;
     int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool pdl = false;              // launch with programmatic dependent launch (set while the Lanczos graph is built)
     bool allow_pdl = true;         // KCRN_NO_PDL=1 switches it off
@@ -181,7 +189,8 @@ int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s);
 void free_segmat(SegMat *A);
 int launch_forward(kcrn_problem *h, const double *x);                 // A x and everything derived
 int launch_rows_weighted(kcrn_problem *h, const double *v);           // t = D .* (A v)
-int launch_rows_lanczos(kcrn_problem *h);                             // same, source picked by ctl
+int launch_rows_lanczos(kcrn_problem *h, double *alpha_raw);          // same, source picked by ctl; sharded runs:
+                                                                      // raw alpha sum -> alpha_raw[0]
 int launch_cols_raw(kcrn_problem *h, const double *src, double *out); // out = A' src
 int launch_cols_scaled(kcrn_problem *h, const double *src, const double *u, double *out);  // A' src / n + l2 u
 int launch_cols_lanczos(kcrn_problem *h, int update_ctl);             // w' and beta fused
@@ -193,6 +202,7 @@ int launch_lanczos_init(kcrn_problem *h, int m);      // ctl, alphas, bet reset;
 int launch_lanczos_post(kcrn_problem *h, const double *hv_or_raw, int raw);  // epilogue after allreduce / generic feed
 int launch_lanczos_update(kcrn_problem *h, int reorth, int fused);
 int launch_lanczos_post_sharded(kcrn_problem *h, const double *y_allreduced, int reorth);
+int launch_lanczos_post_peer(kcrn_problem *h, int buf, int reorth);
 int launch_normalise_current(kcrn_problem *h);        // V[col] = src / bet[col] outside the fused sweep
 int launch_sum(kcrn_problem *h, const double *a, int64_t len, double scale, double *out);  // deterministic sum
 int launch_axpy_basis(const double *x, const double *V, const double *s, int m, const int32_t *info,

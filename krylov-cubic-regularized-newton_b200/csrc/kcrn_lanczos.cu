@@ -39,6 +39,12 @@ struct VecParams {
     int from_wp;               // reorth stage 1 inside the fused loop: w' was already formed by the column sweep
     const double *alpha_raw, *alpha_raw2;   // row-sharded fused loop: sum_i t_i (Av)_i (allreduced) and |v|^2
     double inv_n;
+    // fused epilogue + allreduce over NVLink peer memory (kcrn_p2p_attach): every rank's exchange buffer and
+    // arrival flags, mapped into this process
+    const double *peer_y[kMaxPeers];
+    unsigned *peer_flags[kMaxPeers];
+    unsigned *my_flags, *epoch;
+    int rank, world;
     double n_samples, l2;
     int32_t *info;
 };
@@ -87,6 +93,13 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_init_kernel(VecParams P) 
     }
     double tot = 0.0;
     if (!grid_sum(loc, P.red_partials, P.red_ticket, sh, &s_last, &tot)) return;
+    if (P.my_flags && threadIdx.x < P.world) {
+        // peer exchange: the two buffers alternate inside a run, but a new run restarts at buffer 0 -- do not let the
+        // sweeps that follow overwrite it before every peer has finished reading my vectors of the previous run
+        const unsigned seen = *P.epoch;
+        const volatile unsigned *ack = P.my_flags + 2 * kMaxPeers + threadIdx.x;
+        while (*ack < seen) __nanosleep(40);
+    }
     for (int i = threadIdx.x; i < P.m; i += blockDim.x) {
         P.alphas[i] = 0.0;
         P.bet[i + 1] = 0.0;
@@ -151,7 +164,16 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_post_kernel(VecParams P) 
 
 // Row-sharded fused loop, after the allreduce of {A't, sum_i t_i (Av)_i}: alpha = v'Hv, w' = y/n + l2 v -
 // beta_prev v_prev - alpha v, beta = |w'|, then the bookkeeping of cubic.py:98-109 -- replicated on every rank.
-template <int E>
+//
+// PEER = true: no NCCL call in front of it -- the kernel itself is the allreduce.  Every rank publishes "my partial
+// A't is complete" by storing a new epoch into its slot of every peer's flag array (NVLink peer stores), waits
+// until all slots of its own array show that epoch, then reads the partial vectors of all ranks through peer
+// pointers and adds them in rank order -- the same order on every rank, so the replicas stay bit-identical --
+// while it applies the epilogue.  One pass over the d-vector instead of reduce + broadcast + epilogue, and the
+// latency of one flag round instead of a collective launch (the 378 KB vector of the rcv1 shape is latency-bound).
+// The exchange buffer is double-buffered by step parity, so a rank may run ahead by one step without overwriting
+// data a slower rank still reads.
+template <int E, bool PEER>
 __global__ void __launch_bounds__(kVecThreads) lanczos_post_sharded_kernel(VecParams P) {
     __shared__ double sh[kVecThreads / 32];
     __shared__ int s_last;
@@ -160,7 +182,25 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_post_sharded_kernel(VecPa
     if (P.ctl->done) return;
     const int col = P.ctl->col, store_idx = P.ctl->store_idx;
     const bool final_ = P.ctl->final_ != 0;
-    const double alpha = __dadd_rn(quotient(P.alpha_raw[0], P.n_samples, P.inv_n), __dmul_rn(P.l2, P.alpha_raw2[0]));
+    unsigned target = 0;
+    double s1 = 0.0;
+    if constexpr (PEER) {
+        target = *P.epoch + 1u;
+        if (blockIdx.x == 0 && threadIdx.x < P.world) {
+            __threadfence_system();                                   // my partial vector before my flag
+            *reinterpret_cast<volatile unsigned *>(P.peer_flags[threadIdx.x] + P.rank) = target;
+        }
+        if (threadIdx.x < P.world) {
+            const volatile unsigned *f = P.my_flags + threadIdx.x;
+            while (*f < target) __nanosleep(40);
+            __threadfence_system();                                   // flags before the peers' vectors
+        }
+        __syncthreads();
+        for (int k = 0; k < P.world; ++k) s1 += __ldcv(P.peer_y[k] + P.d);
+    } else {
+        s1 = P.alpha_raw[0];
+    }
+    const double alpha = __dadd_rn(quotient(s1, P.n_samples, P.inv_n), __dmul_rn(P.l2, P.alpha_raw2[0]));
     const double *v = P.V + (size_t)col * P.d;
     const bool subtract = col > 0;
     const double *vpre = subtract ? P.V + (size_t)(col - 1) * P.d : nullptr;
@@ -173,7 +213,14 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_post_sharded_kernel(VecPa
             const int64_t c = base + (int64_t)e * kVecThreads;
             if (c < P.d) {
                 const double vc = v[c];
-                double hv = __dadd_rn(quotient(P.w_in[c], P.n_samples, P.inv_n), __dmul_rn(P.l2, vc));
+                double y;
+                if constexpr (PEER) {
+                    y = 0.0;
+                    for (int k = 0; k < P.world; ++k) y += __ldcv(P.peer_y[k] + c);   // rank order: identical everywhere
+                } else {
+                    y = P.w_in[c];
+                }
+                double hv = __dadd_rn(quotient(y, P.n_samples, P.inv_n), __dmul_rn(P.l2, vc));
                 if (subtract) hv = __dsub_rn(hv, __dmul_rn(beta_prev, vpre[c]));
                 hv = __dsub_rn(hv, __dmul_rn(alpha, vc));
                 P.wp[c] = hv;
@@ -184,6 +231,12 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_post_sharded_kernel(VecPa
     double tot = 0.0;
     if (!grid_sum(loc, P.red_partials, P.red_ticket, sh, &s_last, &tot)) return;
     if (threadIdx.x == 0) {
+        if constexpr (PEER) {
+            *P.epoch = target;
+            // all my CTAs have read the peers' vectors of this step (the ticket says so): acknowledge
+            for (int k = 0; k < P.world; ++k)
+                *reinterpret_cast<volatile unsigned *>(P.peer_flags[k] + 2 * kMaxPeers + P.rank) = target;
+        }
         P.alphas[final_ ? store_idx : col] = alpha;
         P.ctl->hvps += 1;
         if (final_) P.ctl->done = 1;
@@ -420,6 +473,7 @@ int launch_lanczos_init(kcrn_problem *h, int m) {
     VecParams P = base_params(h);
     P.m = m;
     P.red_ticket = h->red_ticket + 4;
+    if (h->p2p_ready) { P.my_flags = h->p2p_flags; P.epoch = h->p2p_flags + kMaxPeers; P.world = h->world; }
     KCRN_CUDA(launch_kernel(lanczos_init_kernel, dim3(grid_stride_blocks(h->d)), dim3(kVecThreads), 0, h->stream, h->pdl, P));
     h->counters[0] += 1;
     return KCRN_OK;
@@ -445,11 +499,29 @@ int launch_lanczos_post(kcrn_problem *h, const double *hv_or_raw, int raw) {
 
 int launch_lanczos_post_sharded(kcrn_problem *h, const double *y_allreduced, int reorth) {
     VecParams P = base_params(h);
-    P.w_in = y_allreduced; P.alpha_raw = h->ypart + h->d; P.alpha_raw2 = h->scal + 17; P.inv_n = 1.0 / P.n_samples; P.stage = reorth ? 1 : 0;
+    P.w_in = y_allreduced; P.alpha_raw = h->ypart + h->d; P.alpha_raw2 = h->scal + 17; P.inv_n = 1.0 / P.n_samples;
+    P.stage = reorth ? 1 : 0;
     P.red_ticket = h->red_ticket + 2;
-    if (h->vec_elems == 4) KCRN_CUDA(launch_kernel(lanczos_post_sharded_kernel<4>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
-    else KCRN_CUDA(launch_kernel(lanczos_post_sharded_kernel<1>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
+    if (h->vec_elems == 4) KCRN_CUDA(launch_kernel(lanczos_post_sharded_kernel<4, false>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
+    else KCRN_CUDA(launch_kernel(lanczos_post_sharded_kernel<1, false>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
     h->counters[0] += 1;
+    return KCRN_OK;
+}
+
+// the same with the allreduce done inside the kernel over peer memory; buf = parity of the Lanczos step
+int launch_lanczos_post_peer(kcrn_problem *h, int buf, int reorth) {
+    VecParams P = base_params(h);
+    P.alpha_raw2 = h->scal + 17; P.inv_n = 1.0 / P.n_samples; P.stage = reorth ? 1 : 0;
+    P.red_ticket = h->red_ticket + 2;
+    P.rank = h->rank; P.world = h->world; P.my_flags = h->p2p_flags; P.epoch = h->p2p_flags + kMaxPeers;
+    for (int k = 0; k < h->world; ++k) {
+        P.peer_y[k] = h->peer_y[k] + (size_t)buf * (size_t)(h->d + 2);
+        P.peer_flags[k] = h->peer_flags[k];
+    }
+    if (h->vec_elems == 4) KCRN_CUDA(launch_kernel(lanczos_post_sharded_kernel<4, true>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
+    else KCRN_CUDA(launch_kernel(lanczos_post_sharded_kernel<1, true>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
+    h->counters[0] += 1;
+    h->counters[5] += 1;
     return KCRN_OK;
 }
 

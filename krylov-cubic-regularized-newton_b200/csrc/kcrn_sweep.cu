@@ -530,12 +530,12 @@ int launch_rows_weighted(kcrn_problem *h, const double *v) {
     return launch<kRowsWeighted>(h, h->csr, P);
 }
 
-int launch_rows_lanczos(kcrn_problem *h) {
+int launch_rows_lanczos(kcrn_problem *h, double *alpha_raw) {
     SweepParams P{};
     P.D = h->D; P.out = h->t; P.ctl = h->ctl; P.V = h->V; P.g = h->g; P.wp = h->wp; P.bet = h->bet; P.d = h->d;
     P.alphas = h->alphas; P.n_samples = (double)h->n_global; P.inv_n = 1.0 / P.n_samples; P.l2 = h->l2;
     P.red_partials = h->red_partials; P.red_ticket = h->red_ticket + 7;
-    P.alpha_mode = h->world > 1 ? 1 : 0; P.alpha_raw = h->ypart + h->d; P.alpha_raw2 = h->scal + 17;   // the first is allreduced together with A't
+    P.alpha_mode = h->world > 1 ? 1 : 0; P.alpha_raw = alpha_raw; P.alpha_raw2 = h->scal + 17;   // the first is summed over the ranks with A't
     h->counters[3] += 1;
     return launch<kRowsLanczos>(h, h->csr, P);
 }

@@ -25,6 +25,9 @@ SIGNATURES = {
     "kcrn_sync": (c_int, [c_void_p]),
     "kcrn_nccl_unique_id": (c_int, [c_void_p]),
     "kcrn_comm_init": (c_int, [c_void_p, c_void_p, c_int, c_int]),
+    "kcrn_p2p_export": (c_int, [c_void_p, c_void_p]),
+    "kcrn_p2p_attach": (c_int, [c_void_p, c_void_p]),
+    "kcrn_p2p_enable": (c_int, [c_void_p, c_int]),
     "kcrn_csc_view": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "kcrn_set_x": (c_int, [c_void_p, c_void_p]),
     "kcrn_value": (c_int, [c_void_p, c_void_p]),

@@ -128,6 +128,18 @@ class Engine:
         check(self.lib.kcrn_comm_init(self.h, buf, int(rank), int(world)))
         self.world = int(world)
 
+    def p2p_export(self) -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        check(self.lib.kcrn_p2p_export(self.h, buf))
+        return buf.raw
+
+    def p2p_attach(self, all_handles: bytes):
+        buf = ctypes.create_string_buffer(bytes(all_handles), len(all_handles))
+        check(self.lib.kcrn_p2p_attach(self.h, buf))
+
+    def p2p_enable(self, on: bool):
+        check(self.lib.kcrn_p2p_enable(self.h, int(bool(on))))
+
     def nccl_unique_id(self) -> bytes:
         buf = ctypes.create_string_buffer(128)
         check(self.lib.kcrn_nccl_unique_id(buf))

@@ -54,13 +54,48 @@ def main():
     ref = h.clone()
     dist.broadcast(ref, 0)
     errs["replica_bits_equal"] = 0.0 if torch.equal(ref, h) else 1.0
+    # fused Lanczos: the epilogue kernel that sums the ranks' partial A't over NVLink peer memory against the NCCL
+    # allreduce in front of the same epilogue.  Odd m replayed back to back (no host sync) exercises the
+    # read-done acknowledgement between runs; m = 10 with re-orthogonalisation the second epilogue stage.
+    eng = loss.engine
+    eng.set_x(xd)
+    gd = loss.gradient(xd)
+    for m, reorth in ((5, False), (10, True), (1, False)):
+        got = {}
+        for mode in (True, False):
+            try:
+                eng.p2p_enable(mode)
+            except Exception as e:       # peer exchange not attached (no peer access): nothing to compare
+                print(f"rank {rank}: peer exchange unavailable ({e})", flush=True)
+                break
+            for _ in range(12):
+                eng.lanczos(m, reorth=reorth, g=gd)
+            V, a, bt, info = eng.lanczos_view()
+            torch.cuda.synchronize()
+            got[mode] = (a.cpu().numpy().copy(), bt.cpu().numpy().copy(), V.cpu().numpy().copy())
+            if mode:
+                mine = torch.cat([a.flatten(), bt.flatten(), V.flatten()])
+                ref0 = mine.clone()
+                dist.broadcast(ref0, 0)
+                if not torch.equal(ref0, mine):
+                    errs["peer_replica_bits_equal"] = 1.0
+        if len(got) == 2:
+            key = f"peer_vs_nccl_m{m}{'_reorth' if reorth else ''}"
+            errs[key] = max(rel(got[True][0], got[False][0]), rel(got[True][2][:2], got[False][2][:2]))
+            if errs[key] > 1e-10:
+                errs["peer_fail"] = 1.0
+    try:
+        eng.p2p_enable(True)
+    except Exception:
+        pass
     opt = Cubic_Krylov_LS(loss=loss, reg_coef=1e-3, subspace_dim=10, tolerance=1e-9, label="mg", tqdm=False)
     opt.run(P.x0, it_max=8)
     g = np.load(os.path.join(HERE, "golden", f"traj_{name}.npz"))
     f = np.array([hh["f"] for hh in opt.history])
     errs["trajectory_prefix"] = float(np.max(np.abs(f - g["m10_ref_f"][:len(f)]) / np.abs(g["m10_ref_f"][:len(f)])))
     ok = (errs["value"] <= 1e-12 and errs["gradient"] <= 1e-12 and errs["hvp"] <= 1e-12
-          and errs["replica_bits_equal"] == 0.0 and errs["trajectory_prefix"] <= 1e-8)
+          and errs["replica_bits_equal"] == 0.0 and errs["trajectory_prefix"] <= 1e-8
+          and "peer_fail" not in errs and "peer_replica_bits_equal" not in errs)
     cnt = loss.engine.counters()
     print(f"rank {rank}/{world}: rows {S.n} nnz {S.nnz} errs {errs} allreduces {cnt['allreduces']} -> {'OK' if ok else 'FAIL'}",
           flush=True)
