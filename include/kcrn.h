@@ -59,12 +59,13 @@ int kcrn_sync(kcrn_handle h);
 int kcrn_nccl_unique_id(void *unique_id_128_host);
 int kcrn_comm_init(kcrn_handle h, const void *unique_id_128_host, int rank, int world);
 
-/* Optional, after kcrn_comm_init on ranks that share one NVLink domain: exchange buffers mapped into every peer
- * (CUDA IPC).  export writes this rank's two 64-byte cudaIpcMemHandle_t; the host plumbing all-gathers them
- * (world x 128 bytes, rank order) and hands them to attach.  The fused Lanczos step then adds the partial A't of
- * all ranks inside its epilogue kernel through NVLink peer loads (no NCCL call) whenever the d-vector is small
- * enough for the collective to be latency-bound; gradient, HVP and value keep the NCCL allreduce. */
-int kcrn_p2p_export(kcrn_handle h, void *handles_128_host);
+/* Optional, after kcrn_comm_init on ranks that share one NVLink domain (one GPU per rank): receive buffers mapped
+ * into every peer (CUDA IPC).  export writes this rank's 64-byte cudaIpcMemHandle_t; the host plumbing all-gathers
+ * them (world x 64 bytes, rank order) and hands them to attach.  The fused Lanczos step then sums the partial A't
+ * of all ranks inside its epilogue kernel -- each rank pushes {value, step} slots into its peers over NVLink and
+ * polls its own buffer; no NCCL call -- whenever (world - 1)(d + 2) 16 bytes <= 8 MiB, i.e. where the collective is
+ * latency-bound (otherwise both calls are no-ops and NCCL stays); gradient, HVP and value keep NCCL. */
+int kcrn_p2p_export(kcrn_handle h, void *handle_64_host);
 int kcrn_p2p_attach(kcrn_handle h, const void *all_handles_host);
 /* Collective (every rank, same value): switch between the fused peer exchange (1) and NCCL (0); A/B and tests. */
 int kcrn_p2p_enable(kcrn_handle h, int on);

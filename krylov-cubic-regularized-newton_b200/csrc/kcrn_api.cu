@@ -23,6 +23,8 @@ int launch_lanczos_finish(kcrn_problem *h);
 int launch_sumsq(kcrn_problem *h, const double *a, int64_t len, double *out);
 int launch_value_combine(kcrn_problem *h, double *out);
 int launch_scale(kcrn_problem *h, const double *y, const double *u, double *out);
+int launch_scale_peer(kcrn_problem *h, const double *y_partial, const double *u, double *out);
+int launch_value_combine_peer(kcrn_problem *h, double *out);
 int launch_record(kcrn_problem *h);
 int config4_hessian_dense(kcrn_problem *h, double *out);
 int config4_partial_gradient(kcrn_problem *h, const int64_t *I, int m, double *out);
@@ -66,6 +68,7 @@ int need_x(kcrn_problem *h, const char *what) {
 int cols_product(kcrn_problem *h, const double *src, const double *u, double *out) {
     if (h->world > 1) {
         KCRN_TRY(launch_cols_raw(h, src, h->ypart));
+        if (h->p2p_ready) return launch_scale_peer(h, h->ypart, u, out);     // the sum over the ranks inside
         KCRN_TRY(nccl_allreduce_sum(h, h->ypart, h->d));
         return launch_scale(h, h->ypart, u, out);
     }
@@ -74,8 +77,9 @@ int cols_product(kcrn_problem *h, const double *src, const double *u, double *ou
 
 int enqueue_value(kcrn_problem *h, double *out) {
     KCRN_TRY(launch_sum(h, h->ell, h->n, 1.0, h->scal + 1));
-    if (h->world > 1) KCRN_TRY(nccl_allreduce_sum(h, h->scal + 1, 1));
     if (h->l2 != 0.0) KCRN_TRY(launch_sumsq(h, h->x_cur, h->d, h->scal + 2));
+    if (h->world > 1 && h->p2p_ready) return launch_value_combine_peer(h, out);
+    if (h->world > 1) KCRN_TRY(nccl_allreduce_sum(h, h->scal + 1, 1));
     return launch_value_combine(h, out);
 }
 
@@ -85,22 +89,16 @@ int enqueue_lanczos(kcrn_problem *h, int m, int reorth) {
     for (int slot = 0; slot < m; ++slot) {
         // rows sweep: t = D (A v), basis column, and alpha = v'Hv one sweep early (so that the column sweep can
         // form w' = Hv - beta v_prev - alpha v and beta = |w'| itself: two kernels per Lanczos step)
-        const bool peer = h->world > 1 && h->p2p_ready &&
-                          (int64_t)(h->world - 1) * h->d * (int64_t)sizeof(double) <= (8 << 20);
-        if (peer) {
-            // fused epilogue + allreduce over NVLink peer memory (small d: the collective is latency-bound)
-            double *buf = h->p2p_y + (size_t)(slot & 1) * (size_t)(h->d + 2);
-            KCRN_TRY(launch_rows_lanczos(h, buf + h->d));
-            KCRN_TRY(launch_cols_raw(h, h->t, buf));
-            KCRN_TRY(launch_lanczos_post_peer(h, slot & 1, reorth));
-            if (reorth && slot + 1 < m) KCRN_TRY(launch_lanczos_update(h, 1, 1));
-            continue;
-        }
         KCRN_TRY(launch_rows_lanczos(h, h->ypart + h->d));
         if (h->world > 1) {
             KCRN_TRY(launch_cols_raw(h, h->t, h->ypart));
-            KCRN_TRY(nccl_allreduce_sum(h, h->ypart, (h->d + 2) & ~(int64_t)1));   // even count: 16-byte multiple
-            KCRN_TRY(launch_lanczos_post_sharded(h, h->ypart, reorth));
+            if (h->p2p_ready) {
+                // small d: the sum over the ranks happens inside the epilogue kernel, over NVLink peer memory
+                KCRN_TRY(launch_lanczos_post_peer(h, h->ypart, reorth));
+            } else {
+                KCRN_TRY(nccl_allreduce_sum(h, h->ypart, (h->d + 2) & ~(int64_t)1));   // even count: 16-byte multiple
+                KCRN_TRY(launch_lanczos_post_sharded(h, h->ypart, reorth));
+            }
         } else if (slot + 1 < m) {
             KCRN_TRY(launch_cols_lanczos(h, reorth ? 0 : 1));
         }
@@ -261,12 +259,10 @@ int kcrn_destroy(kcrn_handle h) {
     for (auto &ge : h->graphs) cudaGraphExecDestroy(ge.exec);
     h->graphs.clear();
     cudaDeviceSynchronize();
-    for (int k = 0; k < kMaxPeers; ++k) {
-        if (k != h->rank && h->peer_y[k]) cudaIpcCloseMemHandle(h->peer_y[k]);
-        if (k != h->rank && h->peer_flags[k]) cudaIpcCloseMemHandle(h->peer_flags[k]);
-    }
-    cudaFree(h->p2p_y);
-    cudaFree(h->p2p_flags);
+    for (int k = 0; k < kMaxPeers; ++k)
+        if (k != h->rank && h->peer_recv[k]) cudaIpcCloseMemHandle(h->peer_recv[k]);
+    cudaFree(h->p2p_recv);
+    cudaFree(h->p2p_epoch);
     nccl_destroy(h);
     free_segmat(&h->csr);
     free_segmat(&h->csc);
@@ -307,41 +303,49 @@ int kcrn_comm_init(kcrn_handle h, const void *unique_id_128_host, int rank, int 
     return nccl_init(h, unique_id_128_host, rank, world);
 }
 
-int kcrn_p2p_export(kcrn_handle h, void *handles_128_host) {
-    if (!h || !handles_128_host) { set_error("kcrn_p2p_export: null argument"); return KCRN_E_ARG; }
-    if (!h->p2p_y) {
-        KCRN_CUDA(cudaMalloc(&h->p2p_y, sizeof(double) * 2 * (size_t)(h->d + 2)));
-        KCRN_CUDA(cudaMalloc(&h->p2p_flags, sizeof(unsigned) * 3 * kMaxPeers));
-        KCRN_CUDA(cudaMemset(h->p2p_y, 0, sizeof(double) * 2 * (size_t)(h->d + 2)));
-        KCRN_CUDA(cudaMemset(h->p2p_flags, 0, sizeof(unsigned) * 3 * kMaxPeers));
-    }
-    cudaIpcMemHandle_t hy, hf;
-    KCRN_CUDA(cudaIpcGetMemHandle(&hy, h->p2p_y));
-    KCRN_CUDA(cudaIpcGetMemHandle(&hf, h->p2p_flags));
+// pushes of one exchange step, per rank: (world - 1) (d + 2) slots of 16 bytes; beyond a few MB the collective is
+// bandwidth-bound and NCCL's ring / NVLS does better than all-to-all pushes
+static bool p2p_fits(const kcrn_problem *h) {
+    // the CTAs of the exchanging kernel wait for CTAs of the SAME kernel on the peers: all of them must be co-resident
+    return h->world >= 2 && h->world <= kMaxPeers && (int64_t)(h->world - 1) * (h->d + 2) * 16 <= (int64_t)8 << 20 &&
+           h->vec_grid <= kNumSm * 4;
+}
+
+int kcrn_p2p_export(kcrn_handle h, void *handle_64_host) {
+    if (!h || !handle_64_host) { set_error("kcrn_p2p_export: null argument"); return KCRN_E_ARG; }
+    if (h->world < 2) { set_error("kcrn_p2p_export: kcrn_comm_init first"); return KCRN_E_STATE; }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    memcpy(handles_128_host, &hy, 64);
-    memcpy((char *)handles_128_host + 64, &hf, 64);
+    memset(handle_64_host, 0, 64);
+    if (!p2p_fits(h)) return KCRN_OK;         // attach will leave the NCCL path in place
+    if (!h->p2p_recv) {
+        const size_t bytes = sizeof(uint4) * 2 * (size_t)h->world * (size_t)(h->d + 2);
+        KCRN_CUDA(cudaMalloc(&h->p2p_recv, bytes));
+        KCRN_CUDA(cudaMalloc(&h->p2p_epoch, sizeof(unsigned)));
+        KCRN_CUDA(cudaMemset(h->p2p_recv, 0, bytes));
+        KCRN_CUDA(cudaMemset(h->p2p_epoch, 0, sizeof(unsigned)));
+        KCRN_CUDA(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t hr;
+    KCRN_CUDA(cudaIpcGetMemHandle(&hr, h->p2p_recv));
+    memcpy(handle_64_host, &hr, 64);
     return KCRN_OK;
 }
 
 int kcrn_p2p_attach(kcrn_handle h, const void *all_handles_host) {
     if (!h || !all_handles_host) { set_error("kcrn_p2p_attach: null argument"); return KCRN_E_ARG; }
-    if (h->world < 2 || h->world > kMaxPeers || !h->p2p_y) {
-        set_error("kcrn_p2p_attach: needs kcrn_comm_init (2..%d ranks) and kcrn_p2p_export first", kMaxPeers);
-        return KCRN_E_STATE;
-    }
+    if (h->world < 2) { set_error("kcrn_p2p_attach: kcrn_comm_init first"); return KCRN_E_STATE; }
+    if (!p2p_fits(h)) return KCRN_OK;
+    if (!h->p2p_recv) { set_error("kcrn_p2p_attach: kcrn_p2p_export first"); return KCRN_E_STATE; }
+    if (h->peer_recv[h->rank]) { set_error("kcrn_p2p_attach: already attached"); return KCRN_E_STATE; }
     for (auto &ge : h->graphs) cudaGraphExecDestroy(ge.exec);
     h->graphs.clear();
     for (int k = 0; k < h->world; ++k) {
-        if (k == h->rank) { h->peer_y[k] = h->p2p_y; h->peer_flags[k] = h->p2p_flags; continue; }
-        cudaIpcMemHandle_t hy, hf;
-        memcpy(&hy, (const char *)all_handles_host + (size_t)k * 128, 64);
-        memcpy(&hf, (const char *)all_handles_host + (size_t)k * 128 + 64, 64);
-        void *py = nullptr, *pf = nullptr;
-        KCRN_CUDA(cudaIpcOpenMemHandle(&py, hy, cudaIpcMemLazyEnablePeerAccess));
-        KCRN_CUDA(cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess));
-        h->peer_y[k] = (double *)py;
-        h->peer_flags[k] = (unsigned *)pf;
+        if (k == h->rank) { h->peer_recv[k] = h->p2p_recv; continue; }
+        cudaIpcMemHandle_t hr;
+        memcpy(&hr, (const char *)all_handles_host + (size_t)k * 64, 64);
+        void *pr = nullptr;
+        KCRN_CUDA(cudaIpcOpenMemHandle(&pr, hr, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_recv[k] = (uint4 *)pr;
     }
     h->p2p_ready = getenv("KCRN_NO_P2P") == nullptr;
     return KCRN_OK;
@@ -349,7 +353,7 @@ int kcrn_p2p_attach(kcrn_handle h, const void *all_handles_host) {
 
 int kcrn_p2p_enable(kcrn_handle h, int on) {
     if (!h) { set_error("kcrn_p2p_enable: null handle"); return KCRN_E_ARG; }
-    if (on && !h->peer_y[h->rank]) { set_error("kcrn_p2p_enable: kcrn_p2p_attach first"); return KCRN_E_STATE; }
+    if (on && !h->peer_recv[h->rank]) { set_error("kcrn_p2p_enable: no peer exchange attached (kcrn_p2p_attach; d too large?)"); return KCRN_E_STATE; }
     if ((on != 0) != h->p2p_ready) {
         KCRN_CUDA(cudaStreamSynchronize(h->stream));
         for (auto &ge : h->graphs) cudaGraphExecDestroy(ge.exec);

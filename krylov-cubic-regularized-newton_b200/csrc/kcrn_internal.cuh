@@ -165,11 +165,9 @@ struct kcrn_problem {
     void *comm = nullptr;
     int rank = 0, world = 1;
     // NVLink peer exchange of the fused Lanczos step (kcrn_p2p_export / kcrn_p2p_attach)
-    double *p2p_y = nullptr;            // [2][d + 2] my partial A't (+ alpha partial), double-buffered by step parity
-    unsigned *p2p_flags = nullptr;      // [kMaxPeers] arrival epochs written by the peers, [kMaxPeers] my
-                                        // epoch, [kMaxPeers] read-done acknowledgements written by the peers
-    double *peer_y[kcrn::kMaxPeers] = {};
-    unsigned *peer_flags[kcrn::kMaxPeers] = {};
+    uint4 *p2p_recv = nullptr;          // [2][world][d + 2] slots {value.lo, step, value.hi, step} the peers push into
+    unsigned *p2p_epoch = nullptr;      // exchange steps done so far (device counter; picks the buffer half)
+    uint4 *peer_recv[kcrn::kMaxPeers] = {};
     bool p2p_ready = false;
     int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool pdl = false;              // launch with programmatic dependent launch (set while the Lanczos graph is built)
@@ -202,7 +200,7 @@ int launch_lanczos_init(kcrn_problem *h, int m);      // ctl, alphas, bet reset;
 int launch_lanczos_post(kcrn_problem *h, const double *hv_or_raw, int raw);  // epilogue after allreduce / generic feed
 int launch_lanczos_update(kcrn_problem *h, int reorth, int fused);
 int launch_lanczos_post_sharded(kcrn_problem *h, const double *y_allreduced, int reorth);
-int launch_lanczos_post_peer(kcrn_problem *h, int buf, int reorth);
+int launch_lanczos_post_peer(kcrn_problem *h, const double *y_partial, int reorth);
 int launch_normalise_current(kcrn_problem *h);        // V[col] = src / bet[col] outside the fused sweep
 int launch_sum(kcrn_problem *h, const double *a, int64_t len, double scale, double *out);  // deterministic sum
 int launch_axpy_basis(const double *x, const double *V, const double *s, int m, const int32_t *info,

@@ -22,6 +22,17 @@ namespace kcrn {
 
 namespace {
 
+// Receive buffers of the NVLink peer exchange (kcrn_p2p_attach): every rank's buffer mapped into this process,
+// mine, the count of exchange steps done so far (device-side; its parity picks the buffer half), a ticket for
+// the kernels that need "last CTA" to bump it.  Slot layout: [half][source rank][d + 2].
+struct PeerSet {
+    uint4 *recv[kMaxPeers];
+    uint4 *mine;
+    unsigned *epoch, *ticket;
+    int rank, world;
+    int64_t stride;
+};
+
 struct VecParams {
     LanczosCtl *ctl;
     double *V;
@@ -39,12 +50,9 @@ struct VecParams {
     int from_wp;               // reorth stage 1 inside the fused loop: w' was already formed by the column sweep
     const double *alpha_raw, *alpha_raw2;   // row-sharded fused loop: sum_i t_i (Av)_i (allreduced) and |v|^2
     double inv_n;
-    // fused epilogue + allreduce over NVLink peer memory (kcrn_p2p_attach): every rank's exchange buffer and
-    // arrival flags, mapped into this process
-    const double *peer_y[kMaxPeers];
-    unsigned *peer_flags[kMaxPeers];
-    unsigned *my_flags, *epoch;
-    int rank, world;
+    // fused epilogue + allreduce over NVLink peer memory (kcrn_p2p_attach): every rank's receive buffer mapped
+    // into this process, mine, and my step counter
+    PeerSet peer;
     double n_samples, l2;
     int32_t *info;
 };
@@ -93,13 +101,6 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_init_kernel(VecParams P) 
     }
     double tot = 0.0;
     if (!grid_sum(loc, P.red_partials, P.red_ticket, sh, &s_last, &tot)) return;
-    if (P.my_flags && threadIdx.x < P.world) {
-        // peer exchange: the two buffers alternate inside a run, but a new run restarts at buffer 0 -- do not let the
-        // sweeps that follow overwrite it before every peer has finished reading my vectors of the previous run
-        const unsigned seen = *P.epoch;
-        const volatile unsigned *ack = P.my_flags + 2 * kMaxPeers + threadIdx.x;
-        while (*ack < seen) __nanosleep(40);
-    }
     for (int i = threadIdx.x; i < P.m; i += blockDim.x) {
         P.alphas[i] = 0.0;
         P.bet[i + 1] = 0.0;
@@ -165,38 +166,72 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_post_kernel(VecParams P) 
 // Row-sharded fused loop, after the allreduce of {A't, sum_i t_i (Av)_i}: alpha = v'Hv, w' = y/n + l2 v -
 // beta_prev v_prev - alpha v, beta = |w'|, then the bookkeeping of cubic.py:98-109 -- replicated on every rank.
 //
-// PEER = true: no NCCL call in front of it -- the kernel itself is the allreduce.  Every rank publishes "my partial
-// A't is complete" by storing a new epoch into its slot of every peer's flag array (NVLink peer stores), waits
-// until all slots of its own array show that epoch, then reads the partial vectors of all ranks through peer
-// pointers and adds them in rank order -- the same order on every rank, so the replicas stay bit-identical --
-// while it applies the epilogue.  One pass over the d-vector instead of reduce + broadcast + epilogue, and the
-// latency of one flag round instead of a collective launch (the 378 KB vector of the rcv1 shape is latency-bound).
-// The exchange buffer is double-buffered by step parity, so a rank may run ahead by one step without overwriting
-// data a slower rank still reads.
+// PEER = true: no NCCL call in front of it -- the kernel itself is the allreduce, in the style of NCCL's
+// low-latency protocol.  Every rank PUSHES its partial A't into a slot of every peer's receive buffer with 16-byte
+// stores {value.lo, step, value.hi, step} (posted NVLink writes: one-way latency, no fence, no separate flag), then
+// polls the slots of its own buffer -- local L2 reads -- until both step words match, and adds the ranks' values
+// in rank order (the same order on every rank, so the replicas stay bit-identical) while it applies the
+// epilogue.  A thread pushes and polls the same elements, so there is no intra-kernel barrier.  The receive
+// buffer is double-buffered by the parity of the step counter: a rank can start step s+2 only after it received
+// everybody's step s+1 data, i.e. after every peer has finished reading step s.
+__device__ __forceinline__ void ll_push(uint4 *slot, double v, unsigned step) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(slot), "r"((unsigned)__double2loint(v)),
+                 "r"(step), "r"((unsigned)__double2hiint(v)), "r"(step)
+                 : "memory");
+}
+
+__device__ __forceinline__ double ll_poll(const uint4 *slot, unsigned step) {
+    unsigned lo, f0, hi, f1;
+    unsigned long long t0 = 0;
+    for (unsigned spin = 0;; ++spin) {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(slot) : "memory");
+        if (f0 == step && f1 == step) break;
+        if ((spin & 0xffffu) == 0xffffu) {       // a peer that died must not hang the box: give up after ~20 s
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 20000000000ull) __trap();
+        }
+    }
+    return __hiloint2double((int)hi, (int)lo);
+}
+
 template <int E, bool PEER>
 __global__ void __launch_bounds__(kVecThreads) lanczos_post_sharded_kernel(VecParams P) {
     __shared__ double sh[kVecThreads / 32];
+    __shared__ double s_alpha[kMaxPeers];
     __shared__ int s_last;
     pdl_wait();
     pdl_trigger();
     if (P.ctl->done) return;
     const int col = P.ctl->col, store_idx = P.ctl->store_idx;
     const bool final_ = P.ctl->final_ != 0;
-    unsigned target = 0;
-    double s1 = 0.0;
+    const int64_t base = (int64_t)blockIdx.x * (kVecThreads * E) + threadIdx.x;
+    unsigned step = 0;
+    const uint4 *mine = nullptr;
+    double s1 = 0.0, ymine[E];
     if constexpr (PEER) {
-        target = *P.epoch + 1u;
-        if (blockIdx.x == 0 && threadIdx.x < P.world) {
-            __threadfence_system();                                   // my partial vector before my flag
-            *reinterpret_cast<volatile unsigned *>(P.peer_flags[threadIdx.x] + P.rank) = target;
+        const PeerSet &S = P.peer;
+        step = *S.epoch + 1u;
+        mine = S.mine + (size_t)(step & 1u) * S.world * S.stride;
+        const size_t my_slot = ((size_t)(step & 1u) * S.world + S.rank) * S.stride;
+        if (blockIdx.x == 0 && threadIdx.x < S.world && threadIdx.x != S.rank)
+            ll_push(S.recv[threadIdx.x] + my_slot + P.d, P.alpha_raw[0], step);
+        if (!final_) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int64_t c = base + (int64_t)e * kVecThreads;
+                if (c < P.d) {
+                    ymine[e] = P.w_in[c];
+                    for (int k = 0; k < S.world; ++k)
+                        if (k != S.rank) ll_push(S.recv[k] + my_slot + c, ymine[e], step);
+                }
+            }
         }
-        if (threadIdx.x < P.world) {
-            const volatile unsigned *f = P.my_flags + threadIdx.x;
-            while (*f < target) __nanosleep(40);
-            __threadfence_system();                                   // flags before the peers' vectors
-        }
+        if (threadIdx.x < S.world)
+            s_alpha[threadIdx.x] = threadIdx.x == S.rank ? P.alpha_raw[0] : ll_poll(mine + threadIdx.x * S.stride + P.d, step);
         __syncthreads();
-        for (int k = 0; k < P.world; ++k) s1 += __ldcv(P.peer_y[k] + P.d);
+        for (int k = 0; k < S.world; ++k) s1 += s_alpha[k];
     } else {
         s1 = P.alpha_raw[0];
     }
@@ -205,7 +240,6 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_post_sharded_kernel(VecPa
     const bool subtract = col > 0;
     const double *vpre = subtract ? P.V + (size_t)(col - 1) * P.d : nullptr;
     const double beta_prev = subtract ? P.bet[col] : 0.0;
-    const int64_t base = (int64_t)blockIdx.x * (kVecThreads * E) + threadIdx.x;
     double loc = 0.0;
     if (!final_) {
 #pragma unroll
@@ -216,7 +250,8 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_post_sharded_kernel(VecPa
                 double y;
                 if constexpr (PEER) {
                     y = 0.0;
-                    for (int k = 0; k < P.world; ++k) y += __ldcv(P.peer_y[k] + c);   // rank order: identical everywhere
+                    for (int k = 0; k < P.peer.world; ++k)      // rank order: identical bits everywhere
+                        y += k == P.peer.rank ? ymine[e] : ll_poll(mine + (size_t)k * P.peer.stride + c, step);
                 } else {
                     y = P.w_in[c];
                 }
@@ -231,12 +266,7 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_post_sharded_kernel(VecPa
     double tot = 0.0;
     if (!grid_sum(loc, P.red_partials, P.red_ticket, sh, &s_last, &tot)) return;
     if (threadIdx.x == 0) {
-        if constexpr (PEER) {
-            *P.epoch = target;
-            // all my CTAs have read the peers' vectors of this step (the ticket says so): acknowledge
-            for (int k = 0; k < P.world; ++k)
-                *reinterpret_cast<volatile unsigned *>(P.peer_flags[k] + 2 * kMaxPeers + P.rank) = target;
-        }
+        if constexpr (PEER) *P.peer.epoch = step;
         P.alphas[final_ ? store_idx : col] = alpha;
         P.ctl->hvps += 1;
         if (final_) P.ctl->done = 1;
@@ -405,6 +435,57 @@ __global__ void scale_kernel(const double *__restrict__ y, const double *__restr
     }
 }
 
+// the same with the sum over the ranks inside: y is this rank's partial A' r; push, poll, add in rank order
+__global__ void __launch_bounds__(kVecThreads) scale_peer_kernel(PeerSet S, const double *__restrict__ y,
+                                                                 const double *__restrict__ u, int64_t d,
+                                                                 double n_samples, double l2, double *__restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
+    const unsigned step = *S.epoch + 1u;
+    const uint4 *mine = S.mine + (size_t)(step & 1u) * S.world * S.stride;
+    const size_t my_slot = ((size_t)(step & 1u) * S.world + S.rank) * S.stride;
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, hop = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = first; i < d; i += hop) {
+        const double v = y[i];
+        for (int k = 0; k < S.world; ++k)
+            if (k != S.rank) ll_push(S.recv[k] + my_slot + i, v, step);
+    }
+    for (int64_t i = first; i < d; i += hop) {
+        double tot = 0.0;
+        for (int k = 0; k < S.world; ++k) tot += k == S.rank ? y[i] : ll_poll(mine + (size_t)k * S.stride + i, step);
+        double v = tot / n_samples;
+        if (u) v = __dadd_rn(v, __dmul_rn(l2, u[i]));
+        out[i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicInc(S.ticket, gridDim.x - 1) == gridDim.x - 1) *S.epoch = step;
+}
+
+// value with the sum of the ranks' loss terms inside (one warp; slot d + 1 of the exchange buffer)
+__global__ void value_combine_peer_kernel(PeerSet S, const double *scal, int64_t d, double n_samples, double l2,
+                                          double *out) {
+    const unsigned step = *S.epoch + 1u;
+    const uint4 *mine = S.mine + (size_t)(step & 1u) * S.world * S.stride;
+    const size_t my_slot = ((size_t)(step & 1u) * S.world + S.rank) * S.stride;
+    const int lane = threadIdx.x;
+    double part = 0.0;
+    if (lane < S.world) {
+        if (lane != S.rank) ll_push(S.recv[lane] + my_slot + d + 1, scal[1], step);
+        part = lane == S.rank ? scal[1] : ll_poll(mine + (size_t)lane * S.stride + d + 1, step);
+    }
+    double tot = 0.0;
+    for (int k = 0; k < S.world; ++k) tot += __shfl_sync(0xffffffffu, part, k);
+    if (lane == 0) {
+        double v = tot / n_samples;
+        if (l2 != 0.0) {
+            const double nx = sqrt(scal[2]);
+            v = __dadd_rn(v, __dmul_rn(l2 / 2.0, __dmul_rn(nx, nx)));
+        }
+        out[0] = v;
+        *S.epoch = step;
+    }
+}
+
 // out = x + sum_{i < cols} s[i] V[i]     (cubic.py:291,301); optionally |out - x| for the stopping rule
 // of the step loop (optimizer.py:110)
 __global__ void __launch_bounds__(kVecThreads) axpy_basis_kernel(const double *__restrict__ x,
@@ -443,6 +524,14 @@ VecParams base_params(kcrn_problem *h) {
     return P;
 }
 
+PeerSet peer_set(kcrn_problem *h) {
+    PeerSet S{};
+    for (int k = 0; k < h->world; ++k) S.recv[k] = h->peer_recv[k];
+    S.mine = h->p2p_recv; S.epoch = h->p2p_epoch; S.ticket = h->red_ticket + 6;
+    S.rank = h->rank; S.world = h->world; S.stride = h->d + 2;
+    return S;
+}
+
 int grid_stride_blocks(int64_t len) {
     int64_t b = (len + kVecThreads - 1) / kVecThreads;
     if (b < 1) b = 1;
@@ -473,7 +562,6 @@ int launch_lanczos_init(kcrn_problem *h, int m) {
     VecParams P = base_params(h);
     P.m = m;
     P.red_ticket = h->red_ticket + 4;
-    if (h->p2p_ready) { P.my_flags = h->p2p_flags; P.epoch = h->p2p_flags + kMaxPeers; P.world = h->world; }
     KCRN_CUDA(launch_kernel(lanczos_init_kernel, dim3(grid_stride_blocks(h->d)), dim3(kVecThreads), 0, h->stream, h->pdl, P));
     h->counters[0] += 1;
     return KCRN_OK;
@@ -508,16 +596,14 @@ int launch_lanczos_post_sharded(kcrn_problem *h, const double *y_allreduced, int
     return KCRN_OK;
 }
 
-// the same with the allreduce done inside the kernel over peer memory; buf = parity of the Lanczos step
-int launch_lanczos_post_peer(kcrn_problem *h, int buf, int reorth) {
+// the same with the allreduce done inside the kernel over peer memory; y_partial = this rank's A't, alpha
+// partial behind it at [d]
+int launch_lanczos_post_peer(kcrn_problem *h, const double *y_partial, int reorth) {
     VecParams P = base_params(h);
-    P.alpha_raw2 = h->scal + 17; P.inv_n = 1.0 / P.n_samples; P.stage = reorth ? 1 : 0;
+    P.w_in = y_partial; P.alpha_raw = y_partial + h->d; P.alpha_raw2 = h->scal + 17; P.inv_n = 1.0 / P.n_samples;
+    P.stage = reorth ? 1 : 0;
     P.red_ticket = h->red_ticket + 2;
-    P.rank = h->rank; P.world = h->world; P.my_flags = h->p2p_flags; P.epoch = h->p2p_flags + kMaxPeers;
-    for (int k = 0; k < h->world; ++k) {
-        P.peer_y[k] = h->peer_y[k] + (size_t)buf * (size_t)(h->d + 2);
-        P.peer_flags[k] = h->peer_flags[k];
-    }
+    P.peer = peer_set(h);
     if (h->vec_elems == 4) KCRN_CUDA(launch_kernel(lanczos_post_sharded_kernel<4, true>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
     else KCRN_CUDA(launch_kernel(lanczos_post_sharded_kernel<1, true>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
     h->counters[0] += 1;
@@ -581,6 +667,22 @@ int launch_record(kcrn_problem *h) {
 int launch_scale(kcrn_problem *h, const double *y, const double *u, double *out) {
     KCRN_CUDA(launch_kernel(scale_kernel, dim3(grid_stride_blocks(h->d)), dim3(kVecThreads), 0, h->stream, h->pdl, y, u, h->d, (double)h->n_global, h->l2, out));
     h->counters[0] += 1;
+    return KCRN_OK;
+}
+
+int launch_scale_peer(kcrn_problem *h, const double *y_partial, const double *u, double *out) {
+    KCRN_CUDA(launch_kernel(scale_peer_kernel, dim3(grid_stride_blocks(h->d)), dim3(kVecThreads), 0, h->stream, h->pdl,
+                            peer_set(h), y_partial, u, h->d, (double)h->n_global, h->l2, out));
+    h->counters[0] += 1;
+    h->counters[5] += 1;
+    return KCRN_OK;
+}
+
+int launch_value_combine_peer(kcrn_problem *h, double *out) {
+    value_combine_peer_kernel<<<1, 32, 0, h->stream>>>(peer_set(h), h->scal, h->d, (double)h->n_global, h->l2, out);
+    KCRN_LAUNCH_CHECK();
+    h->counters[0] += 1;
+    h->counters[5] += 1;
     return KCRN_OK;
 }
 

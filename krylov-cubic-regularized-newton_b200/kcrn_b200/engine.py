@@ -129,7 +129,7 @@ class Engine:
         self.world = int(world)
 
     def p2p_export(self) -> bytes:
-        buf = ctypes.create_string_buffer(128)
+        buf = ctypes.create_string_buffer(64)
         check(self.lib.kcrn_p2p_export(self.h, buf))
         return buf.raw
 
