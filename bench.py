@@ -222,6 +222,37 @@ def main():
     hvps = sum(h["hvps"] for h in opt.history[n_hist:])
     value = world * hvps / (ms * 1e-3)
 
+    # ---------------- the same iterations with the step loop itself on the device (kcrn_krylov_run: one graph launch
+    # for K outer iterations, line search in WHILE nodes); no flush between the iterations of one launch
+    device_loop = None
+    try:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # the same iterations as above: restart at x0, W warm-up iterations (they also capture the graph), then K
+        v0 = loss.value(loss.to_device(P.x0))
+        eng.krylov_run(max(W, K), args.m, bool(args.reorth), v0, 1e-3, 0.5, 0.1)     # sizes the buffers, captures
+        loss.reset()
+        v0 = loss.value(loss.to_device(P.x0))
+        recs, _ = eng.krylov_run(W, args.m, bool(args.reorth), v0, 1e-3, 0.5, 0.1)
+        state = (recs[-1][0], recs[-1][12], recs[-1][2])
+        barrier()
+        flush.fill_(1)
+        ev0.record()
+        recs, _ = eng.krylov_run(K, args.m, bool(args.reorth), *state[:2], 0.5, state[2])
+        ev1.record()
+        barrier()
+        ms3 = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms3], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms3 = float(t.item())
+        device_loop = {"ms_per_step": ms3 / len(recs), "outer_iters_per_sec": 1e3 * len(recs) / ms3,
+                       "value": world * float(recs[:, 7].sum()) / (ms3 * 1e-3), "unit": UNIT, "steps": len(recs),
+                       "note": "K outer iterations in ONE graph launch, line search on the device; one L2 flush "
+                               "before the launch, none between its iterations"}
+        loss.reset()
+    except Exception as e:                                         # sharded without peer exchange: host loop only
+        device_loop = {"unavailable": str(e)[:200]}
+
     # ---------------- end to end: numpy iterate in pinned host memory goes in and comes back every step
     opt2 = Cubic_Krylov_LS(loss=loss, reg_coef=1e-3, subspace_dim=args.m, tolerance=0, reorth=bool(args.reorth),
                            label="bench-e2e", tqdm=False)
@@ -292,7 +323,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * P.d, "d2h_bytes_per_step": 8 * P.d + 120,
                 "ms_per_step": ms2 / K, "outer_iters_per_sec": 1e3 * K / ms2},
         "gpu_launches": cnt["kernels"], "graph_launches": cnt["graph_launches"],
-        "roofline": roofline, "clocks": clocks,
+        "roofline": roofline, "clocks": clocks, "device_loop": device_loop,
     }
     if rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

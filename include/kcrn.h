@@ -102,6 +102,24 @@ int kcrn_set_Ax(kcrn_handle h, const double *Ax_dev);
  * reorth = 1 adds two classical Gram-Schmidt passes against the basis per step (not in the
  * reference; SURVEY.md section 8(c) "reorth oracle").  Results stay in the handle: */
 int kcrn_lanczos(kcrn_handle h, const double *g_dev, int m, int reorth);
+/* Device-resident outer loop: up to max_iters iterations of Cubic_Krylov_LS.step
+ * (optimizer/cubic.py:265-309) as ONE graph launch -- the line search ("M = reg_coef * beta first", the test
+ * value_new > value - model_decrease and tries < max_tries, M / beta on rejection; cubic.py:286-302), the commit of
+ * (x, value, M, r0), the stopping rule |x_new - x| < tol (optimizer.py:110; tol <= 0: off) and the best-point
+ * tracking of Oracle.value (loss.py:70-72) run on the device, driving CUDA graph WHILE nodes; no host round trip
+ * until the run ends.  Needs kcrn_set_x; value0 = f at that x; f_opt = best value seen so far (+inf: none).
+ * Out: the number of iterations done, the sub-problem status of the last trial (0, or KCRN_E_NOTPD: the run stopped
+ * there), and one 16-double record per iteration: the 12 of kcrn_step_record ([11] = best value seen so far), accepted M, backtracks, seconds
+ * since the start of the run (device clock) and a flag "x_opt changed during this run".  keep_xs: also keep every
+ * accepted iterate (kcrn_run_view).  Afterwards the handle's x and caches are those of the last accepted iterate.
+ * Row-sharded runs need the peer exchange (kcrn_p2p_attach). */
+int kcrn_krylov_run(kcrn_handle h, int max_iters, int m, int reorth, double value0, double reg_coef, double beta,
+                    double r0, double eps, int solver_it_max, double tol, int max_tries, int keep_xs, double f_opt,
+                    int *iters_done_host, int *status_host, double *recs16_host);
+/* Device views after kcrn_krylov_run: accepted iterates [iters][d] (null without keep_xs), the best point [d]
+ * (valid when the record's flag is set), the current iterate [d]. */
+int kcrn_run_view(kcrn_handle h, const double **xs_dev, const double **x_opt_dev, const double **x_dev);
+
 /* basis V as m contiguous d-vectors, alphas[m], bet[m] with bet[0] = |g| and bet[j+1] = beta_j,
  * info[8] int32 = {m_eff, n_valid_columns, broke, hvps, 0...}.  Any pointer may be NULL. */
 int kcrn_lanczos_view(kcrn_handle h, const double **V_dev, const double **alphas_dev,

@@ -151,6 +151,124 @@ int run_graph(kcrn_problem *h, int kind, int m, int reorth, F enqueue) {
     return KCRN_OK;
 }
 
+// WHILE conditional node at the current capture point of `cap`; the loop body is returned as an empty graph to be
+// filled by a capture-to-graph on another stream.  The handle must belong to the graph `cap` captures into.
+int add_while_node(cudaStream_t cap, cudaGraphConditionalHandle handle, cudaGraph_t *body) {
+    cudaStreamCaptureStatus st;
+    unsigned long long id;
+    cudaGraph_t g = nullptr;
+    const cudaGraphNode_t *deps = nullptr;
+    size_t nd = 0;
+    KCRN_CUDA(cudaStreamGetCaptureInfo_v2(cap, &st, &id, &g, &deps, &nd));
+    cudaGraphNodeParams p = {};
+    p.type = cudaGraphNodeTypeConditional;
+    p.conditional.handle = handle;
+    p.conditional.type = cudaGraphCondTypeWhile;
+    p.conditional.size = 1;
+    cudaGraphNode_t node;
+    KCRN_CUDA(cudaGraphAddNode(&node, g, deps, nd, &p));
+    *body = p.conditional.phGraph_out[0];
+    KCRN_CUDA(cudaStreamUpdateCaptureDependencies(cap, &node, 1, cudaStreamSetCaptureDependencies));
+    return KCRN_OK;
+}
+
+int capture_graph_of(cudaStream_t cap, cudaGraph_t *g) {
+    cudaStreamCaptureStatus st;
+    unsigned long long id;
+    const cudaGraphNode_t *deps = nullptr;
+    size_t nd = 0;
+    KCRN_CUDA(cudaStreamGetCaptureInfo_v2(cap, &st, &id, g, &deps, &nd));
+    return KCRN_OK;
+}
+
+// The whole run as one graph:
+//   init; WHILE (iterations left, step not small) { begin; x_base = x; gradient; Lanczos;
+//                                                   WHILE (trial rejected) { sub-problem; x + V s; forward; value; record; decide }
+//                                                   snapshot; commit }
+int build_run_graph(kcrn_problem *h, int m, int reorth, cudaGraphExec_t *exec_out) {
+    cudaStream_t user = h->stream, cap[3] = {nullptr, nullptr, nullptr};
+    for (auto &c : cap) KCRN_CUDA(cudaStreamCreateWithFlags(&c, cudaStreamNonBlocking));
+    int64_t saved[8], mark[8];
+    memcpy(saved, h->counters, sizeof(saved));
+    cudaGraph_t graph = nullptr, outer_body = nullptr, trial_body = nullptr, g0 = nullptr;
+    cudaGraphConditionalHandle outer_loop = 0, trial_loop = 0;
+    int open = 0;
+    auto body = [&]() -> int {
+        h->pdl = h->allow_pdl;
+        h->stream = cap[0];
+        KCRN_CUDA(cudaStreamBeginCapture(cap[0], cudaStreamCaptureModeRelaxed));
+        open = 1;
+        memcpy(mark, h->counters, sizeof(mark));
+        KCRN_TRY(launch_run_init(h));
+        KCRN_TRY(capture_graph_of(cap[0], &g0));
+        KCRN_CUDA(cudaGraphConditionalHandleCreate(&outer_loop, g0, 1, cudaGraphCondAssignDefault));
+        KCRN_TRY(add_while_node(cap[0], outer_loop, &outer_body));
+        for (int i = 0; i < 8; ++i) h->run_delta[0][i] = h->counters[i] - mark[i];
+        // ---- one outer iteration
+        h->stream = cap[1];
+        KCRN_CUDA(cudaStreamBeginCaptureToGraph(cap[1], outer_body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+        open = 2;
+        memcpy(mark, h->counters, sizeof(mark));
+        KCRN_CUDA(cudaGraphConditionalHandleCreate(&trial_loop, outer_body, 1, 0));
+        KCRN_TRY(launch_run_begin(h, (unsigned long long)trial_loop));
+        KCRN_CUDA(cudaMemcpyAsync(h->x_base, h->x_cur, sizeof(double) * h->d, cudaMemcpyDeviceToDevice, h->stream));
+        KCRN_TRY(cols_product(h, h->resid, h->l2 != 0.0 ? h->x_cur : nullptr, h->g));      // gradient
+        KCRN_TRY(enqueue_lanczos(h, m, reorth));
+        h->counters[2] += m;
+        KCRN_TRY(add_while_node(cap[1], trial_loop, &trial_body));
+        int64_t outer_part[8];
+        for (int i = 0; i < 8; ++i) outer_part[i] = h->counters[i] - mark[i];
+        // ---- one trial of the line search
+        h->stream = cap[2];
+        KCRN_CUDA(cudaStreamBeginCaptureToGraph(cap[2], trial_body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+        open = 3;
+        memcpy(mark, h->counters, sizeof(mark));
+        h->counters[0] += 2;
+        KCRN_TRY(launch_cubic(h->alphas, h->bet + 1, m, h->info, h->bet, 0.0, 0.0, 0.0, 0.0, 0, h->sub, h->sub + kMaxM,
+                              h->stream, h->step_params));
+        KCRN_TRY(launch_axpy_basis(h->x_base, h->V, h->sub, m, h->info, h->d, h->x_cur, h->stream, h->red_partials,
+                                   h->red_ticket + 5, h->scal + 3));
+        KCRN_TRY(launch_forward(h, h->x_cur));
+        KCRN_TRY(enqueue_value(h, h->scal + 0));
+        KCRN_TRY(launch_record(h));
+        KCRN_TRY(launch_run_decide(h, (unsigned long long)trial_loop));
+        for (int i = 0; i < 8; ++i) h->run_delta[2][i] = h->counters[i] - mark[i];
+        KCRN_CUDA(cudaStreamEndCapture(cap[2], nullptr));
+        open = 2;
+        // ---- back in the outer iteration
+        h->stream = cap[1];
+        memcpy(mark, h->counters, sizeof(mark));
+        KCRN_TRY(launch_run_commit(h, (unsigned long long)outer_loop));
+        for (int i = 0; i < 8; ++i) h->run_delta[1][i] = outer_part[i] + h->counters[i] - mark[i];
+        KCRN_CUDA(cudaStreamEndCapture(cap[1], nullptr));
+        open = 1;
+        h->stream = cap[0];
+        KCRN_CUDA(cudaStreamEndCapture(cap[0], &graph));
+        open = 0;
+        return KCRN_OK;
+    };
+    int rc = body();
+    if (rc != KCRN_OK) {                       // unwind whatever capture is still open, innermost first
+        cudaGraph_t junk = nullptr;
+        if (open >= 3) cudaStreamEndCapture(cap[2], nullptr);
+        if (open >= 2) cudaStreamEndCapture(cap[1], nullptr);
+        if (open >= 1) cudaStreamEndCapture(cap[0], &junk);
+        if (junk) cudaGraphDestroy(junk);
+        cudaGetLastError();
+    }
+    h->stream = user;
+    h->pdl = false;
+    memcpy(h->counters, saved, sizeof(saved));
+    cudaError_t e = cudaSuccess;
+    if (rc == KCRN_OK) {
+        e = cudaGraphInstantiate(exec_out, graph, 0);
+        if (e != cudaSuccess) { set_error("cudaGraphInstantiate (run loop): %s", cudaGetErrorString(e)); rc = KCRN_E_CUDA; }
+    }
+    if (graph) cudaGraphDestroy(graph);
+    for (auto &c : cap) cudaStreamDestroy(c);
+    return rc;
+}
+
 // one device-to-host copy of the record assembled by record_kernel; synchronous
 int read_step_record(kcrn_problem *h, double *rec12_host) {
     cudaStream_t s = h->stream;
@@ -274,6 +392,8 @@ int kcrn_destroy(kcrn_handle h) {
     cudaFree(h->info);
     cudaFree(h->red_ticket);
     cudaFreeHost(h->rec_host);
+    cudaFreeHost(h->run_host);
+    cudaFree(h->run_ctl); cudaFree(h->run_recs); cudaFree(h->run_xs); cudaFree(h->run_x_opt);
     delete h;
     return KCRN_OK;
 }
@@ -500,6 +620,99 @@ int kcrn_krylov_trial(kcrn_handle h, int first, int m, int reorth, double M, dou
     if (x_out_dev)
         KCRN_CUDA(cudaMemcpyAsync(x_out_dev, h->x_cur, sizeof(double) * h->d, cudaMemcpyDeviceToDevice, s));
     return read_step_record(h, rec12_host);
+}
+
+int kcrn_krylov_run(kcrn_handle h, int max_iters, int m, int reorth, double value0, double reg_coef, double beta,
+                    double r0, double eps, int solver_it_max, double tol, int max_tries, int keep_xs, double f_opt,
+                    int *iters_done_host, int *status_host, double *recs16_host) {
+    KCRN_TRY(need_x(h, "kcrn_krylov_run"));
+    if (m < 1 || m > kMaxM) { set_error("kcrn_krylov_run: m = %d outside [1, %d]", m, kMaxM); return KCRN_E_ARG; }
+    if (max_iters < 1 || max_iters > 65536) { set_error("kcrn_krylov_run: max_iters = %d outside [1, 65536]", max_iters); return KCRN_E_ARG; }
+    if (!iters_done_host || !recs16_host) { set_error("kcrn_krylov_run: null output"); return KCRN_E_ARG; }
+    if (h->world > 1 && !h->p2p_ready) {
+        set_error("kcrn_krylov_run: sharded runs need the peer exchange (kcrn_p2p_attach); use kcrn_krylov_trial");
+        return KCRN_E_STATE;
+    }
+    reorth = reorth ? 1 : 0;
+    KCRN_TRY(lanczos_alloc(h, m));
+    cudaStream_t s = h->stream;
+    const int want_xs = keep_xs ? max_iters : 0;
+    if (!h->run_ctl || max_iters > h->run_cap || want_xs > h->run_xs_cap || (h->run_xs != nullptr) != (keep_xs != 0)) {
+        // buffers baked into the graph change: drop the captured run loops
+        KCRN_CUDA(cudaStreamSynchronize(s));
+        for (size_t i = 0; i < h->graphs.size();)
+            if (h->graphs[i].kind == 3) { cudaGraphExecDestroy(h->graphs[i].exec); h->graphs.erase(h->graphs.begin() + i); }
+            else ++i;
+        if (!h->run_ctl) {
+            KCRN_CUDA(cudaMalloc(&h->run_ctl, sizeof(RunCtl)));
+            KCRN_CUDA(cudaMalloc(&h->run_x_opt, sizeof(double) * h->d));
+        }
+        if (max_iters > h->run_cap) {
+            cudaFree(h->run_recs);
+            cudaFreeHost(h->run_host);
+            h->run_recs = nullptr; h->run_host = nullptr; h->run_cap = 0;
+            KCRN_CUDA(cudaMalloc(&h->run_recs, sizeof(double) * 16 * (size_t)max_iters));
+            KCRN_CUDA(cudaMallocHost(&h->run_host, sizeof(double) * 16 * (size_t)(max_iters + 1)));
+            h->run_cap = max_iters;
+        }
+        if (!keep_xs || want_xs > h->run_xs_cap) { cudaFree(h->run_xs); h->run_xs = nullptr; h->run_xs_cap = 0; }
+        if (keep_xs && !h->run_xs) {
+            KCRN_CUDA(cudaMalloc(&h->run_xs, sizeof(double) * (size_t)want_xs * (size_t)h->d));
+            h->run_xs_cap = want_xs;
+        }
+    }
+    cudaGraphExec_t exec = nullptr;
+    for (auto &ge : h->graphs)
+        if (ge.kind == 3 && ge.m == m && ge.reorth == reorth) exec = ge.exec;
+    if (!exec) {
+        KCRN_TRY(build_run_graph(h, m, reorth, &exec));
+        kcrn_problem::GraphEntry ge;
+        ge.kind = 3; ge.m = m; ge.reorth = reorth; ge.exec = exec;
+        memset(ge.delta, 0, sizeof(ge.delta));
+        h->graphs.push_back(ge);
+    }
+    // parameters: the leading doubles of RunCtl, then {., ., eps, it_max} of the sub-problem solver
+    double *pp = h->run_host;
+    pp[0] = value0; pp[1] = reg_coef; pp[2] = r0; pp[3] = beta; pp[4] = tol; pp[5] = f_opt;
+    pp[6] = (double)max_iters; pp[7] = (double)max_tries; pp[8] = 0.0; pp[9] = 0.0;
+    pp[10] = 0.0; pp[11] = 0.0; pp[12] = eps; pp[13] = (double)solver_it_max;
+    KCRN_CUDA(cudaMemcpyAsync(h->run_ctl, pp, sizeof(double) * 10, cudaMemcpyHostToDevice, s));
+    KCRN_CUDA(cudaMemcpyAsync(h->step_params, pp + 10, sizeof(double) * 4, cudaMemcpyHostToDevice, s));
+    h->cur_m = m;
+    h->cur_reorth = reorth;
+    KCRN_CUDA(cudaGraphLaunch(exec, s));
+    h->counters[1] += 1;
+    // iteration count and status first (they size the record copy)
+    KCRN_CUDA(cudaMemcpyAsync(pp, h->run_ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, s));
+    KCRN_CUDA(cudaStreamSynchronize(s));
+    RunCtl done;
+    memcpy(&done, pp, sizeof(RunCtl));
+    const int iters = done.iter;
+    if (iters > 0) {
+        KCRN_CUDA(cudaMemcpyAsync(h->run_host, h->run_recs, sizeof(double) * 16 * (size_t)iters, cudaMemcpyDeviceToHost, s));
+        KCRN_CUDA(cudaStreamSynchronize(s));
+        memcpy(recs16_host, h->run_host, sizeof(double) * 16 * (size_t)iters);
+    }
+    *iters_done_host = iters;
+    if (status_host) *status_host = done.status;
+    h->counters[6] += (int64_t)sizeof(double) * 14;
+    h->counters[7] += (int64_t)sizeof(RunCtl) + (int64_t)sizeof(double) * 16 * iters;
+    int64_t trials = 0;
+    for (int k = 0; k < iters; ++k) trials += 1 + (int64_t)recs16_host[16 * k + 13];
+    if (done.status != 0) trials += 1 + done.tries;      // the iteration that failed
+    const int64_t outers = iters + (done.status != 0 ? 1 : 0);
+    for (int i = 0; i < 8; ++i)
+        h->counters[i] += h->run_delta[0][i] + outers * h->run_delta[1][i] + trials * h->run_delta[2][i];
+    h->have_base = true;
+    return KCRN_OK;
+}
+
+int kcrn_run_view(kcrn_handle h, const double **xs_dev, const double **x_opt_dev, const double **x_dev) {
+    if (!h) { set_error("kcrn_run_view: null handle"); return KCRN_E_ARG; }
+    if (xs_dev) *xs_dev = h->run_xs;
+    if (x_opt_dev) *x_opt_dev = h->run_x_opt;
+    if (x_dev) *x_dev = h->x_cur;
+    return KCRN_OK;
 }
 
 int kcrn_lanczos_view(kcrn_handle h, const double **V_dev, const double **alphas_dev, const double **bet_dev,

@@ -83,6 +83,17 @@ struct SegMat {
     std::vector<int32_t> cptr_host;   // canonical column pointer (natural order), for kcrn_csc_view
 };
 
+// Device-resident state of the outer loop (kcrn_krylov_run): what Cubic_Krylov_LS carries from one iteration to
+// the next (cubic.py:248-262) and the loop counters.  The first 10 doubles are filled by the host before a run.
+struct RunCtl {
+    double value, reg_coef, r0, beta, tol, f_opt;   // running value f(x), M estimate, r0, backtracking factor, tolerance, best value
+    double max_iters_d, max_tries_d, pad0, pad1;
+    double M;                                        // M of the trial in flight
+    unsigned long long t0;                           // %globaltimer at the start of the run
+    long long solver_it;
+    int iter, max_iters, tries, max_tries, status, copy_best, improved, pad2;
+};
+
 // Device-resident control block of the Lanczos recurrence (written by single threads on the device,
 // read by every kernel of the captured graph; no host involvement).
 struct LanczosCtl {
@@ -134,6 +145,14 @@ struct kcrn_problem {
     double *x_base = nullptr;                      // [d] iterate the trial points of the running step start from
     double *step_params = nullptr;                 // [4] {M, r0, eps, it_max} of the next sub-problem solve (device)
     bool have_base = false;
+    // device-resident outer loop (kcrn_krylov_run)
+    kcrn::RunCtl *run_ctl = nullptr;
+    double *run_recs = nullptr;     // [run_cap][16] one record per outer iteration
+    double *run_xs = nullptr;       // [run_cap][d] accepted iterates, when asked for
+    double *run_x_opt = nullptr;    // [d] best point seen (loss.py:70-72)
+    double *run_host = nullptr;     // pinned: parameters in, records out
+    int run_cap = 0, run_xs_cap = 0;
+    int64_t run_delta[3][8] = {};   // counters of: once per run, once per outer iteration, once per trial
     double *Ax = nullptr, *D = nullptr, *resid = nullptr, *ell = nullptr;  // [n]
     // sweep temporaries
     double *t = nullptr;        // [n]   D .* (A v)
@@ -200,6 +219,10 @@ int launch_lanczos_init(kcrn_problem *h, int m);      // ctl, alphas, bet reset;
 int launch_lanczos_post(kcrn_problem *h, const double *hv_or_raw, int raw);  // epilogue after allreduce / generic feed
 int launch_lanczos_update(kcrn_problem *h, int reorth, int fused);
 int launch_lanczos_post_sharded(kcrn_problem *h, const double *y_allreduced, int reorth);
+int launch_run_init(kcrn_problem *h);
+int launch_run_begin(kcrn_problem *h, unsigned long long trial_loop);
+int launch_run_decide(kcrn_problem *h, unsigned long long trial_loop);
+int launch_run_commit(kcrn_problem *h, unsigned long long outer_loop);
 int launch_lanczos_post_peer(kcrn_problem *h, const double *y_partial, int reorth);
 int launch_normalise_current(kcrn_problem *h);        // V[col] = src / bet[col] outside the fused sweep
 int launch_sum(kcrn_problem *h, const double *a, int64_t len, double scale, double *out);  // deterministic sum

@@ -38,6 +38,9 @@ SIGNATURES = {
     "kcrn_cached_Ax": (c_int, [c_void_p, POINTER(c_void_p)]),
     "kcrn_set_Ax": (c_int, [c_void_p, c_void_p]),
     "kcrn_lanczos": (c_int, [c_void_p, c_void_p, c_int, c_int]),
+    "kcrn_krylov_run": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_double, c_double, c_double, c_double, c_int,
+                                c_double, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p]),
+    "kcrn_run_view": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "kcrn_lanczos_view": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                   POINTER(c_void_p)]),
     "kcrn_lanczos_begin": (c_int, [c_void_p, c_void_p, c_int, c_int]),

@@ -258,6 +258,29 @@ class Engine:
         r = self._rec
         return r[0], r[1], r[2], int(r[3]), int(r[4]), int(r[5]), r[6], int(r[7]), r[8]
 
+    def krylov_run(self, max_iters: int, m: int, reorth: bool, value0: float, reg_coef: float, beta: float = 0.5,
+                   r0: float = 0.1, eps: float = 1e-8, solver_it_max: int = 100, tol: float = 0.0, max_tries: int = 20,
+                   keep_xs: bool = False, f_opt: float = float("inf")):
+        """Up to ``max_iters`` outer iterations of Krylov CRN with the line search on the device: one graph launch
+        (kcrn_krylov_run).  Returns (records [iters, 16], status)."""
+        self._use_stream()
+        recs = np.empty((int(max_iters), 16), dtype=np.float64)
+        iters, status = ctypes.c_int(0), ctypes.c_int(0)
+        check(self.lib.kcrn_krylov_run(self.h, int(max_iters), int(m), int(bool(reorth)), float(value0), float(reg_coef),
+                                       float(beta), float(r0), float(eps), int(solver_it_max), float(tol), int(max_tries),
+                                       int(bool(keep_xs)), float(f_opt), byref(iters), byref(status),
+                                       recs.ctypes.data_as(c_void_p)))
+        self._m = int(m)
+        self._views = None
+        return recs[:iters.value], status.value
+
+    def run_view(self, iters: int):
+        """(accepted iterates [iters, d] or None, best point [d], current iterate [d]) -- device views."""
+        pxs, pb, px = c_void_p(), c_void_p(), c_void_p()
+        check(self.lib.kcrn_run_view(self.h, byref(pxs), byref(pb), byref(px)))
+        xs = self.view(pxs.value, (int(iters), self.d)) if pxs.value and iters > 0 else None
+        return xs, self.view(pb.value, (self.d,)), self.view(px.value, (self.d,))
+
     def step_record(self, with_value: bool = True):
         """(value, model_decrease, r, newton_its, status, m_eff, |g|, hvps, |x_trial - x|) -- one D2H, synchronous."""
         self._use_stream()

@@ -14,6 +14,8 @@ backtracking loop on the regulariser M (cubic.py:294-303) stays on the host, as 
 """
 from __future__ import annotations
 
+import time
+
 import numpy as np
 
 from kcrn_b200 import engine as _engine
@@ -116,10 +118,16 @@ class Cubic_Krylov_LS(Optimizer):
         solver_eps (float): accuracy of the Newton solve of the cubic sub-problem
         beta (float): backtracking factor for M
         reorth (bool): full re-orthogonalisation inside Lanczos (extension; default False = reference)
+        device_loop (bool): run() keeps the whole step loop on the device (kcrn_krylov_run: line search, commit and
+            stopping rule in CUDA-graph WHILE nodes) in chunks of ``device_chunk`` iterations; same arithmetic, same
+            trace, no per-iteration host round trip.  trace.ts then comes from the device clock.
     """
 
-    def __init__(self, reg_coef=None, subspace_dim=100, solver_eps=1e-8, beta=0.5, reorth=False, *args, **kwargs):
+    def __init__(self, reg_coef=None, subspace_dim=100, solver_eps=1e-8, beta=0.5, reorth=False, device_loop=False,
+                 device_chunk=64, *args, **kwargs):
         super().__init__(*args, **kwargs)
+        self.device_loop = device_loop
+        self.device_chunk = device_chunk
         self.solver_it = 0
         self.subspace_dim = subspace_dim
         self.solver_eps = solver_eps
@@ -166,6 +174,60 @@ class Cubic_Krylov_LS(Optimizer):
         self._dx = dx
         self.history.append(dict(f=value_new, M=M, solver_it=self.solver_it, m_eff=m_eff, backtracks=tries, r=r,
                                  hvps=hvps, gnorm=gnorm, dx=dx))
+
+    def run(self, x0, t_max=np.inf, it_max=np.inf, ls_it_max=None):
+        if not self.device_loop:
+            return super().run(x0, t_max=t_max, it_max=it_max, ls_it_max=ls_it_max)
+        if t_max is np.inf and it_max is np.inf:
+            it_max = 100
+            print(f'{self.label}: The number of iterations is set to {it_max}.')
+        self.t_max, self.it_max, self.ls_it_max = t_max, it_max, it_max
+        if not self.initialized:
+            self.init_run(x0)
+            self.initialized = True
+        loss, eng = self.loss, self.loss.engine
+        if self.value is None:
+            self.value = loss.value(self.x)
+        else:
+            loss._forward(self.x)
+        while not self.check_convergence():
+            left = self.it_max - self.it if self.it_max is not np.inf else self.device_chunk
+            chunk = int(max(1, min(left, self.device_chunk, (2 << 30) // (8 * self.dim))))
+            if self.t_max is not np.inf:
+                chunk = min(chunk, 8)                  # the time budget is checked between chunks
+            recs, status = eng.krylov_run(chunk, self.subspace_dim, self.reorth, self.value, self.reg_coef, self.beta,
+                                          self.r0, self.solver_eps, 100, self.tolerance, 20, keep_xs=True,
+                                          f_opt=loss.f_opt)
+            xs, x_best, x_now = eng.run_view(len(recs))
+            t_chunk = self.t
+            for k, rec in enumerate(recs):
+                tries = int(rec[13])
+                loss.calls["gradient"] += 1
+                loss.calls["hess_vec_prod"] += self.subspace_dim
+                loss.calls["value"] += 1 + tries
+                loss.calls["forward"] += 1 + tries
+                self.reg_coef, self.value, self.r0, self._dx = rec[12], rec[0], rec[2], rec[8]
+                self.solver_it += int(rec[3])
+                self.history.append(dict(f=rec[0], M=rec[12], solver_it=self.solver_it, m_eff=int(rec[5]), backtracks=tries,
+                                         r=rec[2], hvps=int(rec[7]), gnorm=rec[6], dx=rec[8]))
+                self.x = xs[k]
+                self.it += 1
+                self.t = t_chunk + rec[14]
+                if self.should_update_trace():
+                    self.update_trace()                # clones self.x
+                self.max_progress = max(self.time_progress, self.iterations_progress)
+            if len(recs):
+                if recs[-1][15] != 0.0:
+                    loss.x_opt, loss.f_opt = x_best.clone(), float(recs[-1][11])
+                self.x = x_now.clone()
+                loss.adopt_iterate(self.x)
+                if self.tolerance > 0:
+                    self.x_old_tol = self.x            # step_length() reads the device's |x_new - x|
+            if status == KCRN_E_NOTPD:
+                raise np.linalg.LinAlgError("T + r I is not positive definite in the cubic sub-problem")
+            self.t = max(self.t, time.perf_counter() - self.t_start)
+        self.initialized = False
+        return self.trace
 
     def step_length(self):
         return self._dx if self._dx is not None else super().step_length()

@@ -345,6 +345,38 @@ def test_free_running_trajectory_vs_reference(torch, golden, name, m, iters, reo
     assert f[-1] <= ref[0]
 
 
+@pytest.mark.parametrize("name,m,reorth,tol,iters", [("small", 10, False, 0.0, 30), ("rcv1", 10, False, 0.0, 40),
+                                                      ("rcv1", 50, True, 0.0, 12), ("w8a", 10, False, 1e-5, 200)])
+def test_device_resident_loop_equals_host_loop(torch, name, m, reorth, tol, iters):
+    """kcrn_krylov_run (line search, commit and stopping rule in CUDA-graph WHILE nodes) against the host-driven
+    loop over kcrn_krylov_trial: the same kernels in the same order, so every number is bit-identical -- values,
+    accepted M, backtracks, Newton iterations, iterates kept in the trace, the best point and where the run stops."""
+    P = make_problem(name, seed=0)
+    host = _make_opt(P, m, reorth)
+    host.tolerance = tol
+    host.run(P.x0, it_max=iters)
+    dev = _make_opt(P, m, reorth)
+    dev.tolerance = tol
+    dev.device_loop, dev.device_chunk = True, 7           # several chunks, the last one ragged
+    dev.run(P.x0, it_max=iters)
+    assert len(dev.history) == len(host.history) and dev.it == host.it
+    if tol > 0:
+        assert dev.it < iters                             # stopped by |x_new - x| < tol, on the device
+    for a, b in zip(dev.history, host.history):
+        assert a == b, (a, b)
+    assert sum(h["backtracks"] for h in host.history) > 0 or name != "small"
+    assert dev.reg_coef == host.reg_coef and dev.value == host.value and dev.r0 == host.r0
+    assert dev.solver_it == host.solver_it
+    assert torch.equal(dev.x, host.x)
+    assert dev.trace.its == host.trace.its and dev.trace.solver_its == host.trace.solver_its
+    assert all(torch.equal(a, b) for a, b in zip(dev.trace.xs, host.trace.xs))
+    assert np.all(np.diff(dev.trace.ts) > 0)
+    assert dev.loss.f_opt == host.loss.f_opt and torch.equal(dev.loss.x_opt, host.loss.x_opt)
+    assert dev.loss.calls == host.loss.calls
+    # the caches belong to the last iterate: the next gradient needs no forward sweep and equals the host loop's
+    assert torch.equal(dev.loss.gradient(dev.x), host.loss.gradient(host.x))
+
+
 def test_drop_in_driver_flow_with_numpy_iterates(torch):
     """What cubic_newton.py does (:58-68, :94-111, :140): numpy x0, run, compute_loss_of_iterates, f_opt."""
     P = make_problem("small", seed=0)
