@@ -116,6 +116,11 @@ int kcrn_lanczos(kcrn_handle h, const double *g_dev, int m, int reorth);
 int kcrn_krylov_run(kcrn_handle h, int max_iters, int m, int reorth, double value0, double reg_coef, double beta,
                     double r0, double eps, int solver_it_max, double tol, int max_tries, int keep_xs, double f_opt,
                     int *iters_done_host, int *status_host, double *recs16_host);
+/* f(x_j) for k stored iterates X[k][d] (device, row-major) -> out[k]: Trace.compute_loss_of_iterates
+ * (optimizer/opt_trace.py:39-43) with the matrix read once per 8 iterates instead of once per iterate.  Leaves the
+ * caches of the current x alone.  Row-sharded: every rank passes the same X, every rank gets the full values. */
+int kcrn_values_batch(kcrn_handle h, const double *X_dev, int k, double *out_dev);
+
 /* Device views after kcrn_krylov_run: accepted iterates [iters][d] (null without keep_xs), the best point [d]
  * (valid when the record's flag is set), the current iterate [d]. */
 int kcrn_run_view(kcrn_handle h, const double **xs_dev, const double **x_opt_dev, const double **x_dev);
@@ -170,6 +175,16 @@ int kcrn_hessian_dense(kcrn_handle h, double *out_dev);
 int kcrn_partial_gradient(kcrn_handle h, const int64_t *I_dev, int m, double *out_dev);
 int kcrn_partial_hessian(kcrn_handle h, const int64_t *I_dev, int m, double *out_dev);
 int kcrn_update_Ax(kcrn_handle h, const int64_t *I_dev, const double *delta_dev, int m);
+
+/* ---- LIBSVM / svmlight text -> CSR (host only; replaces sklearn.datasets.load_svmlight_file at
+ * cubic_newton.py:52).  count: rows, stored entries and the smallest / largest feature index as written; parse:
+ * fills labels[n_rows], indptr[n_rows + 1], indices[nnz], data[nnz] (indices as written: the zero- / one-based
+ * decision and the per-row sort stay with the caller, as in sklearn).  threads < 1: all host threads.  The text
+ * must be NUL-terminated at text[len]. */
+int kcrn_svmlight_count(const char *text, int64_t len, int threads, int64_t *n_rows, int64_t *nnz,
+                        int32_t *min_index, int32_t *max_index);
+int kcrn_svmlight_parse(const char *text, int64_t len, int threads, int64_t n_rows, int64_t nnz, double *labels,
+                        int64_t *indptr, int32_t *indices, double *data);
 
 /* ---- introspection for the benchmark --------------------------------------------------------
  * counters[0..8): kernels launched, graph launches, HVPs, forward sweeps, transpose sweeps,

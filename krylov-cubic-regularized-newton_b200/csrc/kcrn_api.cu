@@ -393,6 +393,7 @@ int kcrn_destroy(kcrn_handle h) {
     cudaFree(h->red_ticket);
     cudaFreeHost(h->rec_host);
     cudaFreeHost(h->run_host);
+    cudaFree(h->batch_xt); cudaFree(h->batch_scal); cudaFree(h->batch_partial); cudaFree(h->batch_ticket);
     cudaFree(h->run_ctl); cudaFree(h->run_recs); cudaFree(h->run_xs); cudaFree(h->run_x_opt);
     delete h;
     return KCRN_OK;
@@ -705,6 +706,12 @@ int kcrn_krylov_run(kcrn_handle h, int max_iters, int m, int reorth, double valu
         h->counters[i] += h->run_delta[0][i] + outers * h->run_delta[1][i] + trials * h->run_delta[2][i];
     h->have_base = true;
     return KCRN_OK;
+}
+
+int kcrn_values_batch(kcrn_handle h, const double *X_dev, int k, double *out_dev) {
+    if (!h || !X_dev || !out_dev) { set_error("kcrn_values_batch: null argument"); return KCRN_E_ARG; }
+    if (k < 0) { set_error("kcrn_values_batch: k = %d", k); return KCRN_E_ARG; }
+    return values_batch(h, X_dev, k, out_dev);
 }
 
 int kcrn_run_view(kcrn_handle h, const double **xs_dev, const double **x_opt_dev, const double **x_dev) {

@@ -153,6 +153,10 @@ struct kcrn_problem {
     double *run_host = nullptr;     // pinned: parameters in, records out
     int run_cap = 0, run_xs_cap = 0;
     int64_t run_delta[3][8] = {};   // counters of: once per run, once per outer iteration, once per trial
+    // batched values of stored iterates (kcrn_values_batch)
+    double *batch_xt = nullptr, *batch_scal = nullptr, *batch_partial = nullptr;
+    unsigned *batch_ticket = nullptr;
+    int batch_grid = 0;
     double *Ax = nullptr, *D = nullptr, *resid = nullptr, *ell = nullptr;  // [n]
     // sweep temporaries
     double *t = nullptr;        // [n]   D .* (A v)
@@ -219,6 +223,7 @@ int launch_lanczos_init(kcrn_problem *h, int m);      // ctl, alphas, bet reset;
 int launch_lanczos_post(kcrn_problem *h, const double *hv_or_raw, int raw);  // epilogue after allreduce / generic feed
 int launch_lanczos_update(kcrn_problem *h, int reorth, int fused);
 int launch_lanczos_post_sharded(kcrn_problem *h, const double *y_allreduced, int reorth);
+int values_batch(kcrn_problem *h, const double *X, int k, double *out);
 int launch_run_init(kcrn_problem *h);
 int launch_run_begin(kcrn_problem *h, unsigned long long trial_loop);
 int launch_run_decide(kcrn_problem *h, unsigned long long trial_loop);

@@ -41,6 +41,9 @@ SIGNATURES = {
     "kcrn_krylov_run": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_double, c_double, c_double, c_double, c_int,
                                 c_double, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p]),
     "kcrn_run_view": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kcrn_values_batch": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "kcrn_svmlight_count": (c_int, [c_char_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kcrn_svmlight_parse": (c_int, [c_char_p, c_int64, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "kcrn_lanczos_view": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                   POINTER(c_void_p)]),
     "kcrn_lanczos_begin": (c_int, [c_void_p, c_void_p, c_int, c_int]),

@@ -281,6 +281,17 @@ class Engine:
         xs = self.view(pxs.value, (int(iters), self.d)) if pxs.value and iters > 0 else None
         return xs, self.view(pb.value, (self.d,)), self.view(px.value, (self.d,))
 
+    def values_batch(self, X):
+        """f(x_j) for the rows of X [k, d] (device tensor) -- one sweep of A per 8 iterates (kcrn_values_batch)."""
+        self._use_stream()
+        torch = self.torch
+        X = X.contiguous()
+        if X.dim() != 2 or X.shape[1] != self.d or X.dtype != torch.float64 or not X.is_cuda:
+            raise ValueError(f"values_batch expects a float64 CUDA tensor [k, {self.d}]")
+        out = torch.empty(X.shape[0], dtype=torch.float64, device=X.device)
+        check(self.lib.kcrn_values_batch(self.h, X.data_ptr(), int(X.shape[0]), out.data_ptr()))
+        return out
+
     def step_record(self, with_value: bool = True):
         """(value, model_decrease, r, newton_its, status, m_eff, |g|, hvps, |x_trial - x|) -- one D2H, synchronous."""
         self._use_stream()

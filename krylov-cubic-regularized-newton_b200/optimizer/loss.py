@@ -138,6 +138,18 @@ class LogisticRegression(Oracle):
         self._forward(x)
         return self._out(self.engine.cached_Ax(), x)
 
+    def values_of_iterates(self, xs):
+        """[f(x) for x in xs] with the book-keeping of value() (calls, f_opt / x_opt; loss.py:66-73), evaluated in
+        batches on the device.  The cached A x of the current iterate is left alone."""
+        if len(xs) == 0:
+            return np.asarray([])
+        X = self.torch.stack([self.to_device(x) for x in xs])
+        vals = self.engine.values_batch(X).cpu().numpy()
+        for v, x in zip(vals, xs):
+            self.calls["value"] += 1
+            self._note_value(float(v), x)
+        return vals
+
     def _value(self, x):
         self.calls["value"] += 1
         self._forward(x)

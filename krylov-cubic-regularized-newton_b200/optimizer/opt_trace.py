@@ -26,7 +26,9 @@ class Trace:
         if len(self.loss_vals) > 0:
             warnings.warn('Loss values have already been computed. Set .loss_vals = [] to recompute.')
             return
-        self.loss_vals = np.asarray([self.loss.value(x) for x in self.xs])
+        batched = getattr(self.loss, "values_of_iterates", None)
+        # the engine reads the matrix once per 8 stored iterates instead of once per iterate (kcrn_values_batch)
+        self.loss_vals = batched(self.xs) if batched is not None else np.asarray([self.loss.value(x) for x in self.xs])
 
     def convert_its_to_epochs(self, batch_size=1):
         if self.its_converted_to_epochs:

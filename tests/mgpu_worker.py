@@ -90,12 +90,29 @@ def main():
         pass
     opt = Cubic_Krylov_LS(loss=loss, reg_coef=1e-3, subspace_dim=10, tolerance=1e-9, label="mg", tqdm=False)
     opt.run(P.x0, it_max=8)
+    # the step loop kept on the device (nested WHILE graph nodes, peer exchange inside) = the host-driven loop, bit
+    # for bit, on every rank; batched values of stored iterates = the whole-matrix oracle
+    try:
+        eng.p2p_enable(True)
+        dev = Cubic_Krylov_LS(loss=loss, reg_coef=1e-3, subspace_dim=10, tolerance=1e-9, label="mgd", tqdm=False,
+                              device_loop=True, device_chunk=3)
+        dev.run(P.x0, it_max=8)
+        same = len(dev.history) == len(opt.history) and all(a == b for a, b in zip(dev.history, opt.history))
+        same = same and torch.equal(dev.x, opt.x)
+        errs["device_loop_equals_host_loop"] = 0.0 if same else 1.0
+    except Exception as e:
+        print(f"rank {rank}: device loop unavailable ({e})", flush=True)
+    Xs = torch.stack([loss.to_device(x) for x in opt.trace.xs[:5]])
+    vb = eng.values_batch(Xs).cpu().numpy()
+    vo = np.array([L.value(x.cpu().numpy()) for x in opt.trace.xs[:5]])
+    errs["values_batch"] = float(np.max(np.abs(vb - vo) / np.abs(vo)))
     g = np.load(os.path.join(HERE, "golden", f"traj_{name}.npz"))
     f = np.array([hh["f"] for hh in opt.history])
     errs["trajectory_prefix"] = float(np.max(np.abs(f - g["m10_ref_f"][:len(f)]) / np.abs(g["m10_ref_f"][:len(f)])))
     ok = (errs["value"] <= 1e-12 and errs["gradient"] <= 1e-12 and errs["hvp"] <= 1e-12
           and errs["replica_bits_equal"] == 0.0 and errs["trajectory_prefix"] <= 1e-8
-          and "peer_fail" not in errs and "peer_replica_bits_equal" not in errs)
+          and "peer_fail" not in errs and "peer_replica_bits_equal" not in errs
+          and errs.get("device_loop_equals_host_loop", 0.0) == 0.0 and errs["values_batch"] <= 1e-12)
     cnt = loss.engine.counters()
     print(f"rank {rank}/{world}: rows {S.n} nnz {S.nnz} errs {errs} allreduces {cnt['allreduces']} -> {'OK' if ok else 'FAIL'}",
           flush=True)

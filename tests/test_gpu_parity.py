@@ -377,6 +377,29 @@ def test_device_resident_loop_equals_host_loop(torch, name, m, reorth, tol, iter
     assert torch.equal(dev.loss.gradient(dev.x), host.loss.gradient(host.x))
 
 
+@pytest.mark.parametrize("name,l2,k", [("tiny", 1e-3, 3), ("w8a", 0.0, 8), ("rcv1", 1e-4, 11), ("news20", 0.0, 2)])
+def test_batched_values_of_iterates_vs_oracle(torch, name, l2, k):
+    """kcrn_values_batch (Trace.compute_loss_of_iterates, opt_trace.py:39-43): f(x_j) for k stored iterates with one
+    sweep of A per 8 of them, against the oracle's value() one iterate at a time; run-to-run identical; the cached
+    A x of the current iterate untouched."""
+    P = make_problem(name, seed=3 if name == "tiny" else 0)
+    eng = _engine(P, l2=l2)
+    L = _oracle(P, l2=l2)
+    rng = np.random.default_rng(9)
+    X = P.x0[None, :] * rng.uniform(0.0, 1.0, (k, 1)) + 0.05 * rng.standard_normal((k, P.d))
+    x_cur = _dev(torch, P.x0)
+    eng.set_x(x_cur)
+    Ax_before = eng.cached_Ax().clone()
+    Xd = _dev(torch, X)
+    got = eng.values_batch(Xd)
+    want = np.array([L.value(x) for x in X])
+    assert np.max(np.abs(got.cpu().numpy() - want) / np.abs(want)) <= TOL
+    assert torch.equal(got, eng.values_batch(Xd))
+    assert torch.equal(eng.cached_Ax(), Ax_before)
+    assert abs(float(eng.value()) - L.value(P.x0)) <= TOL * abs(L.value(P.x0))
+    assert eng.values_batch(Xd[:0]).numel() == 0
+
+
 def test_drop_in_driver_flow_with_numpy_iterates(torch):
     """What cubic_newton.py does (:58-68, :94-111, :140): numpy x0, run, compute_loss_of_iterates, f_opt."""
     P = make_problem("small", seed=0)
