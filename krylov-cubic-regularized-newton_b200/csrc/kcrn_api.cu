@@ -709,8 +709,9 @@ int kcrn_krylov_run(kcrn_handle h, int max_iters, int m, int reorth, double valu
 }
 
 int kcrn_values_batch(kcrn_handle h, const double *X_dev, int k, double *out_dev) {
-    if (!h || !X_dev || !out_dev) { set_error("kcrn_values_batch: null argument"); return KCRN_E_ARG; }
     if (k < 0) { set_error("kcrn_values_batch: k = %d", k); return KCRN_E_ARG; }
+    if (h && k == 0) return KCRN_OK;
+    if (!h || !X_dev || !out_dev) { set_error("kcrn_values_batch: null argument"); return KCRN_E_ARG; }
     return values_batch(h, X_dev, k, out_dev);
 }
 
