@@ -19,7 +19,7 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
-int launch_lanczos_finish(kcrn_problem *h);
+int launch_lanczos_finish(kcrn_problem *h, int m, int defer);
 int launch_sumsq(kcrn_problem *h, const double *a, int64_t len, double *out);
 int launch_value_combine(kcrn_problem *h, double *out);
 int launch_scale(kcrn_problem *h, const double *y, const double *u, double *out);
@@ -85,11 +85,15 @@ int enqueue_value(kcrn_problem *h, double *out) {
 
 // the whole m-step recurrence, enqueued on h->stream (captured into a graph by kcrn_lanczos)
 int enqueue_lanczos(kcrn_problem *h, int m, int reorth) {
+    // single GPU: the grid-wide sums (alpha after the row sweep, beta after the column sweep) are finished by the
+    // kernel that consumes them -- 2: both, the row sweep also advances the recurrence; 1: alpha only (the
+    // re-orthogonalisation kernel owns beta and the advance).  Row-sharded: 0, the exchange kernels own both.
+    const int defer = (h->world > 1 || !lanczos_defer_fits(h)) ? 0 : (reorth ? 1 : 2);
     KCRN_TRY(launch_lanczos_init(h, m));
     for (int slot = 0; slot < m; ++slot) {
         // rows sweep: t = D (A v), basis column, and alpha = v'Hv one sweep early (so that the column sweep can
         // form w' = Hv - beta v_prev - alpha v and beta = |w'| itself: two kernels per Lanczos step)
-        KCRN_TRY(launch_rows_lanczos(h, h->ypart + h->d));
+        KCRN_TRY(launch_rows_lanczos(h, h->ypart + h->d, slot, defer));
         if (h->world > 1) {
             KCRN_TRY(launch_cols_raw(h, h->t, h->ypart));
             if (h->p2p_ready) {
@@ -100,11 +104,11 @@ int enqueue_lanczos(kcrn_problem *h, int m, int reorth) {
                 KCRN_TRY(launch_lanczos_post_sharded(h, h->ypart, reorth));
             }
         } else if (slot + 1 < m) {
-            KCRN_TRY(launch_cols_lanczos(h, reorth ? 0 : 1));
+            KCRN_TRY(launch_cols_lanczos(h, reorth ? 0 : 1, slot, defer));
         }
         if (reorth && slot + 1 < m) KCRN_TRY(launch_lanczos_update(h, 1, 1));
     }
-    return launch_lanczos_finish(h);
+    return launch_lanczos_finish(h, m, defer);
 }
 
 // Capture `enqueue` once per key = (kind, m, reorth) into a CUDA graph and replay it on the handle's stream.
@@ -346,13 +350,15 @@ int kcrn_create(kcrn_handle *out, int64_t n_rows, int64_t n_cols, int64_t nnz, c
         KCRN_CUDA(cudaMalloc(&h->coef2, sizeof(double) * (kMaxM + 2)));
         KCRN_CUDA(cudaMalloc(&h->sub, sizeof(double) * (kMaxM + 8)));
         KCRN_CUDA(cudaMalloc(&h->scal, sizeof(double) * 32));
-        KCRN_CUDA(cudaMalloc(&h->ctl, sizeof(LanczosCtl)));
+        KCRN_CUDA(cudaMalloc(&h->ctl, 2 * sizeof(LanczosCtl)));
+        KCRN_CUDA(cudaMalloc(&h->lan_rows_part, sizeof(double) * (2 * (size_t)std::max(1, h->csr.grid) + 4)));
+        KCRN_CUDA(cudaMalloc(&h->lan_cols_part, sizeof(double) * ((size_t)std::max(1, h->csc.grid) + 2)));
         KCRN_CUDA(cudaMalloc(&h->info, sizeof(int32_t) * 8));
         KCRN_CUDA(cudaMalloc(&h->red_ticket, sizeof(unsigned) * 8));
         KCRN_CUDA(cudaMemsetAsync(h->red_ticket, 0, sizeof(unsigned) * 8, s));
         KCRN_CUDA(cudaMemsetAsync(h->scal, 0, sizeof(double) * 32, s));
         KCRN_CUDA(cudaMemsetAsync(h->sub, 0, sizeof(double) * (kMaxM + 8), s));
-        KCRN_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(LanczosCtl), s));
+        KCRN_CUDA(cudaMemsetAsync(h->ctl, 0, 2 * sizeof(LanczosCtl), s));
         KCRN_CUDA(cudaMemsetAsync(h->info, 0, sizeof(int32_t) * 8, s));
         KCRN_CUDA(cudaMallocHost(&h->rec_host, sizeof(double) * 16));
         h->vec_elems = n_cols > (int64_t)kNumSm * kVecThreads * 4 ? 4 : 1;
@@ -388,7 +394,7 @@ int kcrn_destroy(kcrn_handle h) {
                       h->alphas, h->bet, h->coef, h->coef2, h->sub, h->scal, h->red_partials, h->x_stage,
                       h->v_stage, h->o_stage};
     for (double *p : bufs) cudaFree(p);
-    cudaFree(h->ctl);
+    cudaFree(h->ctl); cudaFree(h->lan_rows_part); cudaFree(h->lan_cols_part);
     cudaFree(h->info);
     cudaFree(h->red_ticket);
     cudaFreeHost(h->rec_host);
@@ -743,7 +749,7 @@ int kcrn_lanczos_begin(kcrn_handle h, const double *g_dev, int m, int reorth) {
     h->cur_reorth = reorth ? 1 : 0;
     KCRN_TRY(launch_lanczos_init(h, m));
     KCRN_TRY(launch_normalise_current(h));
-    KCRN_TRY(launch_lanczos_finish(h));
+    KCRN_TRY(launch_lanczos_finish(h, h->cur_m, 0));
     h->step_col = 0;
     return KCRN_OK;
 }
@@ -759,7 +765,7 @@ int kcrn_lanczos_feed(kcrn_handle h, const double *hv_dev, int *finished_host) {
     KCRN_TRY(launch_lanczos_post(h, hv_dev, 0));
     KCRN_TRY(launch_lanczos_update(h, h->cur_reorth, 0));   // no-op on the device once the last alpha is in
     KCRN_TRY(launch_normalise_current(h));
-    KCRN_TRY(launch_lanczos_finish(h));
+    KCRN_TRY(launch_lanczos_finish(h, h->cur_m, 0));
     int32_t info[8];
     KCRN_CUDA(cudaMemcpyAsync(info, h->info, sizeof(info), cudaMemcpyDeviceToHost, h->stream));
     KCRN_CUDA(cudaStreamSynchronize(h->stream));

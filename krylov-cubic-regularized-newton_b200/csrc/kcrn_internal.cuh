@@ -107,9 +107,13 @@ struct LanczosCtl {
     int m;
     int broke;
     int hvps;       // operator applications consumed
-    int pad0, pad1;
     double last_beta;
+    // the two scalars every kernel of a step needs, kept in the same 64-byte line as the indices above so that one
+    // round trip to L2 fetches everything (bet[col] / alphas[col] would be a second, dependent one)
+    double cur_beta;    // = bet[col]: the norm that normalises column col (|g| for col 0)
+    double cur_alpha;   // = alphas[col] once the row sweep of the step has produced it
 };
+static_assert(sizeof(LanczosCtl) == 64, "control block = one 64-byte line");
 
 #ifdef __CUDACC__
 // Bookkeeping of cubic.py:98-109 once beta = |w'| of column `col` is known (executed by ONE thread).
@@ -123,7 +127,8 @@ __device__ inline void lanczos_advance(LanczosCtl *c, double *bet, double beta) 
         c->redo = 1;                       // cubic.py:109 re-applies the operator to the same v
         c->final_ = 1;
     } else {
-        bet[col + 1] = beta;
+        if (bet) bet[col + 1] = beta;
+        c->cur_beta = beta;
         c->col = col + 1;
         c->nvalid = col + 2;
         if (col + 1 == m - 1) { c->final_ = 1; c->store_idx = m - 1; }
@@ -166,7 +171,8 @@ struct kcrn_problem {
     double *V = nullptr;        // [m_cap * d]
     double *w = nullptr, *wp = nullptr, *g = nullptr;  // [d]
     double *alphas = nullptr, *bet = nullptr, *coef = nullptr, *coef2 = nullptr;  // [kMaxM + 1]
-    kcrn::LanczosCtl *ctl = nullptr;
+    kcrn::LanczosCtl *ctl = nullptr;               // [2]: deferred mode ping-pongs between them, everything else uses [0]
+    double *lan_rows_part = nullptr, *lan_cols_part = nullptr;   // per-CTA pieces of alpha (2 x csr.grid) / beta^2 (csc.grid)
     int32_t *info = nullptr;    // [8]
     int cur_m = 0, cur_reorth = 0;
     // sub-problem result {s[kMaxM], r, model_decrease, iterations, status}
@@ -210,11 +216,12 @@ int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s);
 void free_segmat(SegMat *A);
 int launch_forward(kcrn_problem *h, const double *x);                 // A x and everything derived
 int launch_rows_weighted(kcrn_problem *h, const double *v);           // t = D .* (A v)
-int launch_rows_lanczos(kcrn_problem *h, double *alpha_raw);          // same, source picked by ctl; sharded runs:
+int launch_rows_lanczos(kcrn_problem *h, double *alpha_raw, int slot, int defer);          // same, source picked by ctl; sharded runs:
                                                                       // raw alpha sum -> alpha_raw[0]
 int launch_cols_raw(kcrn_problem *h, const double *src, double *out); // out = A' src
 int launch_cols_scaled(kcrn_problem *h, const double *src, const double *u, double *out);  // A' src / n + l2 u
-int launch_cols_lanczos(kcrn_problem *h, int update_ctl);             // w' and beta fused
+int launch_cols_lanczos(kcrn_problem *h, int update_ctl, int slot, int defer);
+bool lanczos_defer_fits(const kcrn_problem *h);      // small grids only: see kcrn_sweep.cu             // w' and beta fused
 int launch_derive_from_Ax(kcrn_problem *h);
 
 // ----------------------------------------------------------------------------- kcrn_lanczos.cu

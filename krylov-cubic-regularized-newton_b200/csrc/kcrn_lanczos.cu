@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_init_kernel(VecParams P) 
         P.bet[0] = sqrt(tot);
         LanczosCtl c;
         c.col = 0; c.redo = 0; c.final_ = (P.m == 1); c.done = 0; c.m_eff = P.m; c.nvalid = 1;
-        c.store_idx = P.m - 1; c.m = P.m; c.broke = 0; c.hvps = 0; c.pad0 = c.pad1 = 0; c.last_beta = 0.0;
+        c.store_idx = P.m - 1; c.m = P.m; c.broke = 0; c.hvps = 0; c.last_beta = 0.0;
+        c.cur_beta = sqrt(tot); c.cur_alpha = 0.0;
         *P.ctl = c;
     }
 }
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(kVecThreads) normalise_kernel(VecParams P) {
     if (P.ctl->done || P.ctl->redo) return;
     const int col = P.ctl->col;
     const double *src = col == 0 ? P.g : P.wp;
-    const double beta = P.bet[col], rinv = 1.0 / beta;
+    const double beta = P.ctl->cur_beta, rinv = 1.0 / beta;
     double *vout = P.V + (size_t)col * P.d;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.d; i += (int64_t)gridDim.x * blockDim.x)
         vout[i] = quotient(src[i], beta, rinv);
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_post_kernel(VecParams P) 
     const double *v = P.V + (size_t)col * P.d;
     const bool subtract = col > 0 && !final_;
     const double *vpre = subtract ? P.V + (size_t)(col - 1) * P.d : nullptr;
-    const double beta_prev = subtract ? P.bet[col] : 0.0;
+    const double beta_prev = subtract ? P.ctl->cur_beta : 0.0;
     const int64_t base = (int64_t)blockIdx.x * (kVecThreads * E) + threadIdx.x;
     double loc = 0.0;
 #pragma unroll
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_post_kernel(VecParams P) 
     if (!grid_sum(loc, P.red_partials, P.red_ticket, sh, &s_last, &tot)) return;
     if (threadIdx.x == 0) {
         P.alphas[final_ ? store_idx : col] = tot;
+        P.ctl->cur_alpha = tot;
         P.ctl->hvps += 1;
         if (final_) P.ctl->done = 1;
     }
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_post_sharded_kernel(VecPa
     const double *v = P.V + (size_t)col * P.d;
     const bool subtract = col > 0;
     const double *vpre = subtract ? P.V + (size_t)(col - 1) * P.d : nullptr;
-    const double beta_prev = subtract ? P.bet[col] : 0.0;
+    const double beta_prev = subtract ? P.ctl->cur_beta : 0.0;
     double loc = 0.0;
     if (!final_) {
 #pragma unroll
@@ -268,6 +270,7 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_post_sharded_kernel(VecPa
     if (threadIdx.x == 0) {
         if constexpr (PEER) *P.peer.epoch = step;
         P.alphas[final_ ? store_idx : col] = alpha;
+        P.ctl->cur_alpha = alpha;
         P.ctl->hvps += 1;
         if (final_) P.ctl->done = 1;
         else if (P.stage == 0) lanczos_advance(P.ctl, P.bet, sqrt(tot));   // stage 1: re-orthogonalisation follows
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P
             x[e] = c < P.d ? P.wp[c] : 0.0;
         }
     } else if (P.stage <= 1) {
-        const double alpha = P.alphas[col];
+        const double alpha = P.ctl->cur_alpha;
         const double *v = P.V + (size_t)col * P.d;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
@@ -371,13 +374,48 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P
     }
 }
 
-__global__ void lanczos_finish_kernel(const LanczosCtl *ctl, int32_t *info, double *bet) {
+struct FinishParams {
+    const LanczosCtl *ctl_in;      // where the last kernel of the recurrence left the state
+    LanczosCtl *ctl_main;          // h->ctl[0]: where everybody else looks
+    int32_t *info;
+    double *bet, *alphas;
+    // deferred mode: the alpha of the last operator application is still in per-CTA pieces
+    int defer;
+    const double *part, *longdot;
+    int count, nlong;
+    double n_samples, inv_n, l2;
+};
+
+__global__ void __launch_bounds__(kVecThreads) lanczos_finish_kernel(FinishParams P) {
+    __shared__ double sh[2 * (kVecThreads / 32)];
     pdl_wait();
     pdl_trigger();
+    LanczosCtl st = *P.ctl_in;
+    if (P.defer && !st.done) {
+        // same order as the consumer-side sum of the sweep kernels (thread-strided, warp tree, warps in order)
+        double x = 0.0, y = 0.0;
+        for (int i = threadIdx.x; i < P.count; i += kVecThreads) {
+            x += __ldcg(P.part + i);
+            y += __ldcg(P.part + ((P.count + 1) & ~1) + i);
+        }
+        for (int i = threadIdx.x; i < P.nlong; i += kVecThreads) x += __ldcg(P.longdot + i);
+        x = warp_sum(x);
+        y = warp_sum(y);
+        if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = x; sh[kVecThreads / 32 + (threadIdx.x >> 5)] = y; }
+        __syncthreads();
+        double s1 = 0.0, s2 = 0.0;
+        for (int w = 0; w < kVecThreads / 32; ++w) { s1 += sh[w]; s2 += sh[kVecThreads / 32 + w]; }
+        const double alpha = __dadd_rn(quotient(s1, P.n_samples, P.inv_n), __dmul_rn(P.l2, s2));
+        if (threadIdx.x == 0) P.alphas[st.final_ ? st.store_idx : st.col] = alpha;
+        st.cur_alpha = alpha;
+        st.hvps += 1;
+        if (st.final_) st.done = 1;
+    }
     if (threadIdx.x == 0) {
-        bet[ctl->m] = ctl->last_beta;   // slot m is free: bet[j + 1] = beta_j only for j <= m - 2
-        info[0] = ctl->m_eff; info[1] = ctl->nvalid; info[2] = ctl->broke; info[3] = ctl->hvps;
-        info[4] = ctl->col; info[5] = ctl->done; info[6] = ctl->redo; info[7] = ctl->final_;
+        P.bet[st.m] = st.last_beta;   // slot m is free: bet[j + 1] = beta_j only for j <= m - 2
+        P.info[0] = st.m_eff; P.info[1] = st.nvalid; P.info[2] = st.broke; P.info[3] = st.hvps;
+        P.info[4] = st.col; P.info[5] = st.done; P.info[6] = st.redo; P.info[7] = st.final_;
+        *P.ctl_main = st;
     }
 }
 
@@ -628,8 +666,15 @@ int launch_lanczos_update(kcrn_problem *h, int reorth, int fused) {
     return KCRN_OK;
 }
 
-int launch_lanczos_finish(kcrn_problem *h) {
-    KCRN_CUDA(launch_kernel(lanczos_finish_kernel, dim3(1), dim3(32), 0, h->stream, h->pdl, (const LanczosCtl *)h->ctl, h->info, h->bet));
+// m, defer: as the recurrence was enqueued (defer 2: the state ends in h->ctl[m & 1]); defer 0 for the step-wise API
+int launch_lanczos_finish(kcrn_problem *h, int m, int defer) {
+    static_assert(kVecThreads == kSweepThreads, "the finish kernel repeats the sweep kernels' summation order");
+    FinishParams P{};
+    P.ctl_in = defer == 2 ? h->ctl + (m & 1) : h->ctl;
+    P.ctl_main = h->ctl; P.info = h->info; P.bet = h->bet; P.alphas = h->alphas;
+    P.defer = defer; P.part = h->lan_rows_part; P.longdot = h->csr.longdot; P.count = h->csr.grid; P.nlong = h->csr.nlong;
+    P.n_samples = (double)h->n_global; P.inv_n = 1.0 / P.n_samples; P.l2 = h->l2;
+    KCRN_CUDA(launch_kernel(lanczos_finish_kernel, dim3(1), dim3(kVecThreads), 0, h->stream, h->pdl, P));
     h->counters[0] += 1;
     return KCRN_OK;
 }

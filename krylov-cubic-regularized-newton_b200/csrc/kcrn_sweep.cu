@@ -103,10 +103,10 @@ int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s) {
     KCRN_CUDA(cudaMalloc(&A->tiles, sizeof(int4) * std::max<size_t>(tiles.size(), 1)));
     KCRN_CUDA(cudaMalloc(&A->longtab, sizeof(int4) * std::max<size_t>(longtab.size(), 1)));
     KCRN_CUDA(cudaMalloc(&A->partial, sizeof(double) * std::max(npartial, 1)));
-    KCRN_CUDA(cudaMalloc(&A->longdot, sizeof(double) * std::max(A->nlong, 1)));
+    KCRN_CUDA(cudaMalloc(&A->longdot, sizeof(double) * (std::max(A->nlong, 1) + 1)));      // even length: 16-byte copies
     KCRN_CUDA(cudaMalloc(&A->ticket, sizeof(unsigned) * std::max(A->nlong, 1)));
     KCRN_CUDA(cudaMemsetAsync(A->ticket, 0, sizeof(unsigned) * std::max(A->nlong, 1), s));
-    KCRN_CUDA(cudaMemsetAsync(A->longdot, 0, sizeof(double) * std::max(A->nlong, 1), s));
+    KCRN_CUDA(cudaMemsetAsync(A->longdot, 0, sizeof(double) * (std::max(A->nlong, 1) + 1), s));
     if (!tiles.empty())
         KCRN_CUDA(cudaMemcpyAsync(A->tiles, tiles.data(), sizeof(int4) * tiles.size(), cudaMemcpyHostToDevice, s));
     if (!longtab.empty())
@@ -147,7 +147,13 @@ struct SweepParams {
     double n_samples, inv_n, l2;   // inv_n = 1 / n_samples (IEEE), for the three-operation exact quotient
     int add_l2;
     // Lanczos
-    LanczosCtl *ctl;
+    LanczosCtl *ctl;               // control block this kernel leaves behind (and reads, unless ctl_in differs)
+    const LanczosCtl *ctl_in;      // state at the start of the kernel (deferred mode: the other half of the pair)
+    int defer;                     // 1: grid-wide sums are finished by the CONSUMER kernel's prologue, not by a tail here
+    int advance_here;              // rows-Lanczos, deferred: finish beta of the previous column sweep and advance
+    const double *prev_part;       // per-CTA pieces left by the producer kernel (+ its long-segment pieces)
+    const double *prev_longdot;
+    int prev_count, prev_nlong;
     double *V;
     const double *g, *wp;
     double *bet;
@@ -248,6 +254,46 @@ __device__ __forceinline__ void cta_sum2_to_thread0(double a, double b, double *
         for (int w = 0; w < kSweepWarps; ++w) { ra += sred[w]; rb += sred[kSweepWarps + w]; }
 }
 
+// Deferred grid-wide sums: the producer kernel leaves one piece per CTA (and per long segment) and simply ends --
+// no fence, no ticket, no last-CTA stage in its tail, which every CTA of every wave would otherwise pay for.  Each
+// CTA of the consumer adds the pieces itself, in the fixed order of the old last-CTA stage (thread-strided, warp
+// tree, warps in order), so all CTAs -- and all runs -- get the same bits.  The pieces travel global -> shared with
+// cp.async (no registers, L2 only), issued as early as the data exists and collected as late as the result is
+// needed, so that their latency hides behind the tile's own gathers.
+//   a[n0] (and b[n0] right behind it at the even stride) + c[n1]; arrays are allocated to an even length.
+__device__ __forceinline__ void defer_begin(const double *a, bool two, int n0, const double *c, int n1, double *sbuf) {
+    const int n0e = (n0 + 1) & ~1, n1e = (n1 + 1) & ~1;
+    for (int i = 2 * threadIdx.x; i < n0e; i += 2 * kSweepThreads) {
+        cp_async_16(sbuf + i, a + i);
+        if (two) cp_async_16(sbuf + n0e + i, a + n0e + i);
+    }
+    double *sc = sbuf + (two ? 2 : 1) * n0e;
+    for (int i = 2 * threadIdx.x; i < n1e; i += 2 * kSweepThreads) cp_async_16(sc + i, c + i);
+}
+
+__device__ __forceinline__ void defer_end(bool two, int n0, int n1, const double *sbuf, double *sred, double &ra,
+                                          double &rb) {
+    const int n0e = (n0 + 1) & ~1;
+    cp_async_wait_all();
+    __syncthreads();
+    double x = 0.0, y = 0.0;
+    for (int i = threadIdx.x; i < n0; i += kSweepThreads) {
+        x += sbuf[i];
+        if (two) y += sbuf[n0e + i];
+    }
+    const double *sc = sbuf + (two ? 2 : 1) * n0e;
+    for (int i = threadIdx.x; i < n1; i += kSweepThreads) x += sc[i];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    x = warp_sum(x);
+    y = warp_sum(y);
+    if (lane == 0) { sred[warp] = x; sred[kSweepWarps + warp] = y; }
+    __syncthreads();
+    ra = rb = 0.0;
+#pragma unroll
+    for (int w = 0; w < kSweepWarps; ++w) { ra += sred[w]; rb += sred[kSweepWarps + w]; }
+    __syncthreads();      // sbuf (the product buffer of the tile) and sred are free again
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepParams P) {
     __shared__ double sprod[kTileNnz];           // products of the tile
@@ -290,29 +336,70 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
     S.src = P.src;
     bool final_ = false;
     int col = 0, store_idx = 0, redo = 0;
+    double xv[kItems];                   // gathered values of the tile
+    bool gathered = false;
+    bool alpha_pending = false;
+    LanczosCtl st_cols;
     if constexpr (MODE == kRowsLanczos) {
-        if (P.ctl->done) return;
-        col = P.ctl->col;
-        redo = P.ctl->redo;
-        final_ = P.ctl->final_ != 0;
-        store_idx = P.ctl->store_idx;
+        LanczosCtl st = *P.ctl_in;
+        const bool scribe = blockIdx.x == 0 && tid == 0;      // the one thread that persists what all compute
+        if (st.done) {
+            if (scribe && P.ctl != P.ctl_in) *P.ctl = st;      // keep the pair in step
+            return;
+        }
+        if (P.advance_here) {
+            // beta = |w'| of the column sweep before us is still in pieces.  While they travel, gather from w'
+            // -- the source unless the recurrence breaks down right now, which the sum will tell
+            defer_begin(P.prev_part, false, P.prev_count, P.prev_longdot, P.prev_nlong, sprod);
+#pragma unroll
+            for (int r = 0; r < kItems; ++r) xv[r] = ci[r] >= 0 ? __ldg(P.wp + ci[r]) : 0.0;
+            gathered = true;
+            double bsq, unused;
+            defer_end(false, P.prev_count, P.prev_nlong, sprod, sred, bsq, unused);
+            lanczos_advance(&st, scribe ? P.bet : nullptr, sqrt(bsq));     // cubic.py:98-109, in registers
+            if (st.redo) gathered = false;                     // breakdown: the operator is re-applied to V[col]
+        }
+        if (scribe && P.ctl != P.ctl_in) *P.ctl = st;
+        col = st.col;
+        redo = st.redo;
+        final_ = st.final_ != 0;
+        store_idx = st.store_idx;
         if (redo) {
             S.src = P.V + (size_t)col * P.d;
         } else {
             S.src = col == 0 ? P.g : P.wp;
-            S.beta = P.bet[col];
+            S.beta = st.cur_beta;                // = bet[col], without a dependent second load
             S.rinv = 1.0 / S.beta;
         }
     }
     if constexpr (MODE == kColsLanczos) {
-        if (P.ctl->done) return;
-        col = P.ctl->col;
-        S.alpha = P.alphas[col];
+        st_cols = *P.ctl_in;
+        if (st_cols.done) return;
+        col = st_cols.col;
+        if (P.defer) {
+            // alpha = v'Hv of the row sweep before us is still in pieces; it is needed by the epilogue only
+            defer_begin(P.prev_part, true, P.prev_count, P.prev_longdot, P.prev_nlong, sprod);
+            alpha_pending = true;
+            if (st_cols.final_) {                              // cubic.py:109: the last alpha needs no further vector
+                double s1, s2;
+                defer_end(true, P.prev_count, P.prev_nlong, sprod, sred, s1, s2);
+                if (blockIdx.x == 0 && tid == 0) {
+                    const double alpha = __dadd_rn(quotient(s1, P.n_samples, P.inv_n), __dmul_rn(P.l2, s2));
+                    P.alphas[st_cols.store_idx] = alpha;
+                    P.ctl->cur_alpha = alpha;
+                    P.ctl->hvps = st_cols.hvps + 1;
+                    P.ctl->done = 1;
+                }
+                return;
+            }
+        } else {
+            S.alpha = st_cols.cur_alpha;         // = alphas[col], written by the row sweep of this step
+        }
         S.vcol = P.V + (size_t)col * P.d;
         if (col > 0) {
             S.subtract = true;
             S.vpre = P.V + (size_t)(col - 1) * P.d;
-            S.beta_prev = P.bet[col];
+            S.beta_prev = st_cols.cur_beta;      // = bet[col]
         }
     }
 
@@ -360,13 +447,28 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
                 if constexpr (NOP > 1) o1[0] = a1;
             }
         }
+        if (!gathered) {
+#pragma unroll
+            for (int r = 0; r < kItems; ++r) xv[r] = ci[r] >= 0 ? __ldg(S.src + ci[r]) : 0.0;
+        }
+        if constexpr (MODE == kColsLanczos) {
+            if (alpha_pending) {                 // the gathers above are in flight while the pieces are added
+                double s1, s2;
+                defer_end(true, P.prev_count, P.prev_nlong, sprod, sred, s1, s2);
+                S.alpha = __dadd_rn(quotient(s1, P.n_samples, P.inv_n), __dmul_rn(P.l2, s2));
+                if (blockIdx.x == 0 && tid == 0) {
+                    P.alphas[col] = S.alpha;
+                    P.ctl->cur_alpha = S.alpha;
+                    P.ctl->hvps = st_cols.hvps + 1;
+                }
+            }
+        }
         double p[kItems];
 #pragma unroll
         for (int r = 0; r < kItems; ++r) {
-            double xv = 0.0;
-            if (ci[r] >= 0) xv = __ldg(S.src + ci[r]);
-            if constexpr (MODE == kRowsLanczos) xv = quotient(xv, S.beta, S.rinv);
-            p[r] = av[r] * xv;
+            double x = xv[r];
+            if constexpr (MODE == kRowsLanczos) x = quotient(x, S.beta, S.rinv);      // beta = 1 when re-applying
+            p[r] = av[r] * x;
         }
         if (!stream) {
             // one segment (or one piece of a long one) spread over the whole CTA
@@ -428,13 +530,17 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
     pdl_trigger();
 
     if constexpr (MODE == kRowsLanczos) {
-        // alpha = v'Hv: threads -> tile (fixed order) -> the last CTA adds the tile sums in tile order
+        // alpha = v'Hv: threads -> tile (fixed order) -> tiles in tile order, by the consumer (deferred) or by the
+        // last CTA here
         __syncthreads();
         double mine, mine2;
         cta_sum2_to_thread0(acc, vsq, sred, mine, mine2);
         if (tid == 0) {
             P.red_partials[blockIdx.x] = mine;
-            P.red_partials[gridDim.x + blockIdx.x] = mine2;
+            P.red_partials[((gridDim.x + 1) & ~1u) + blockIdx.x] = mine2;      // even stride: 16-byte copies later
+        }
+        if (P.defer) return;
+        if (tid == 0) {
             __threadfence();
             s_last = atomicInc(P.red_ticket, gridDim.x - 1) == gridDim.x - 1;
         }
@@ -444,7 +550,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
             double tot = 0.0, tot2 = 0.0;
             for (int i = tid; i < (int)gridDim.x; i += kSweepThreads) {
                 tot += __ldcg(P.red_partials + i);
-                tot2 += __ldcg(P.red_partials + gridDim.x + i);
+                tot2 += __ldcg(P.red_partials + ((gridDim.x + 1) & ~1u) + i);
             }
             for (int i = tid; i < P.nlong; i += kSweepThreads) tot += __ldcg(P.longdot + i);
             __syncthreads();
@@ -454,6 +560,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
                 if (P.alpha_mode == 0) {
                     const double alpha = __dadd_rn(quotient(s1, P.n_samples, P.inv_n), __dmul_rn(P.l2, s2));
                     P.alphas[final_ ? store_idx : col] = alpha;
+                    P.ctl->cur_alpha = alpha;
                     P.ctl->hvps += 1;
                     if (final_) P.ctl->done = 1;           // cubic.py:109: the last alpha needs no further vector
                 } else {
@@ -465,16 +572,19 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
     }
 
     if constexpr (MODE == kColsLanczos) {
-        // beta^2 = |w'|^2: threads -> tile (fixed order) -> the last CTA adds the tile sums in tile order
+        // beta^2 = |w'|^2: threads -> tile (fixed order) -> tiles in tile order, by the next row sweep (deferred) or
+        // by the last CTA here
+        if (!P.update_ctl) return;                 // re-orthogonalisation follows: it recomputes the norm
         __syncthreads();
         const double mine = cta_sum_to_thread0(acc, sred);
+        if (tid == 0) P.red_partials[blockIdx.x] = mine;
+        if (P.defer) return;
         if (tid == 0) {
-            P.red_partials[blockIdx.x] = mine;
             __threadfence();
             s_last = atomicInc(P.red_ticket, gridDim.x - 1) == gridDim.x - 1;
         }
         __syncthreads();
-        if (s_last && P.update_ctl) {
+        if (s_last) {
             __threadfence();
             double tot = 0.0;
             for (int i = tid; i < (int)gridDim.x; i += kSweepThreads) tot += __ldcg(P.red_partials + i);
@@ -530,12 +640,29 @@ int launch_rows_weighted(kcrn_problem *h, const double *v) {
     return launch<kRowsWeighted>(h, h->csr, P);
 }
 
-int launch_rows_lanczos(kcrn_problem *h, double *alpha_raw) {
+// The consumer-side sums stage the producer's pieces in the tile's product buffer: both sets must fit
+bool lanczos_defer_fits(const kcrn_problem *h) {
+    auto even = [](int v) { return (v + 1) & ~1; };
+    return 2 * even(h->csr.grid) + even(h->csr.nlong) <= kTileNnz && even(h->csc.grid) + even(h->csc.nlong) <= kTileNnz;
+}
+
+// slot = position of the step in the captured recurrence; defer = 1 (single-GPU fused loop): grid-wide sums are
+// finished by the consumer kernel and the control block ping-pongs between h->ctl[0] and h->ctl[1] so that the
+// row sweep can advance the recurrence in registers while other CTAs still read the old state.
+int launch_rows_lanczos(kcrn_problem *h, double *alpha_raw, int slot, int defer) {
     SweepParams P{};
-    P.D = h->D; P.out = h->t; P.ctl = h->ctl; P.V = h->V; P.g = h->g; P.wp = h->wp; P.bet = h->bet; P.d = h->d;
+    P.D = h->D; P.out = h->t; P.V = h->V; P.g = h->g; P.wp = h->wp; P.bet = h->bet; P.d = h->d;
     P.alphas = h->alphas; P.n_samples = (double)h->n_global; P.inv_n = 1.0 / P.n_samples; P.l2 = h->l2;
-    P.red_partials = h->red_partials; P.red_ticket = h->red_ticket + 7;
     P.alpha_mode = h->world > 1 ? 1 : 0; P.alpha_raw = alpha_raw; P.alpha_raw2 = h->scal + 17;   // the first is summed over the ranks with A't
+    P.defer = defer;
+    if (defer == 2) {                      // advance here: beta pieces of the previous column sweep
+        P.ctl_in = h->ctl + (slot & 1); P.ctl = h->ctl + ((slot + 1) & 1);
+        P.advance_here = slot > 0;
+        P.prev_part = h->lan_cols_part; P.prev_count = h->csc.grid; P.prev_longdot = h->csc.longdot; P.prev_nlong = h->csc.nlong;
+    } else {
+        P.ctl_in = P.ctl = h->ctl;
+    }
+    P.red_partials = defer ? h->lan_rows_part : h->red_partials; P.red_ticket = h->red_ticket + 7;
     h->counters[3] += 1;
     return launch<kRowsLanczos>(h, h->csr, P);
 }
@@ -555,12 +682,17 @@ int launch_cols_scaled(kcrn_problem *h, const double *src, const double *u, doub
     return launch<kColsScaled>(h, h->csc, P);
 }
 
-int launch_cols_lanczos(kcrn_problem *h, int update_ctl) {
+int launch_cols_lanczos(kcrn_problem *h, int update_ctl, int slot, int defer) {
     SweepParams P{};
-    P.src = h->t; P.ctl = h->ctl; P.V = h->V; P.bet = h->bet; P.w = h->wp; P.alphas = h->alphas; P.d = h->d;
+    P.src = h->t; P.V = h->V; P.bet = h->bet; P.w = h->wp; P.alphas = h->alphas; P.d = h->d;
     P.update_ctl = update_ctl;
     P.n_samples = (double)h->n_global; P.inv_n = 1.0 / P.n_samples; P.l2 = h->l2;
-    P.red_partials = h->red_partials; P.red_ticket = h->red_ticket + 0;
+    P.defer = defer;
+    P.ctl_in = P.ctl = defer == 2 ? h->ctl + ((slot + 1) & 1) : h->ctl;
+    if (defer) {
+        P.prev_part = h->lan_rows_part; P.prev_count = h->csr.grid; P.prev_longdot = h->csr.longdot; P.prev_nlong = h->csr.nlong;
+    }
+    P.red_partials = defer ? h->lan_cols_part : h->red_partials; P.red_ticket = h->red_ticket + 0;
     h->counters[4] += 1;
     return launch<kColsLanczos>(h, h->csc, P);
 }
