@@ -88,7 +88,8 @@ int enqueue_lanczos(kcrn_problem *h, int m, int reorth) {
     // single GPU: the grid-wide sums (alpha after the row sweep, beta after the column sweep) are finished by the
     // kernel that consumes them -- 2: both, the row sweep also advances the recurrence; 1: alpha only (the
     // re-orthogonalisation kernel owns beta and the advance).  Row-sharded: 0, the exchange kernels own both.
-    const int defer = (h->world > 1 || !lanczos_defer_fits(h)) ? 0 : (reorth ? 1 : 2);
+    static const bool no_defer = getenv("KCRN_NO_DEFER") != nullptr;                 // A/B switch
+    const int defer = (h->world > 1 || no_defer || !lanczos_defer_fits(h)) ? 0 : (reorth ? 1 : 2);
     KCRN_TRY(launch_lanczos_init(h, m));
     for (int slot = 0; slot < m; ++slot) {
         // rows sweep: t = D (A v), basis column, and alpha = v'Hv one sweep early (so that the column sweep can
