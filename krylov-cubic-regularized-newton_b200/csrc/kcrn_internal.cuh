@@ -46,7 +46,7 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
 }
 
 // ----------------------------------------------------------------------------- geometry
-constexpr int kTileNnz = 2048;     // non-zeros per CTA tile (8 per thread)
+constexpr int kTileNnz = 2048;     // non-zeros per CTA tile at the default 8 per thread (11 or 12 per thread for small matrices, see build_tiles)
 constexpr int kTileSegs = 1024;    // at most this many segments (rows / columns) per stream tile
 constexpr int kShortSeg = 1024;    // longest segment that shares a stream tile with others
 constexpr int kSingleTag = 15;     // descriptor tag of a tile that holds one medium segment
@@ -70,6 +70,7 @@ struct SegMat {
     double *val = nullptr;
     int4 *tiles = nullptr;
     int ntiles = 0;
+    int items = 8;               // non-zeros per thread of the tiles: 8, 11 or 12 (tile = items x 256)
     int4 *longtab = nullptr;
     int nlong = 0, npartial = 0;
     double *partial = nullptr;   // [npartial] piece sums of long segments

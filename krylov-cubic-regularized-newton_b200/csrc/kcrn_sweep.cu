@@ -43,27 +43,22 @@ void free_segmat(SegMat *A) {
     *A = SegMat();
 }
 
-int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s) {
-    A->gather_len = gather_len;
-    const int64_t nseg = A->nseg;
-    std::vector<int32_t> ptr((size_t)nseg + 1);
-    KCRN_CUDA(cudaMemcpyAsync(ptr.data(), A->ptr, sizeof(int32_t) * (nseg + 1), cudaMemcpyDeviceToHost, s));
-    KCRN_CUDA(cudaStreamSynchronize(s));
-    std::vector<int4> tiles, longtab;
-    const char *env_short = getenv("KCRN_SHORT_SEG");       // tuning knob: longest segment that shares a tile
-    const int short_seg = env_short ? std::max(1, std::min(kTileNnz, atoi(env_short))) : kShortSeg;
-    tiles.reserve((size_t)(A->nnz / kTileNnz * 2 + nseg / kTileSegs + 16));
-    int npartial = 0;
+// Tile list for one candidate tile size (tile_nnz non-zeros per CTA tile)
+static void make_tiles(const std::vector<int32_t> &ptr, int64_t nseg, int64_t nnz, int tile_nnz, int short_seg,
+                       std::vector<int4> &tiles, std::vector<int4> &longtab, int &npartial) {
+    tiles.clear(); longtab.clear();
+    tiles.reserve((size_t)(nnz / tile_nnz * 2 + nseg / kTileSegs + 16));
+    npartial = 0;
     int64_t sg = 0;
     while (sg < nseg) {
         const int len = ptr[sg + 1] - ptr[sg];
-        if (len > kTileNnz) {                                   // long segment: pieces + ordered combine
-            const int pieces = (len + kTileNnz - 1) / kTileNnz;
+        if (len > tile_nnz) {                                   // long segment: pieces + ordered combine
+            const int pieces = (len + tile_nnz - 1) / tile_nnz;
             const int lid = (int)longtab.size();
             longtab.push_back(make_int4(npartial, pieces, ptr[sg], (int)sg));
             for (int p = 0; p < pieces; ++p) {
-                const int k0 = ptr[sg] + p * kTileNnz;
-                const int nk = std::min(kTileNnz, ptr[sg + 1] - k0);
+                const int k0 = ptr[sg] + p * tile_nnz;
+                const int nk = std::min(tile_nnz, ptr[sg + 1] - k0);
                 tiles.push_back(make_int4((int)sg, k0, -(lid + 1), nk));
             }
             npartial += pieces;
@@ -80,7 +75,7 @@ int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s) {
         int nk = 0, maxlen = 0;
         while (sg < nseg && sg - s0 < kTileSegs) {
             const int l = ptr[sg + 1] - ptr[sg];
-            if (l > short_seg || nk + l > kTileNnz) break;
+            if (l > short_seg || nk + l > tile_nnz) break;
             nk += l;
             maxlen = std::max(maxlen, l);
             ++sg;
@@ -96,6 +91,41 @@ int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s) {
         }
         tiles.push_back(make_int4((int)s0, k0, ns, nk | (best << 16)));
     }
+}
+
+// The tile size is picked per matrix.  A sweep over a small (L2-resident) matrix is a handful of waves of CTA
+// tiles, each wave one latency chain long: what counts is the NUMBER OF WAVES, e.g. the rcv1-shape CSR copy is 732
+// tiles of 2048 -- two waves on 148 SMs x 4 CTAs, the second one a quarter full -- but 533 tiles of 2816: one wave
+// (measured: 28.4 -> 25.2 us per HVP inside the Lanczos graph).  Among the candidates (8, 11, 12 non-zeros per
+// thread) take the fewest waves, then the smaller tile; matrices of many waves keep 2048.
+int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s) {
+    A->gather_len = gather_len;
+    const int64_t nseg = A->nseg;
+    std::vector<int32_t> ptr((size_t)nseg + 1);
+    KCRN_CUDA(cudaMemcpyAsync(ptr.data(), A->ptr, sizeof(int32_t) * (nseg + 1), cudaMemcpyDeviceToHost, s));
+    KCRN_CUDA(cudaStreamSynchronize(s));
+    const char *env_short = getenv("KCRN_SHORT_SEG");       // tuning knob: longest segment that shares a tile
+    const char *env_items = getenv("KCRN_TILE_ITEMS");      // tuning knob: force 8, 11 or 12 non-zeros per thread
+    if (env_items && atoi(env_items) == 0) env_items = nullptr;
+    std::vector<int4> tiles, longtab;
+    int npartial = 0;
+    const int cand[3] = {8, 11, 12};
+    const int slots = kNumSm * 4 - 32;                      // resident CTAs, minus a margin for the neighbours under PDL
+    int items = 8;
+    long best_waves = -1;
+    for (int c : cand) {
+        if (env_items && atoi(env_items) != c) continue;
+        const int tile_nnz = c * kSweepThreads;
+        const int short_seg = env_short ? std::max(1, std::min(tile_nnz, atoi(env_short))) : kShortSeg;
+        make_tiles(ptr, nseg, A->nnz, tile_nnz, short_seg, tiles, longtab, npartial);
+        const long waves = ((long)tiles.size() + slots - 1) / slots;
+        if (best_waves < 0 || waves < best_waves) { best_waves = waves; items = c; }
+        if (c == 8 && waves > 4 && !env_items) break;        // many waves: the quantisation no longer matters
+    }
+    const int tile_nnz = items * kSweepThreads;
+    const int short_seg = env_short ? std::max(1, std::min(tile_nnz, atoi(env_short))) : kShortSeg;
+    make_tiles(ptr, nseg, A->nnz, tile_nnz, short_seg, tiles, longtab, npartial);
+    A->items = items;
     A->ntiles = (int)tiles.size();
     A->nlong = (int)longtab.size();
     A->npartial = npartial;
@@ -174,7 +204,6 @@ struct SweepState {
     bool subtract = false;
 };
 
-constexpr int kItems = kTileNnz / kSweepThreads;       // non-zeros per thread
 constexpr int kSegRounds = kTileSegs / kSweepThreads;  // segments per thread in the epilogue
 __host__ __device__ constexpr int sweep_operands(int mode) { return mode == kColsRaw ? 0 : (mode == kColsLanczos ? 2 : 1); }
 
@@ -294,8 +323,9 @@ __device__ __forceinline__ void defer_end(bool two, int n0, int n1, const double
     __syncthreads();      // sbuf (the product buffer of the tile) and sred are free again
 }
 
-template <int MODE>
+template <int MODE, int kItems>
 __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepParams P) {
+    constexpr int kTileNnz = kItems * kSweepThreads;       // non-zeros per CTA tile, kItems per thread
     __shared__ double sprod[kTileNnz];           // products of the tile
     __shared__ double ssum[kTileSegs];           // per-segment sums of the tile
     __shared__ int sptr[kTileSegs + 8];          // segment pointers of the tile
@@ -605,7 +635,9 @@ void fill_matrix(SweepParams &P, const SegMat &A) {
 template <int MODE>
 int launch(kcrn_problem *h, const SegMat &A, SweepParams &P) {
     fill_matrix(P, A);
-    KCRN_CUDA(launch_kernel(sweep_kernel<MODE>, dim3(A.grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
+    if (A.items == 11) KCRN_CUDA(launch_kernel(sweep_kernel<MODE, 11>, dim3(A.grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
+    else if (A.items == 12) KCRN_CUDA(launch_kernel(sweep_kernel<MODE, 12>, dim3(A.grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
+    else KCRN_CUDA(launch_kernel(sweep_kernel<MODE, 8>, dim3(A.grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
     h->counters[0] += 1;
     return KCRN_OK;
 }
@@ -643,7 +675,9 @@ int launch_rows_weighted(kcrn_problem *h, const double *v) {
 // The consumer-side sums stage the producer's pieces in the tile's product buffer: both sets must fit
 bool lanczos_defer_fits(const kcrn_problem *h) {
     auto even = [](int v) { return (v + 1) & ~1; };
-    return 2 * even(h->csr.grid) + even(h->csr.nlong) <= kTileNnz && even(h->csc.grid) + even(h->csc.nlong) <= kTileNnz;
+    // staged in the CONSUMER's product buffer: row pieces in the column sweep's, column pieces in the row sweep's
+    return 2 * even(h->csr.grid) + even(h->csr.nlong) <= h->csc.items * kSweepThreads &&
+           even(h->csc.grid) + even(h->csc.nlong) <= h->csr.items * kSweepThreads;
 }
 
 // slot = position of the step in the captured recurrence; defer = 1 (single-GPU fused loop): grid-wide sums are

@@ -83,6 +83,8 @@ def load():
     """Load libkcrn.so (once).  Raises if it has not been built: there is no CPU path."""
     global _lib
     if _lib is None:
+        global LIB_PATH
+        LIB_PATH = os.environ.get("KCRN_LIBRARY", LIB_PATH)      # development: a kernel variant built elsewhere
         if not os.path.exists(LIB_PATH):
             raise ImportError(f"{LIB_PATH} is missing -- run `python -m kcrn_b200.build` "
                               "(__graft_entry__.build()); there is no fallback implementation")

@@ -1,0 +1,26 @@
+"""Sweep and Lanczos-graph timing of one libkcrn variant (KCRN_LIBRARY), rcv1 / w8a shapes."""
+import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "..", "tests"))
+import conftest  # noqa
+import torch
+from kcrn_b200.engine import Engine
+from kcrn_b200.synth import make_problem
+from oracle import oracle as O
+for name in sys.argv[1:] or ["rcv1"]:
+    P = make_problem(name, seed=0)
+    eng = Engine(P.indptr, P.indices, P.data, O.map_labels(P.b), (P.n, P.d))
+    eng.set_x(torch.as_tensor(P.x0, device="cuda"))
+    eng.gradient(keep_internal=True)
+    us = [min(eng.time_sweep(w, 200) for _ in range(3)) for w in (0, 1)]
+    for _ in range(5):
+        eng.lanczos(10, False)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 1e9
+    for _ in range(5):
+        a.record()
+        for _ in range(50):
+            eng.lanczos(10, False)
+        b.record(); torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b) / 50 * 1e3)
+    print(f"{os.path.basename(os.environ.get('KCRN_LIBRARY', 'default')):22s} {name:6s} sweeps {us[0]:6.2f} {us[1]:6.2f} us   Lanczos graph {best / 10:6.2f} us per HVP")
+    eng.close()
