@@ -282,7 +282,9 @@ def main():
     gbs = [eng.sweep_bytes(w) / (us[w] * 1e-6) / 1e9 for w in (0, 1)]
     step_ms = ms / K
     hvp_us = 1e3 * step_ms / max(1.0, hvps / K)                 # whole step amortised per HVP
-    # the captured m-step Lanczos graph alone (m HVPs + the vector kernels between them), back to back
+    # the captured m-step Lanczos graph alone (m HVPs + the vector kernels between them), back to back, at x0 (late
+    # iterates break down early -- cubic.py:98 -- and the rest of the graph is no-op nodes)
+    eng.set_x(loss.to_device(P.x0))
     eng.gradient(keep_internal=True)
     for _ in range(3):
         eng.lanczos(args.m, bool(args.reorth))

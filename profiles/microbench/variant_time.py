@@ -16,11 +16,20 @@ for name in sys.argv[1:] or ["rcv1"]:
         eng.lanczos(10, False)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     best = 1e9
+    allb = []
     for _ in range(5):
         a.record()
         for _ in range(50):
             eng.lanczos(10, False)
         b.record(); torch.cuda.synchronize()
+        allb.append(round(a.elapsed_time(b) / 50 * 1e2, 2))
         best = min(best, a.elapsed_time(b) / 50 * 1e3)
-    print(f"{os.path.basename(os.environ.get('KCRN_LIBRARY', 'default')):22s} {name:6s} sweeps {us[0]:6.2f} {us[1]:6.2f} us   Lanczos graph {best / 10:6.2f} us per HVP")
+    print(f"{os.path.basename(os.environ.get('KCRN_LIBRARY', 'default')):22s} {name:6s} sweeps {us[0]:6.2f} {us[1]:6.2f} us   Lanczos graph {best / 10:6.2f} us per HVP  batches {allb}")
+    x = eng.new_vector(); x.copy_(torch.as_tensor(P.x0, device="cuda")); x.mul_(0.2)
+    eng.set_x(x); eng.gradient(keep_internal=True)
+    a.record()
+    for _ in range(20):
+        eng.lanczos(10, False)
+    b.record(); torch.cuda.synchronize()
+    print("   at another x, 20 reps once:", round(a.elapsed_time(b) / 20 * 1e2, 2), "us per HVP, hvps", int(eng.lanczos_view()[3][3].item()))
     eng.close()
