@@ -111,21 +111,28 @@ int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s) {
     int npartial = 0;
     const int cand[3] = {8, 11, 12};
     const int slots = kNumSm * 4 - 32;                      // resident CTAs, minus a margin for the neighbours under PDL
-    int items = 8;
+    int items = 8, short_seg = kShortSeg;
     long best_waves = -1;
     for (int c : cand) {
         if (env_items && atoi(env_items) != c) continue;
         const int tile_nnz = c * kSweepThreads;
-        const int short_seg = env_short ? std::max(1, std::min(tile_nnz, atoi(env_short))) : kShortSeg;
-        make_tiles(ptr, nseg, A->nnz, tile_nnz, short_seg, tiles, longtab, npartial);
-        const long waves = ((long)tiles.size() + slots - 1) / slots;
-        if (best_waves < 0 || waves < best_waves) { best_waves = waves; items = c; }
-        if (c == 8 && waves > 4 && !env_items) break;        // many waves: the quantisation no longer matters
+        // few waves: also let segments of up to 2048 share tiles (fewer, fuller tiles; measured 24.6 -> 24.0 us per HVP)
+        const int ss = env_short ? std::max(1, std::min(tile_nnz, atoi(env_short))) : 2 * kShortSeg;
+        make_tiles(ptr, nseg, A->nnz, tile_nnz, c == 8 && !env_short ? kShortSeg : ss, tiles, longtab, npartial);
+        long waves = ((long)tiles.size() + slots - 1) / slots;
+        if (c == 8 && waves > 4 && !env_items) { items = 8; short_seg = env_short ? ss : kShortSeg; best_waves = waves; break; }
+        if (c == 8 && !env_short) {              // the small-matrix packing for the default tile size as well
+            make_tiles(ptr, nseg, A->nnz, tile_nnz, ss, tiles, longtab, npartial);
+            waves = ((long)tiles.size() + slots - 1) / slots;
+        }
+        if (best_waves < 0 || waves < best_waves) { best_waves = waves; items = c; short_seg = ss; }
     }
     const int tile_nnz = items * kSweepThreads;
-    const int short_seg = env_short ? std::max(1, std::min(tile_nnz, atoi(env_short))) : kShortSeg;
     make_tiles(ptr, nseg, A->nnz, tile_nnz, short_seg, tiles, longtab, npartial);
     A->items = items;
+    if (getenv("KCRN_VERBOSE"))
+        fprintf(stderr, "kcrn: %lld segments, %lld non-zeros -> %zu tiles of %d (%zu long segments)\n", (long long)nseg,
+                (long long)A->nnz, tiles.size(), tile_nnz, longtab.size());
     A->ntiles = (int)tiles.size();
     A->nlong = (int)longtab.size();
     A->npartial = npartial;

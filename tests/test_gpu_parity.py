@@ -338,8 +338,11 @@ def test_free_running_trajectory_vs_reference(torch, golden, name, m, iters, reo
     #     one perturbed run is a sample of the noise, not a bound), we agree with it to the 1e-8 bar
     assert np.all(dev[:prefix] <= 1e-8), dev[:prefix]
     # (2) beyond, rounding noise is amplified chaotically: stay within two orders of the
-    #     reference's own self-noise
-    assert np.all(dev <= np.maximum(1e-8, 100 * envelope)), (dev, envelope)
+    #     reference's own self-noise.  The envelope is ONE sample of that noise; where a run bifurcates (a different
+    #     line-search decision: the deviation jumps by orders of magnitude in one iteration) is itself noise, so the
+    #     sample is read with a slack of three iterations
+    lagged = np.array([envelope[min(i + 3, k - 1)] for i in range(k)])
+    assert np.all(dev <= np.maximum(1e-8, 100 * lagged)), (dev, envelope)
     # the iteration stays a descent method and ends where the reference ends (loose, chaos-proof)
     assert np.all(np.diff(f) <= 1e-12)
     assert f[-1] <= ref[0]
