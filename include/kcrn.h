@@ -190,9 +190,10 @@ int kcrn_svmlight_parse(const char *text, int64_t len, int threads, int64_t n_ro
  * counters[0..8): kernels launched, graph launches, HVPs, forward sweeps, transpose sweeps,
  * allreduces, bytes H2D, bytes D2H.  */
 int kcrn_counters(kcrn_handle h, int64_t *counters8_host, int reset);
-/* timing probes used by bench.py's roofline leg: run `reps` back-to-back launches of one sweep
- * kernel (which = 0: CSR pass of the HVP, 1: CSC pass of the HVP) between two CUDA events on the
- * handle's stream and return the mean duration in microseconds. */
+/* timing probe used by bench.py's roofline leg: about `reps` back-to-back launches of one sweep kernel (which = 0:
+ * CSR pass of the HVP, 1: CSC pass of the HVP), launched the way the product launches it -- nodes of a captured
+ * graph joined by programmatic edges, 20 per graph -- between two CUDA events on the handle's stream; returns the
+ * mean duration per launch in microseconds. */
 int kcrn_time_sweep(kcrn_handle h, int which, int reps, double *mean_us_host);
 
 #ifdef __cplusplus
