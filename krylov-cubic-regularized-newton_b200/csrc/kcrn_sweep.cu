@@ -40,6 +40,7 @@ namespace kcrn {
 void free_segmat(SegMat *A) {
     cudaFree(A->ptr); cudaFree(A->idx); cudaFree(A->val); cudaFree(A->tiles); cudaFree(A->longtab);
     cudaFree(A->partial); cudaFree(A->longdot); cudaFree(A->ticket); cudaFree(A->segid); cudaFree(A->pos);
+    cudaFree(A->gidx); cudaFree(A->gval);
     *A = SegMat();
 }
 
@@ -90,6 +91,43 @@ static void make_tiles(const std::vector<int32_t> &ptr, int64_t nseg, int64_t nn
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = lg; }
         }
         tiles.push_back(make_int4((int)s0, k0, ns, nk | (best << 16)));
+    }
+}
+
+// Gather order (setup, once per matrix): one CTA per tile sorts the entries of a stream tile by the index they
+// gather with -- bitonic network over `index << kSlotBits | natural position` in shared memory; the words are
+// unique, so the order is total -- and writes the words and the values in that order.  Single-segment tiles and
+// pieces keep their natural order (sorted already for canonical input; their CTA-wide sums depend on it).
+constexpr int kSortCap = 1 << kSlotBits;
+__global__ void __launch_bounds__(kSweepThreads) gather_order_kernel(const int4 *__restrict__ tiles,
+                                                                     const int32_t *__restrict__ idx,
+                                                                     const double *__restrict__ val,
+                                                                     uint32_t *__restrict__ gidx,
+                                                                     double *__restrict__ gval) {
+    __shared__ uint32_t key[kSortCap];
+    const int4 td = tiles[blockIdx.x];
+    const int k0 = td.y, nk = td.w & 0xffff, tag = td.w >> 16, tid = threadIdx.x;
+    const bool stream = td.z > 0 && tag != kSingleTag;
+    for (int i = tid; i < kSortCap; i += kSweepThreads)
+        key[i] = i < nk ? ((uint32_t)idx[k0 + i] << kSlotBits) | (uint32_t)i : 0xffffffffu;
+    __syncthreads();
+    if (stream) {
+        int np = 2;
+        while (np < nk) np <<= 1;
+        for (int k = 2; k <= np; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (np >> 1); t += kSweepThreads) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                    const uint32_t a = key[i], b = key[l];
+                    if ((a > b) == ((i & k) == 0)) { key[i] = b; key[l] = a; }
+                }
+                __syncthreads();
+            }
+    }
+    for (int i = tid; i < nk; i += kSweepThreads) {
+        const uint32_t w = key[i];
+        gidx[k0 + i] = w;
+        gval[k0 + i] = val[k0 + (int)(w & (kSortCap - 1))];
     }
 }
 
@@ -148,6 +186,14 @@ int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s) {
         KCRN_CUDA(cudaMemcpyAsync(A->tiles, tiles.data(), sizeof(int4) * tiles.size(), cudaMemcpyHostToDevice, s));
     if (!longtab.empty())
         KCRN_CUDA(cudaMemcpyAsync(A->longtab, longtab.data(), sizeof(int4) * longtab.size(), cudaMemcpyHostToDevice, s));
+    // gather-ordered copy for the sweeps (KCRN_NO_GATHER_ORDER=1: A/B switch, sweeps read idx / val as stored)
+    if (A->nnz > 0 && A->ntiles > 0 && gather_len <= ((int64_t)1 << (32 - kSlotBits)) && tile_nnz <= kSortCap &&
+        getenv("KCRN_NO_GATHER_ORDER") == nullptr) {
+        KCRN_CUDA(cudaMalloc(&A->gidx, sizeof(uint32_t) * (size_t)A->nnz));
+        KCRN_CUDA(cudaMalloc(&A->gval, sizeof(double) * (size_t)A->nnz));
+        gather_order_kernel<<<(unsigned)A->ntiles, kSweepThreads, 0, s>>>(A->tiles, A->idx, A->val, A->gidx, A->gval);
+        KCRN_LAUNCH_CHECK();
+    }
     KCRN_CUDA(cudaStreamSynchronize(s));
     return KCRN_OK;
 }
@@ -167,6 +213,8 @@ enum SweepMode {
 struct SweepParams {
     const int32_t *ptr, *idx;
     const double *val;
+    const uint32_t *gidx;          // gather-ordered words and values of the tiles (null: idx / val as stored)
+    const double *gval;
     const int4 *tiles;
     int ntiles;
     const int4 *longtab;
@@ -212,6 +260,9 @@ struct SweepState {
 };
 
 constexpr int kSegRounds = kTileSegs / kSweepThreads;  // segments per thread in the epilogue
+__device__ __forceinline__ int gather_index(int word, bool ordered) {
+    return ordered ? (int)((unsigned)word >> kSlotBits) : word;
+}
 __host__ __device__ constexpr int sweep_operands(int mode) { return mode == kColsRaw ? 0 : (mode == kColsLanczos ? 2 : 1); }
 
 // Epilogue of one finished segment.  op0 / op1 are the pass's per-segment operands, already in registers:
@@ -346,12 +397,13 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
     // still finishing, so the descriptor -> (index, value) part of the latency chain overlaps with its tail.
     const int tile = blockIdx.x;
     int4 td = make_int4(0, 0, 0, 0);
-    int ci[kItems];
+    int ci[kItems];                  // index, or gather-ordered word (index << kSlotBits | natural position); -1: none
     double av[kItems];
+    const bool ordered = P.gidx != nullptr;
     if (tile < P.ntiles) {
         td = __ldg(P.tiles + tile);
-        const int32_t *ip = P.idx + td.y;
-        const double *vp = P.val + td.y;
+        const int32_t *ip = (ordered ? reinterpret_cast<const int32_t *>(P.gidx) : P.idx) + td.y;
+        const double *vp = (ordered ? P.gval : P.val) + td.y;
         const int nk0 = td.w & 0xffff;
 #pragma unroll
         for (int r = 0; r < kItems; ++r) {
@@ -389,7 +441,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
             // -- the source unless the recurrence breaks down right now, which the sum will tell
             defer_begin(P.prev_part, false, P.prev_count, P.prev_longdot, P.prev_nlong, sprod);
 #pragma unroll
-            for (int r = 0; r < kItems; ++r) xv[r] = ci[r] >= 0 ? __ldg(P.wp + ci[r]) : 0.0;
+            for (int r = 0; r < kItems; ++r) xv[r] = ci[r] != -1 ? __ldg(P.wp + gather_index(ci[r], ordered)) : 0.0;
             gathered = true;
             double bsq, unused;
             defer_end(false, P.prev_count, P.prev_nlong, sprod, sred, bsq, unused);
@@ -486,7 +538,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         }
         if (!gathered) {
 #pragma unroll
-            for (int r = 0; r < kItems; ++r) xv[r] = ci[r] >= 0 ? __ldg(S.src + ci[r]) : 0.0;
+            for (int r = 0; r < kItems; ++r) xv[r] = ci[r] != -1 ? __ldg(S.src + gather_index(ci[r], ordered)) : 0.0;
         }
         if constexpr (MODE == kColsLanczos) {
             if (alpha_pending) {                 // the gathers above are in flight while the pieces are added
@@ -536,7 +588,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
 #pragma unroll
             for (int r = 0; r < kItems; ++r) {
                 const int i = r * kSweepThreads + tid;
-                if (i < nk) sprod[i] = p[r];
+                if (i < nk) sprod[ordered ? (ci[r] & ((1 << kSlotBits) - 1)) : i] = p[r];   // back to the natural position
             }
             cp_async_wait_all();
             __syncthreads();
@@ -634,7 +686,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
 }
 
 void fill_matrix(SweepParams &P, const SegMat &A) {
-    P.ptr = A.ptr; P.idx = A.idx; P.val = A.val; P.tiles = A.tiles; P.ntiles = A.ntiles;
+    P.ptr = A.ptr; P.idx = A.idx; P.val = A.val; P.gidx = A.gidx; P.gval = A.gval; P.tiles = A.tiles; P.ntiles = A.ntiles;
     P.longtab = A.longtab; P.segid = A.segid; P.partial = A.partial; P.longdot = A.longdot; P.ticket = A.ticket;
     P.nlong = A.nlong;
 }

@@ -145,6 +145,31 @@ def test_hvp_is_linear_symmetric_and_run_to_run_identical(torch):
     assert abs(a - b) <= 1e-12 * max(abs(a), abs(b))                     # H = A' D A is symmetric
 
 
+@pytest.mark.parametrize("name", ["small", "w8a", "rcv1"])
+def test_gather_ordered_tiles_give_the_same_bits(torch, monkeypatch, name):
+    # the sweeps read a copy of the matrix whose tiles are sorted by gather index (fewer distinct lines per warp
+    # load); every product returns to its natural slot, so nothing may change -- not even the last bit -- against
+    # the sweeps over the matrix as stored (KCRN_NO_GATHER_ORDER=1), Lanczos recurrence included
+    P = make_problem(name, seed=0)
+    rng = np.random.default_rng(11)
+    x, v = _dev(torch, 0.3 * rng.standard_normal(P.d)), _dev(torch, rng.standard_normal(P.d))
+    out = []
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv("KCRN_NO_GATHER_ORDER", "1")
+        eng = _engine(P, l2=1e-4)
+        eng.set_x(x)
+        val, Ax, grad, hv = eng.value(), eng.cached_Ax().clone(), eng.gradient().clone(), eng.hvp(v).clone()
+        eng.gradient(keep_internal=True)
+        eng.lanczos(7, False)
+        V, al, bet, info = eng.lanczos_view()
+        out.append((val, Ax, grad, hv, V.clone(), al.clone(), bet.clone()))
+        eng.close()
+    assert out[0][0] == out[1][0]
+    for a, b in zip(out[0][1:], out[1][1:]):
+        assert torch.equal(a, b)
+
+
 def test_long_segments_and_empty_rows(torch):
     # one column present in every row (a 20k-entry CSC segment -> 79 pieces), rows of very uneven length,
     # empty rows, a long row (> 256 entries -> multi-piece CSR segment)
