@@ -298,6 +298,7 @@ def main():
     graph_us = 1e3 * g0.elapsed_time(g1) / reps
     graph_hvps = int(eng.lanczos_view()[3][3].item())
     lan_us = graph_us / max(1, graph_hvps)
+    gather_variants = eng.gather_variants()       # which sweep-kernel variant the engine measured fastest per matrix
     clk.__exit__(None, None, None)
     clocks = clk.summary()
     roofline = {
@@ -325,6 +326,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * P.d, "d2h_bytes_per_step": 8 * P.d + 120,
                 "ms_per_step": ms2 / K, "outer_iters_per_sec": 1e3 * K / ms2},
         "gpu_launches": cnt["kernels"], "graph_launches": cnt["graph_launches"],
+        "gather_variants": gather_variants,
         "roofline": roofline, "clocks": clocks, "device_loop": device_loop,
     }
     if rank == 0 and not args.no_cpu_baseline:

@@ -195,6 +195,11 @@ int kcrn_counters(kcrn_handle h, int64_t *counters8_host, int reset);
  * graph joined by programmatic edges, 20 per graph -- between two CUDA events on the handle's stream; returns the
  * mean duration per launch in microseconds. */
 int kcrn_time_sweep(kcrn_handle h, int which, int reps, double *mean_us_host);
+/* Which gather variant of the sweep kernel was measured fastest for this handle's matrices (no reference
+ * counterpart; all variants compute the same bits): out4 = {CSR plain, CSR Lanczos, CSC plain, CSC Lanczos},
+ * 0 = entries as stored, 1 = gather-ordered tiles, 2 = gather-ordered tiles with asynchronous (LDGSTS) gathers.
+ * The Lanczos entries are final after the first kcrn_lanczos / kcrn_krylov_trial / kcrn_krylov_run. */
+int kcrn_gather_variants(kcrn_handle h, int *out4_host);
 
 #ifdef __cplusplus
 }

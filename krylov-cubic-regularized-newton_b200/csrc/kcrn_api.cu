@@ -112,6 +112,57 @@ int enqueue_lanczos(kcrn_problem *h, int m, int reorth) {
     return launch_lanczos_finish(h, m, defer);
 }
 
+// Which gather variant serves the two Lanczos passes: measured once per handle, right before the first recurrence is
+// captured, on a short recurrence (at most 4 steps) launched as the graph will launch it.  Row-sharded runs keep the
+// defaults of tune_plain_sweeps (a timed recurrence would have to be entered by all ranks alike).  All variants
+// compute the same bits; the recurrence state this leaves behind is rebuilt from g by every real run.
+int tune_lanczos_sweeps(kcrn_problem *h, int m, bool have_g) {
+    if (h->lanczos_tuned) return KCRN_OK;
+    h->lanczos_tuned = true;
+    int fp, fl;
+    forced_gather_variants(&fp, &fl);
+    if (fl >= 0 || h->world > 1 || (!h->csr.gidx && !h->csc.gidx) || h->nnz == 0) return KCRN_OK;
+    int64_t saved[8];
+    memcpy(saved, h->counters, sizeof(saved));
+    cudaStream_t s = h->stream;
+    if (!have_g) KCRN_TRY(cols_product(h, h->resid, h->l2 != 0.0 ? h->x_cur : nullptr, h->g));
+    const int mt = m < 4 ? m : 4, reps = h->nnz > 50000000 ? 1 : 3;
+    cudaEvent_t e0, e1;
+    KCRN_CUDA(cudaEventCreate(&e0));
+    KCRN_CUDA(cudaEventCreate(&e1));
+    int rc = KCRN_OK;
+    h->pdl = h->allow_pdl;
+    for (SegMat *A : {&h->csr, &h->csc}) {
+        if (!A->gidx || rc != KCRN_OK) continue;
+        int best = 0;
+        float best_ms = 0.f;
+        for (int v = 0; v <= 2 && rc == KCRN_OK; ++v) {
+            A->gather_lanczos = v;
+            for (int i = -1; i < reps && rc == KCRN_OK; ++i) {          // one warm-up recurrence, then the timed ones
+                if (i == 0) cudaEventRecord(e0, s);
+                rc = enqueue_lanczos(h, mt, 0);
+            }
+            cudaEventRecord(e1, s);
+            if (rc == KCRN_OK && cudaEventSynchronize(e1) != cudaSuccess) {
+                set_error("tune_lanczos_sweeps: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = KCRN_E_CUDA;
+            }
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (v == 0 || ms < best_ms) { best = v; best_ms = ms; }
+            if (getenv("KCRN_VERBOSE"))
+                fprintf(stderr, "kcrn: Lanczos %s pass, gather variant %d: %.2f us per %d-step recurrence\n",
+                        A == &h->csr ? "row" : "column", v, 1e3 * ms / reps, mt);
+        }
+        A->gather_lanczos = best;
+    }
+    h->pdl = false;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    memcpy(h->counters, saved, sizeof(saved));
+    return rc;
+}
+
 // Capture `enqueue` once per key = (kind, m, reorth) into a CUDA graph and replay it on the handle's stream.
 template <class F>
 int run_graph(kcrn_problem *h, int kind, int m, int reorth, F enqueue) {
@@ -365,6 +416,7 @@ int kcrn_create(kcrn_handle *out, int64_t n_rows, int64_t n_cols, int64_t nnz, c
         h->vec_elems = n_cols > (int64_t)kNumSm * kVecThreads * 4 ? 4 : 1;
         h->vec_grid = (int)((n_cols + (int64_t)kVecThreads * h->vec_elems - 1) / ((int64_t)kVecThreads * h->vec_elems));
         KCRN_TRY(lanczos_alloc(h, 1));
+        KCRN_TRY(tune_plain_sweeps(h));
         KCRN_CUDA(cudaStreamSynchronize(s));
         return KCRN_OK;
     };
@@ -584,6 +636,7 @@ int kcrn_lanczos(kcrn_handle h, const double *g_dev, int m, int reorth) {
     KCRN_TRY(lanczos_alloc(h, m));
     if (g_dev && g_dev != h->g)
         KCRN_CUDA(cudaMemcpyAsync(h->g, g_dev, sizeof(double) * h->d, cudaMemcpyDeviceToDevice, h->stream));
+    KCRN_TRY(tune_lanczos_sweeps(h, m, true));
     KCRN_TRY(run_graph(h, 0, m, reorth, [&]() { return enqueue_lanczos(h, m, reorth); }));
     h->counters[2] += m;
     h->cur_m = m;
@@ -602,6 +655,7 @@ int kcrn_krylov_trial(kcrn_handle h, int first, int m, int reorth, double M, dou
     }
     reorth = reorth ? 1 : 0;
     KCRN_TRY(lanczos_alloc(h, m));
+    if (first) KCRN_TRY(tune_lanczos_sweeps(h, m, false));
     cudaStream_t s = h->stream;
     double *pp = h->rec_host + 12;          // pinned; every trial ends with a stream synchronise, so it is free
     pp[0] = M; pp[1] = r0; pp[2] = eps; pp[3] = (double)it_max;
@@ -643,6 +697,7 @@ int kcrn_krylov_run(kcrn_handle h, int max_iters, int m, int reorth, double valu
     }
     reorth = reorth ? 1 : 0;
     KCRN_TRY(lanczos_alloc(h, m));
+    KCRN_TRY(tune_lanczos_sweeps(h, m, false));
     cudaStream_t s = h->stream;
     const int want_xs = keep_xs ? max_iters : 0;
     if (!h->run_ctl || max_iters > h->run_cap || want_xs > h->run_xs_cap || (h->run_xs != nullptr) != (keep_xs != 0)) {
@@ -836,6 +891,15 @@ int kcrn_counters(kcrn_handle h, int64_t *counters8_host, int reset) {
     if (!h || !counters8_host) { set_error("kcrn_counters: null argument"); return KCRN_E_ARG; }
     memcpy(counters8_host, h->counters, sizeof(h->counters));
     if (reset) memset(h->counters, 0, sizeof(h->counters));
+    return KCRN_OK;
+}
+
+int kcrn_gather_variants(kcrn_handle h, int *out4_host) {
+    if (!h || !out4_host) { set_error("kcrn_gather_variants: null argument"); return KCRN_E_ARG; }
+    out4_host[0] = h->csr.gidx ? h->csr.gather_plain : 0;
+    out4_host[1] = h->csr.gidx ? h->csr.gather_lanczos : 0;
+    out4_host[2] = h->csc.gidx ? h->csc.gather_plain : 0;
+    out4_host[3] = h->csc.gidx ? h->csc.gather_lanczos : 0;
     return KCRN_OK;
 }
 

@@ -30,12 +30,20 @@ __device__ __forceinline__ void cp_async_4(void *smem_dst, const void *gmem_src)
     const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gmem_src) : "memory");
 }
+// 8-byte variant
+__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
 // 16-byte variant, cached in L2 only (.cg)
 __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src) {
     const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// groups: commit what was issued so far; wait until at most the most recent group is still in flight
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_group_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // x / b with b fixed for the whole kernel: rinv = 1/b (IEEE) is formed once per thread, then one
 // Newton correction on the quotient (Markstein).  Bit-identical for every reader of the same x, so

@@ -86,6 +86,9 @@ struct SegMat {
     // keeps its order and its bits.  Null when gather_len does not fit the word (sweeps then use idx / val).
     uint32_t *gidx = nullptr;    // [nnz]
     double *gval = nullptr;      // [nnz] values in the same order
+    // which gather variant of the sweep kernel (kcrn_sweep.cu: GatherVariant) serves this matrix, measured at
+    // set-up: one choice for the Lanczos passes, one for all others
+    int gather_plain = 0, gather_lanczos = 0;
     // CSC copy only: its columns are stored in a length-class order (kcrn_transpose.cu)
     int32_t *segid = nullptr;    // [nseg] original column of the s-th stored segment (null: natural order)
     int32_t *pos = nullptr;      // [nseg] where column c is stored
@@ -208,6 +211,7 @@ struct kcrn_problem {
     uint4 *peer_recv[kcrn::kMaxPeers] = {};
     bool p2p_ready = false;
     int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool lanczos_tuned = false;    // the gather variants of the Lanczos passes have been measured (first use)
     bool pdl = false;              // launch with programmatic dependent launch (set while the Lanczos graph is built)
     bool allow_pdl = true;         // KCRN_NO_PDL=1 switches it off
 };
@@ -232,6 +236,8 @@ int launch_cols_scaled(kcrn_problem *h, const double *src, const double *u, doub
 int launch_cols_lanczos(kcrn_problem *h, int update_ctl, int slot, int defer);
 bool lanczos_defer_fits(const kcrn_problem *h);      // small grids only: see kcrn_sweep.cu             // w' and beta fused
 int launch_derive_from_Ax(kcrn_problem *h);
+int tune_plain_sweeps(kcrn_problem *h);               // once per handle, at the end of kcrn_create
+void forced_gather_variants(int *plain, int *lanczos);   // KCRN_GATHER override, -1 = measure
 
 // ----------------------------------------------------------------------------- kcrn_lanczos.cu
 int lanczos_alloc(kcrn_problem *h, int m);

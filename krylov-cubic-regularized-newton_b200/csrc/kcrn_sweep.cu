@@ -27,7 +27,9 @@
 //
 // Reference arithmetic being replaced: optimizer/loss.py:266-277 (A x), :215-232 (value, gradient),
 // :289-302 (Hessian-vector product) and the v / w bookkeeping of optimizer/cubic.py:92-97.
+#include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -35,6 +37,19 @@
 #include "kcrn_internal.cuh"
 
 namespace kcrn {
+
+// How the gathered values of a tile travel (template parameter GATHER of the sweep kernel; all three give the same
+// bits, which one is fastest depends on the matrix and on the pass, so it is MEASURED per matrix: tune_* below):
+//   kGatherStored   entries as stored, LDG into registers
+//   kGatherOrdered  entries in gather order (fewer distinct 128-byte lines per warp load), LDG into registers,
+//                   products scattered to their natural slots in shared memory
+//   kGatherAsync    entries in gather order, LDGSTS (8-byte cp.async) straight into the natural slot: no registers
+//                   are held while the gathers are in flight (the Lanczos passes, which carry the most state,
+//                   then compile without spills) and the values are read in their stored order
+enum GatherVariant { kGatherStored = 0, kGatherOrdered = 1, kGatherAsync = 2 };
+// shared buffer of the per-segment sums; with asynchronous gathers the product buffer is busy receiving them, so
+// the pieces of the deferred sums are staged here instead
+constexpr int kSumCapAsync = kTileSegs + 256;
 
 // ----------------------------------------------------------------------------- tile lists (host)
 void free_segmat(SegMat *A) {
@@ -358,10 +373,12 @@ __device__ __forceinline__ void defer_begin(const double *a, bool two, int n0, c
     for (int i = 2 * threadIdx.x; i < n1e; i += 2 * kSweepThreads) cp_async_16(sc + i, c + i);
 }
 
+template <bool kAsyncGather>
 __device__ __forceinline__ void defer_end(bool two, int n0, int n1, const double *sbuf, double *sred, double &ra,
                                           double &rb) {
     const int n0e = (n0 + 1) & ~1;
-    cp_async_wait_all();
+    if constexpr (kAsyncGather) cp_async_wait_group_1();      // the pieces; the gathers (last group) stay in flight
+    else cp_async_wait_all();
     __syncthreads();
     double x = 0.0, y = 0.0;
     for (int i = threadIdx.x; i < n0; i += kSweepThreads) {
@@ -381,11 +398,13 @@ __device__ __forceinline__ void defer_end(bool two, int n0, int n1, const double
     __syncthreads();      // sbuf (the product buffer of the tile) and sred are free again
 }
 
-template <int MODE, int kItems>
+template <int MODE, int kItems, int GATHER>
 __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepParams P) {
     constexpr int kTileNnz = kItems * kSweepThreads;       // non-zeros per CTA tile, kItems per thread
+    constexpr bool ordered = GATHER != kGatherStored, kAsyncGather = GATHER == kGatherAsync;
     __shared__ double sprod[kTileNnz];           // products of the tile
-    __shared__ double ssum[kTileSegs];           // per-segment sums of the tile
+    __shared__ double ssum[kAsyncGather ? kSumCapAsync : kTileSegs];   // per-segment sums of the tile
+    double *const spieces = kAsyncGather ? ssum : sprod;   // staging of the deferred sums' pieces
     __shared__ int sptr[kTileSegs + 8];          // segment pointers of the tile
     __shared__ double sred[2 * kSweepWarps];
     __shared__ int s_last;
@@ -399,11 +418,10 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
     int4 td = make_int4(0, 0, 0, 0);
     int ci[kItems];                  // index, or gather-ordered word (index << kSlotBits | natural position); -1: none
     double av[kItems];
-    const bool ordered = P.gidx != nullptr;
     if (tile < P.ntiles) {
         td = __ldg(P.tiles + tile);
         const int32_t *ip = (ordered ? reinterpret_cast<const int32_t *>(P.gidx) : P.idx) + td.y;
-        const double *vp = (ordered ? P.gval : P.val) + td.y;
+        const double *vp = (ordered && !kAsyncGather ? P.gval : P.val) + td.y;
         const int nk0 = td.w & 0xffff;
 #pragma unroll
         for (int r = 0; r < kItems; ++r) {
@@ -427,6 +445,20 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
     int col = 0, store_idx = 0, redo = 0;
     double xv[kItems];                   // gathered values of the tile
     bool gathered = false;
+    // the gathers of the tile from `src`: into registers, or (asynchronous) straight into the natural slots of sprod
+    auto gather_from = [&](const double *src) {
+#pragma unroll
+        for (int r = 0; r < kItems; ++r) {
+            if constexpr (kAsyncGather) {
+                const int i = r * kSweepThreads + tid;
+                if (ci[r] != -1)
+                    cp_async_8(sprod + (ordered ? (ci[r] & ((1 << kSlotBits) - 1)) : i), src + gather_index(ci[r], ordered));
+            } else {
+                xv[r] = ci[r] != -1 ? __ldg(src + gather_index(ci[r], ordered)) : 0.0;
+            }
+        }
+        if constexpr (kAsyncGather) cp_async_commit();
+    };
     bool alpha_pending = false;
     LanczosCtl st_cols;
     if constexpr (MODE == kRowsLanczos) {
@@ -439,14 +471,17 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         if (P.advance_here) {
             // beta = |w'| of the column sweep before us is still in pieces.  While they travel, gather from w'
             // -- the source unless the recurrence breaks down right now, which the sum will tell
-            defer_begin(P.prev_part, false, P.prev_count, P.prev_longdot, P.prev_nlong, sprod);
-#pragma unroll
-            for (int r = 0; r < kItems; ++r) xv[r] = ci[r] != -1 ? __ldg(P.wp + gather_index(ci[r], ordered)) : 0.0;
+            defer_begin(P.prev_part, false, P.prev_count, P.prev_longdot, P.prev_nlong, spieces);
+            if constexpr (kAsyncGather) cp_async_commit();
+            gather_from(P.wp);
             gathered = true;
             double bsq, unused;
-            defer_end(false, P.prev_count, P.prev_nlong, sprod, sred, bsq, unused);
+            defer_end<kAsyncGather>(false, P.prev_count, P.prev_nlong, spieces, sred, bsq, unused);
             lanczos_advance(&st, scribe ? P.bet : nullptr, sqrt(bsq));     // cubic.py:98-109, in registers
-            if (st.redo) gathered = false;                     // breakdown: the operator is re-applied to V[col]
+            if (st.redo) {                                     // breakdown: the operator is re-applied to V[col]
+                gathered = false;
+                if constexpr (kAsyncGather) { cp_async_wait_all(); __syncthreads(); }   // the slots are written again
+            }
         }
         if (scribe && P.ctl != P.ctl_in) *P.ctl = st;
         col = st.col;
@@ -467,11 +502,13 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         col = st_cols.col;
         if (P.defer) {
             // alpha = v'Hv of the row sweep before us is still in pieces; it is needed by the epilogue only
-            defer_begin(P.prev_part, true, P.prev_count, P.prev_longdot, P.prev_nlong, sprod);
+            defer_begin(P.prev_part, true, P.prev_count, P.prev_longdot, P.prev_nlong, spieces);
+            if constexpr (kAsyncGather) cp_async_commit();
             alpha_pending = true;
             if (st_cols.final_) {                              // cubic.py:109: the last alpha needs no further vector
                 double s1, s2;
-                defer_end(true, P.prev_count, P.prev_nlong, sprod, sred, s1, s2);
+                if constexpr (kAsyncGather) cp_async_commit();        // an (empty) last group for defer_end to leave behind
+                defer_end<kAsyncGather>(true, P.prev_count, P.prev_nlong, spieces, sred, s1, s2);
                 if (blockIdx.x == 0 && tid == 0) {
                     const double alpha = __dadd_rn(quotient(s1, P.n_samples, P.inv_n), __dmul_rn(P.l2, s2));
                     P.alphas[st_cols.store_idx] = alpha;
@@ -510,17 +547,18 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         const int seg0 = td.x, k0 = td.y, z = td.z, nk = td.w & 0xffff, tag = td.w >> 16;
         const bool stream = z > 0 && tag != kSingleTag;
         int4 lt = make_int4(0, 1, 0, 0);
+        // epilogue operands to registers: in flight while the gathers run
         double o0[NOP > 0 ? kSegRounds : 1], o1[NOP > 1 ? kSegRounds : 1];
+        double e0 = 0.0, e1 = 0.0;           // operands of a single-segment tile (thread 0)
         int sid[kSegRounds];
         sid[0] = seg0;
         if (stream) {
-            // epilogue operands to registers: in flight while the gathers run
 #pragma unroll
             for (int r = 0; r < kSegRounds; ++r) {
                 const int sg = r * kSweepThreads + tid;
                 if (sg < z) {
-                    double a0, a1;
                     sid[r] = P.segid ? __ldg(P.segid + seg0 + sg) : seg0 + sg;
+                    double a0, a1;
                     load_operands<MODE>(P, S, sid[r], a0, a1);
                     if constexpr (NOP > 0) o0[r] = a0;
                     if constexpr (NOP > 1) o1[r] = a1;
@@ -529,27 +567,30 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         } else {
             if (z < 0) lt = __ldg(P.longtab + (-z - 1));
             if (tid == 0) {
-                double a0, a1;
                 if (P.segid) sid[0] = __ldg(P.segid + seg0);
-                load_operands<MODE>(P, S, sid[0], a0, a1);
-                if constexpr (NOP > 0) o0[0] = a0;
-                if constexpr (NOP > 1) o1[0] = a1;
+                load_operands<MODE>(P, S, sid[0], e0, e1);
             }
         }
-        if (!gathered) {
-#pragma unroll
-            for (int r = 0; r < kItems; ++r) xv[r] = ci[r] != -1 ? __ldg(S.src + gather_index(ci[r], ordered)) : 0.0;
-        }
+        if (!gathered) gather_from(S.src);
         if constexpr (MODE == kColsLanczos) {
             if (alpha_pending) {                 // the gathers above are in flight while the pieces are added
                 double s1, s2;
-                defer_end(true, P.prev_count, P.prev_nlong, sprod, sred, s1, s2);
+                defer_end<kAsyncGather>(true, P.prev_count, P.prev_nlong, spieces, sred, s1, s2);
                 S.alpha = __dadd_rn(quotient(s1, P.n_samples, P.inv_n), __dmul_rn(P.l2, s2));
                 if (blockIdx.x == 0 && tid == 0) {
                     P.alphas[col] = S.alpha;
                     P.ctl->cur_alpha = S.alpha;
                     P.ctl->hvps = st_cols.hvps + 1;
                 }
+            }
+        }
+        if constexpr (kAsyncGather) {        // the gathered values are in their natural slots: collect this thread's
+            cp_async_wait_all();
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < kItems; ++r) {
+                const int i = r * kSweepThreads + tid;
+                xv[r] = i < nk ? sprod[i] : 0.0;
             }
         }
         double p[kItems];
@@ -566,7 +607,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
             for (int r = 0; r < kItems; ++r) s += p[r];
             const double tot = cta_sum_to_thread0(s, sred);
             if (z > 0) {
-                if (tid == 0) finish_segment<MODE>(P, S, sid[0], tot, -1, NOP > 0 ? o0[0] : 0.0, NOP > 1 ? o1[0] : 0.0, acc);
+                if (tid == 0) finish_segment<MODE>(P, S, sid[0], tot, -1, e0, e1, acc);
             } else {
                 const int lseg = -z - 1;
                 if (tid == 0) {
@@ -581,14 +622,14 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
                     for (int i = lane; i < lt.y; i += 32) all += __ldcg(P.partial + lt.x + i);
                     all = warp_sum(all);
                     // thread 0 holds the operands
-                    if (tid == 0) finish_segment<MODE>(P, S, sid[0], all, lseg, NOP > 0 ? o0[0] : 0.0, NOP > 1 ? o1[0] : 0.0, acc);
+                    if (tid == 0) finish_segment<MODE>(P, S, sid[0], all, lseg, e0, e1, acc);
                 }
             }
         } else {
 #pragma unroll
             for (int r = 0; r < kItems; ++r) {
                 const int i = r * kSweepThreads + tid;
-                if (i < nk) sprod[ordered ? (ci[r] & ((1 << kSlotBits) - 1)) : i] = p[r];   // back to the natural position
+                if (i < nk) sprod[GATHER == kGatherOrdered ? (ci[r] & ((1 << kSlotBits) - 1)) : i] = p[r];   // the natural position
             }
             cp_async_wait_all();
             __syncthreads();
@@ -608,8 +649,9 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
 #pragma unroll
             for (int r = 0; r < kSegRounds; ++r) {
                 const int sg = r * kSweepThreads + tid;
-                if (sg < z)
+                if (sg < z) {
                     finish_segment<MODE>(P, S, sid[r], ssum[sg], -1, NOP > 0 ? o0[r] : 0.0, NOP > 1 ? o1[r] : 0.0, acc);
+                }
             }
         }
     }
@@ -691,12 +733,22 @@ void fill_matrix(SweepParams &P, const SegMat &A) {
     P.nlong = A.nlong;
 }
 
+template <int MODE, int GATHER>
+int launch_variant(kcrn_problem *h, const SegMat &A, const SweepParams &P) {
+    if (A.items == 11) KCRN_CUDA(launch_kernel(sweep_kernel<MODE, 11, GATHER>, dim3(A.grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
+    else if (A.items == 12) KCRN_CUDA(launch_kernel(sweep_kernel<MODE, 12, GATHER>, dim3(A.grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
+    else KCRN_CUDA(launch_kernel(sweep_kernel<MODE, 8, GATHER>, dim3(A.grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
+    return KCRN_OK;
+}
+
+// The gather variant is a property of (matrix, class of pass): the Lanczos passes carry more state than the others
 template <int MODE>
 int launch(kcrn_problem *h, const SegMat &A, SweepParams &P) {
     fill_matrix(P, A);
-    if (A.items == 11) KCRN_CUDA(launch_kernel(sweep_kernel<MODE, 11>, dim3(A.grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
-    else if (A.items == 12) KCRN_CUDA(launch_kernel(sweep_kernel<MODE, 12>, dim3(A.grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
-    else KCRN_CUDA(launch_kernel(sweep_kernel<MODE, 8>, dim3(A.grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
+    const int variant = !A.gidx ? kGatherStored : (MODE == kRowsLanczos || MODE == kColsLanczos ? A.gather_lanczos : A.gather_plain);
+    if (variant == kGatherAsync) KCRN_TRY((launch_variant<MODE, kGatherAsync>(h, A, P)));
+    else if (variant == kGatherOrdered) KCRN_TRY((launch_variant<MODE, kGatherOrdered>(h, A, P)));
+    else KCRN_TRY((launch_variant<MODE, kGatherStored>(h, A, P)));
     h->counters[0] += 1;
     return KCRN_OK;
 }
@@ -731,12 +783,78 @@ int launch_rows_weighted(kcrn_problem *h, const double *v) {
     return launch<kRowsWeighted>(h, h->csr, P);
 }
 
+// KCRN_GATHER="p[,l]" forces the gather variant of the plain / Lanczos passes (A/B switch); -1: measure
+void forced_gather_variants(int *plain, int *lanczos) {
+    *plain = *lanczos = -1;
+    const char *e = getenv("KCRN_GATHER");
+    if (!e) return;
+    int a = -1, b = -1;
+    const int k = sscanf(e, "%d,%d", &a, &b);
+    if (k >= 1 && a >= 0 && a <= 2) *plain = *lanczos = a;
+    if (k >= 2 && b >= 0 && b <= 2) *lanczos = b;
+}
+
+// Which gather variant serves the passes outside the Lanczos recurrence: measured per matrix on the weighted row
+// pass / the scaled column pass, a few back-to-back launches each (the operands are zeroed scratch; all variants
+// compute the same bits, so the choice never shows in a result).  The Lanczos passes are measured at their first
+// use (kcrn_api.cu: tune_lanczos_sweeps), when a gradient to start the recurrence from exists.
+int tune_plain_sweeps(kcrn_problem *h) {
+    int fp, fl;
+    forced_gather_variants(&fp, &fl);
+    for (SegMat *A : {&h->csr, &h->csc}) {
+        A->gather_plain = A->gather_lanczos = kGatherStored;
+        if (!A->gidx) continue;
+        A->gather_plain = fp >= 0 ? fp : kGatherOrdered;
+        A->gather_lanczos = fl >= 0 ? fl : kGatherAsync;     // until measured (row-sharded runs never measure)
+    }
+    if (fp >= 0 || (!h->csr.gidx && !h->csc.gidx)) return KCRN_OK;
+    cudaStream_t s = h->stream;
+    KCRN_CUDA(cudaMemsetAsync(h->x_cur, 0, sizeof(double) * h->d, s));
+    KCRN_CUDA(cudaMemsetAsync(h->D, 0, sizeof(double) * h->n, s));
+    KCRN_CUDA(cudaMemsetAsync(h->t, 0, sizeof(double) * h->n, s));
+    int64_t saved[8];
+    memcpy(saved, h->counters, sizeof(saved));
+    cudaEvent_t e0, e1;
+    KCRN_CUDA(cudaEventCreate(&e0));
+    KCRN_CUDA(cudaEventCreate(&e1));
+    int rc = KCRN_OK;
+    for (int which = 0; which < 2 && rc == KCRN_OK; ++which) {
+        SegMat *A = which == 0 ? &h->csr : &h->csc;
+        if (!A->gidx || A->nnz == 0) continue;
+        const int reps = A->nnz > 50000000 ? 3 : 10;
+        int best = kGatherStored;
+        float best_ms = 0.f;
+        for (int v = kGatherStored; v <= kGatherAsync && rc == KCRN_OK; ++v) {
+            A->gather_plain = v;
+            for (int i = -2; i < reps && rc == KCRN_OK; ++i) {        // two warm-up launches, then the timed ones
+                if (i == 0) cudaEventRecord(e0, s);
+                rc = which == 0 ? launch_rows_weighted(h, h->x_cur) : launch_cols_scaled(h, h->t, nullptr, h->o_stage);
+            }
+            cudaEventRecord(e1, s);
+            if (cudaEventSynchronize(e1) != cudaSuccess) { set_error("tune_plain_sweeps: %s", cudaGetErrorString(cudaGetLastError())); rc = KCRN_E_CUDA; }
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (v == kGatherStored || ms < best_ms) { best = v; best_ms = ms; }
+            if (getenv("KCRN_VERBOSE"))
+                fprintf(stderr, "kcrn: %s pass, gather variant %d: %.2f us\n", which == 0 ? "row" : "column", v, 1e3 * ms / reps);
+        }
+        A->gather_plain = best;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    memcpy(h->counters, saved, sizeof(saved));
+    return rc;
+}
+
 // The consumer-side sums stage the producer's pieces in the tile's product buffer: both sets must fit
 bool lanczos_defer_fits(const kcrn_problem *h) {
     auto even = [](int v) { return (v + 1) & ~1; };
     // staged in the CONSUMER's product buffer: row pieces in the column sweep's, column pieces in the row sweep's
-    return 2 * even(h->csr.grid) + even(h->csr.nlong) <= h->csc.items * kSweepThreads &&
-           even(h->csc.grid) + even(h->csc.nlong) <= h->csr.items * kSweepThreads;
+    const bool async_cols = h->csc.gidx && h->csc.gather_lanczos == kGatherAsync;
+    const bool async_rows = h->csr.gidx && h->csr.gather_lanczos == kGatherAsync;
+    const int cap_cols = async_cols ? kSumCapAsync : h->csc.items * kSweepThreads;
+    const int cap_rows = async_rows ? kSumCapAsync : h->csr.items * kSweepThreads;
+    return 2 * even(h->csr.grid) + even(h->csr.nlong) <= cap_cols && even(h->csc.grid) + even(h->csc.nlong) <= cap_rows;
 }
 
 // slot = position of the step in the captured recurrence; defer = 1 (single-GPU fused loop): grid-wide sums are

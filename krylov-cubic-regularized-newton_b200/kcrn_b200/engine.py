@@ -351,6 +351,13 @@ class Engine:
         check(self.lib.kcrn_time_sweep(self.h, int(which), int(reps), byref(us)))
         return us.value
 
+    def gather_variants(self) -> dict:
+        """Gather variant of the sweep kernel measured fastest per matrix and class of pass (0 stored order,
+        1 gather-ordered tiles, 2 gather-ordered tiles + LDGSTS gathers); same bits whichever runs."""
+        out = (c_int * 4)()
+        check(self.lib.kcrn_gather_variants(self.h, out))
+        return {"csr_plain": out[0], "csr_lanczos": out[1], "csc_plain": out[2], "csc_lanczos": out[3]}
+
     # algorithmic bytes of one pass (SURVEY.md section 8(d)); used by bench.py's roofline
     def sweep_bytes(self, which: int) -> int:
         if which == 0:   # CSR: 12 nnz + 4(n+1) + 8d (gather v) + 8n (weights) + 8n (write t)

@@ -24,7 +24,10 @@ for name in sys.argv[1:] or ["rcv1"]:
         b.record(); torch.cuda.synchronize()
         allb.append(round(a.elapsed_time(b) / 50 * 1e2, 2))
         best = min(best, a.elapsed_time(b) / 50 * 1e3)
-    print(f"{os.path.basename(os.environ.get('KCRN_LIBRARY', 'default')):22s} {name:6s} sweeps {us[0]:6.2f} {us[1]:6.2f} us   Lanczos graph {best / 10:6.2f} us per HVP  batches {allb}")
+    tag = os.path.basename(os.environ.get('KCRN_LIBRARY', 'default')) + " KCRN_GATHER=" + os.environ.get("KCRN_GATHER", "auto")
+    if hasattr(eng, "gather_variants") and hasattr(eng.lib, "kcrn_gather_variants"):
+        tag += " -> " + ",".join(str(v) for v in eng.gather_variants().values())
+    print(f"{tag:46s} {name:6s} sweeps {us[0]:6.2f} {us[1]:6.2f} us   Lanczos graph {best / 10:6.2f} us per HVP  batches {allb}")
     x = eng.new_vector(); x.copy_(torch.as_tensor(P.x0, device="cuda")); x.mul_(0.2)
     eng.set_x(x); eng.gradient(keep_internal=True)
     a.record()

@@ -146,17 +146,21 @@ def test_hvp_is_linear_symmetric_and_run_to_run_identical(torch):
 
 
 @pytest.mark.parametrize("name", ["small", "w8a", "rcv1"])
-def test_gather_ordered_tiles_give_the_same_bits(torch, monkeypatch, name):
-    # the sweeps read a copy of the matrix whose tiles are sorted by gather index (fewer distinct lines per warp
-    # load); every product returns to its natural slot, so nothing may change -- not even the last bit -- against
-    # the sweeps over the matrix as stored (KCRN_NO_GATHER_ORDER=1), Lanczos recurrence included
+def test_gather_variants_give_the_same_bits(torch, monkeypatch, name):
+    # the sweeps may read a copy of the matrix whose tiles are sorted by gather index (fewer distinct lines per warp
+    # load), with the gathered values travelling through registers or straight into shared memory (LDGSTS); the
+    # variant is measured per matrix.  Every product returns to its natural slot, so nothing may change -- not even
+    # the last bit -- against the sweeps over the matrix as stored, Lanczos recurrence included
     P = make_problem(name, seed=0)
     rng = np.random.default_rng(11)
     x, v = _dev(torch, 0.3 * rng.standard_normal(P.d)), _dev(torch, rng.standard_normal(P.d))
-    out = []
-    for off in (False, True):
-        if off:
-            monkeypatch.setenv("KCRN_NO_GATHER_ORDER", "1")
+    out, seen = [], []
+    for env in (("KCRN_NO_GATHER_ORDER", "1"), ("KCRN_GATHER", "0"), ("KCRN_GATHER", "1"), ("KCRN_GATHER", "2"),
+                ("KCRN_GATHER", "2,1"), None):
+        monkeypatch.delenv("KCRN_NO_GATHER_ORDER", raising=False)
+        monkeypatch.delenv("KCRN_GATHER", raising=False)
+        if env:
+            monkeypatch.setenv(*env)
         eng = _engine(P, l2=1e-4)
         eng.set_x(x)
         val, Ax, grad, hv = eng.value(), eng.cached_Ax().clone(), eng.gradient().clone(), eng.hvp(v).clone()
@@ -164,10 +168,15 @@ def test_gather_ordered_tiles_give_the_same_bits(torch, monkeypatch, name):
         eng.lanczos(7, False)
         V, al, bet, info = eng.lanczos_view()
         out.append((val, Ax, grad, hv, V.clone(), al.clone(), bet.clone()))
+        seen.append(tuple(eng.gather_variants().values()))
         eng.close()
-    assert out[0][0] == out[1][0]
-    for a, b in zip(out[0][1:], out[1][1:]):
-        assert torch.equal(a, b)
+    assert seen[0] == (0, 0, 0, 0) and seen[1] == (0, 0, 0, 0) and seen[2] == (1, 1, 1, 1) and seen[3] == (2, 2, 2, 2)
+    assert seen[4] == (2, 1, 2, 1)
+    assert all(0 <= c <= 2 for c in seen[5])                 # measured
+    for other in out[1:]:
+        assert out[0][0] == other[0]
+        for a, b in zip(out[0][1:], other[1:]):
+            assert torch.equal(a, b)
 
 
 def test_long_segments_and_empty_rows(torch):
