@@ -41,6 +41,19 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(workload, which):
+    """DRAM bytes per launch of the CSR (0) / CSC (1) pass from the committed `ncu --set full` capture of this
+    workload (profiles/ncu_traffic.json); None when there is no capture for it."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        if t.get("workload") != workload:
+            return None
+        return int(t["csc_pass_bytes_per_launch" if which else "csr_pass_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -302,7 +315,8 @@ def main():
     clk.__exit__(None, None, None)
     clocks = clk.summary()
     roofline = {
-        "bound": "hbm", "achieved": gbs[dom], "peak": peak, "unit": "GB/s", "frac": gbs[dom] / peak, "traffic": None,
+        "bound": "hbm", "achieved": gbs[dom], "peak": peak, "unit": "GB/s", "frac": gbs[dom] / peak,
+        "traffic": ncu_traffic(args.workload, dom),
         "kernel": "sweep_kernel<kColsScaled> (CSC pass: A' t)" if dom else "sweep_kernel<kRowsWeighted> (CSR pass: D.*(A v))",
         "kernel_us": us[dom], "algorithmic_bytes": eng.sweep_bytes(dom), "peak_source": peak_src,
         "other_pass": {"kernel_us": us[1 - dom], "achieved": gbs[1 - dom], "frac": gbs[1 - dom] / peak},

@@ -179,6 +179,38 @@ def test_gather_variants_give_the_same_bits(torch, monkeypatch, name):
             assert torch.equal(a, b)
 
 
+def _lanczos_probe(tmp_path, tag, extra_env):
+    import os, subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    e = {k: v for k, v in os.environ.items() if not k.startswith("KCRN_")}
+    e.update(extra_env)
+    out = str(tmp_path / f"probe_{tag}.npz")
+    subprocess.run([sys.executable, os.path.join(here, "lanczos_probe.py"), "small", "6", "0", out], env=e, check=True,
+                   timeout=300)
+    with np.load(out) as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="module")
+def lanczos_probe_default(tmp_path_factory):
+    return _lanczos_probe(tmp_path_factory.mktemp("probe"), "default", {})
+
+
+@pytest.mark.parametrize("env", [{"KCRN_NO_DEFER": "1", "KCRN_GATHER": "2"}, {"KCRN_NO_DEFER": "1", "KCRN_GATHER": "1"},
+                                 {"KCRN_NO_PDL": "1"}])
+def test_fused_lanczos_under_process_wide_switches(torch, tmp_path, lanczos_probe_default, env):
+    # grid-wide sums finished by a last-CTA tail instead of by the consumer kernel (the mode row-sharded runs use)
+    # under the gather variants, and plain stream order instead of programmatic dependent launches.  The sums keep
+    # their order, so the recurrence is expected to keep its bits; asserted to 1e-10 (the point here is that these
+    # launch modes are exercised at all on one GPU).  The switches are read once per process -> child processes.
+    ref, got = lanczos_probe_default, _lanczos_probe(tmp_path, "switched", env)
+    if "KCRN_GATHER" in env:
+        assert set(got["variants"].tolist()) == {int(env["KCRN_GATHER"])}
+    assert ref["info"][0] == got["info"][0] and ref["info"][3] == got["info"][3]      # m_eff, operator applications
+    for k in ("V", "alphas", "bet"):
+        assert np.allclose(ref[k], got[k], rtol=1e-10, atol=1e-12), k
+
+
 def test_long_segments_and_empty_rows(torch):
     # one column present in every row (a 20k-entry CSC segment -> 79 pieces), rows of very uneven length,
     # empty rows, a long row (> 256 entries -> multi-piece CSR segment)
