@@ -66,7 +66,7 @@ int need_x(kcrn_problem *h, const char *what) {
 
 // transpose sweep with the 1/n (+ l2 u) epilogue, allreduced when the rows are sharded
 int cols_product(kcrn_problem *h, const double *src, const double *u, double *out) {
-    if (h->world > 1) {
+    if (h->sharded()) {
         KCRN_TRY(launch_cols_raw(h, src, h->ypart));
         if (h->p2p_ready) return launch_scale_peer(h, h->ypart, u, out);     // the sum over the ranks inside
         KCRN_TRY(nccl_allreduce_sum(h, h->ypart, h->d));
@@ -89,13 +89,13 @@ int enqueue_lanczos(kcrn_problem *h, int m, int reorth) {
     // kernel that consumes them -- 2: both, the row sweep also advances the recurrence; 1: alpha only (the
     // re-orthogonalisation kernel owns beta and the advance).  Row-sharded: 0, the exchange kernels own both.
     static const bool no_defer = getenv("KCRN_NO_DEFER") != nullptr;                 // A/B switch
-    const int defer = (h->world > 1 || no_defer || !lanczos_defer_fits(h)) ? 0 : (reorth ? 1 : 2);
+    const int defer = (h->sharded() || no_defer || !lanczos_defer_fits(h)) ? 0 : (reorth ? 1 : 2);
     KCRN_TRY(launch_lanczos_init(h, m));
     for (int slot = 0; slot < m; ++slot) {
         // rows sweep: t = D (A v), basis column, and alpha = v'Hv one sweep early (so that the column sweep can
         // form w' = Hv - beta v_prev - alpha v and beta = |w'| itself: two kernels per Lanczos step)
         KCRN_TRY(launch_rows_lanczos(h, h->ypart + h->d, slot, defer));
-        if (h->world > 1) {
+        if (h->sharded()) {
             KCRN_TRY(launch_cols_raw(h, h->t, h->ypart));
             if (h->p2p_ready) {
                 // small d: the sum over the ranks happens inside the epilogue kernel, over NVLink peer memory
@@ -121,7 +121,7 @@ int tune_lanczos_sweeps(kcrn_problem *h, int m, bool have_g) {
     h->lanczos_tuned = true;
     int fp, fl;
     forced_gather_variants(&fp, &fl);
-    if (fl >= 0 || h->world > 1 || (!h->csr.gidx && !h->csc.gidx) || h->nnz == 0) return KCRN_OK;
+    if (fl >= 0 || h->sharded() || (!h->csr.gidx && !h->csc.gidx) || h->nnz == 0) return KCRN_OK;
     int64_t saved[8];
     memcpy(saved, h->counters, sizeof(saved));
     cudaStream_t s = h->stream;
@@ -136,19 +136,24 @@ int tune_lanczos_sweeps(kcrn_problem *h, int m, bool have_g) {
         if (!A->gidx || rc != KCRN_OK) continue;
         int best = 0;
         float best_ms = 0.f;
+        const int batches = h->nnz > 50000000 ? 1 : 3;              // the fastest of a few batches: robust to a stray stall
         for (int v = 0; v <= 2 && rc == KCRN_OK; ++v) {
             A->gather_lanczos = v;
-            for (int i = -1; i < reps && rc == KCRN_OK; ++i) {          // one warm-up recurrence, then the timed ones
-                if (i == 0) cudaEventRecord(e0, s);
-                rc = enqueue_lanczos(h, mt, 0);
-            }
-            cudaEventRecord(e1, s);
-            if (rc == KCRN_OK && cudaEventSynchronize(e1) != cudaSuccess) {
-                set_error("tune_lanczos_sweeps: %s", cudaGetErrorString(cudaGetLastError()));
-                rc = KCRN_E_CUDA;
-            }
             float ms = 0.f;
-            cudaEventElapsedTime(&ms, e0, e1);
+            for (int bt = 0; bt < batches && rc == KCRN_OK; ++bt) {
+                for (int i = (bt == 0 ? -1 : 0); i < reps && rc == KCRN_OK; ++i) {      // one warm-up recurrence first
+                    if (i == 0) cudaEventRecord(e0, s);
+                    rc = enqueue_lanczos(h, mt, 0);
+                }
+                cudaEventRecord(e1, s);
+                if (rc == KCRN_OK && cudaEventSynchronize(e1) != cudaSuccess) {
+                    set_error("tune_lanczos_sweeps: %s", cudaGetErrorString(cudaGetLastError()));
+                    rc = KCRN_E_CUDA;
+                }
+                float t = 0.f;
+                cudaEventElapsedTime(&t, e0, e1);
+                if (bt == 0 || t < ms) ms = t;
+            }
             if (v == 0 || ms < best_ms) { best = v; best_ms = ms; }
             if (getenv("KCRN_VERBOSE"))
                 fprintf(stderr, "kcrn: Lanczos %s pass, gather variant %d: %.2f us per %d-step recurrence\n",
@@ -378,7 +383,8 @@ int kcrn_create(kcrn_handle *out, int64_t n_rows, int64_t n_cols, int64_t nnz, c
         KCRN_TRY(build_csc(h->csr, n_cols, &h->csc, s));
         KCRN_TRY(build_tiles(&h->csr, n_cols, s));   // row sweeps gather a d-vector
         KCRN_TRY(build_tiles(&h->csc, n_rows, s));   // column sweeps gather an n-vector
-        h->allow_pdl = getenv("KCRN_NO_PDL") == nullptr;   // programmatic dependent launch inside the captured graphs
+        h->allow_pdl = getenv("KCRN_NO_PDL") == nullptr;
+        h->emulate_sharded = getenv("KCRN_EMULATE_SHARDED") != nullptr;   // programmatic dependent launch inside the captured graphs
         const size_t n = (size_t)n_rows, d = (size_t)n_cols;
         KCRN_CUDA(cudaMalloc(&h->x_cur, sizeof(double) * d));
         KCRN_CUDA(cudaMalloc(&h->x_base, sizeof(double) * d));

@@ -211,6 +211,11 @@ struct kcrn_problem {
     uint4 *peer_recv[kcrn::kMaxPeers] = {};
     bool p2p_ready = false;
     int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // KCRN_EMULATE_SHARDED=1 (read at kcrn_create): a single-GPU handle takes the code path of a row-sharded one --
+    // raw transpose sweep, (identity) sum over the ranks, separate epilogue kernels -- so that this path is covered by
+    // the one-GPU test suite
+    bool emulate_sharded = false;
+    bool sharded() const { return world > 1 || emulate_sharded; }
     bool lanczos_tuned = false;    // the gather variants of the Lanczos passes have been measured (first use)
     bool pdl = false;              // launch with programmatic dependent launch (set while the Lanczos graph is built)
     bool allow_pdl = true;         // KCRN_NO_PDL=1 switches it off

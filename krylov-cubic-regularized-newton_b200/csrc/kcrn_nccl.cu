@@ -94,6 +94,7 @@ int nccl_init(kcrn_problem *h, const void *id128, int rank, int world) {
 }
 
 int nccl_allreduce_sum(kcrn_problem *h, double *buf, int64_t count) {
+    if (h->world == 1 && h->emulate_sharded) return KCRN_OK;      // one rank: the sum over the ranks is the identity
     Api *a = api();
     if (!a || !h->comm) {
         set_error("NCCL: communicator not initialised");

@@ -197,17 +197,19 @@ def lanczos_probe_default(tmp_path_factory):
 
 
 @pytest.mark.parametrize("env", [{"KCRN_NO_DEFER": "1", "KCRN_GATHER": "2"}, {"KCRN_NO_DEFER": "1", "KCRN_GATHER": "1"},
-                                 {"KCRN_NO_PDL": "1"}])
+                                 {"KCRN_NO_PDL": "1"}, {"KCRN_EMULATE_SHARDED": "1"}])
 def test_fused_lanczos_under_process_wide_switches(torch, tmp_path, lanczos_probe_default, env):
     # grid-wide sums finished by a last-CTA tail instead of by the consumer kernel (the mode row-sharded runs use)
     # under the gather variants, and plain stream order instead of programmatic dependent launches.  The sums keep
     # their order, so the recurrence is expected to keep its bits; asserted to 1e-10 (the point here is that these
-    # launch modes are exercised at all on one GPU).  The switches are read once per process -> child processes.
+    # launch modes are exercised at all on one GPU).  KCRN_EMULATE_SHARDED sends a one-GPU handle down the code path
+    # of a row-sharded one (raw transpose sweep, identity sum over the ranks, separate epilogue kernels) with the
+    # gather variants such handles use.  The switches are read once per process -> child processes.
     ref, got = lanczos_probe_default, _lanczos_probe(tmp_path, "switched", env)
     if "KCRN_GATHER" in env:
         assert set(got["variants"].tolist()) == {int(env["KCRN_GATHER"])}
     assert ref["info"][0] == got["info"][0] and ref["info"][3] == got["info"][3]      # m_eff, operator applications
-    for k in ("V", "alphas", "bet"):
+    for k in ("value", "grad", "hvp", "V", "alphas", "bet"):
         assert np.allclose(ref[k], got[k], rtol=1e-10, atol=1e-12), k
 
 
