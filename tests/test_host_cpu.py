@@ -107,3 +107,38 @@ def test_trace_pickle_roundtrip(tmp_path):
     tr.save("t.pkl", path=str(tmp_path) + "/")
     back = Trace.from_pickle(os.path.join(str(tmp_path), "t.pkl"), loss=loss)
     assert back.loss is loss and np.array_equal(back.loss_vals, tr.loss_vals) and tr.loss is loss
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` is the CPU arm the driver times beside the GPU arm: it must run without a GPU and
+    print ONE JSON line with the contract's keys (metric / unit / config of the GPU arm, cpu_baseline, e2e)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "small",
+                        "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "krylov_crn_hvps_per_sec" and line["unit"] == "HVP/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] == 2
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"]
+
+
+def test_bench_roofline_traffic_comes_from_the_committed_capture():
+    import json
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    with open(os.path.join(root, "profiles", "ncu_traffic.json")) as f:
+        t = json.load(f)
+    assert bench.ncu_traffic(t["workload"], 0) == t["csr_pass_bytes_per_launch"]
+    assert bench.ncu_traffic(t["workload"], 1) == t["csc_pass_bytes_per_launch"]
+    assert bench.ncu_traffic("no-such-workload", 0) is None
+    assert os.path.exists(os.path.join(root, t["source"].split(" ")[0]))
