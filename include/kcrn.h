@@ -197,7 +197,8 @@ int kcrn_counters(kcrn_handle h, int64_t *counters8_host, int reset);
 int kcrn_time_sweep(kcrn_handle h, int which, int reps, double *mean_us_host);
 /* Which gather variant of the sweep kernel was measured fastest for this handle's matrices (no reference
  * counterpart; all variants compute the same bits): out4 = {CSR plain, CSR Lanczos, CSC plain, CSC Lanczos},
- * 0 = entries as stored, 1 = gather-ordered tiles, 2 = gather-ordered tiles with asynchronous (LDGSTS) gathers.
+ * 0 = entries as stored, 1 = gather-ordered tiles, 2 = gather-ordered tiles with asynchronous (LDGSTS) gathers
+ * (3 = experimental: values staged in shared memory; only on request).
  * The Lanczos entries are final after the first kcrn_lanczos / kcrn_krylov_trial / kcrn_krylov_run. */
 int kcrn_gather_variants(kcrn_handle h, int *out4_host);
 

@@ -137,7 +137,7 @@ int tune_lanczos_sweeps(kcrn_problem *h, int m, bool have_g) {
         int best = 0;
         float best_ms = 0.f;
         const int batches = h->nnz > 50000000 ? 1 : 3;              // the fastest of a few batches: robust to a stray stall
-        for (int v = 0; v <= 2 && rc == KCRN_OK; ++v) {
+        for (int v = 0; v <= gather_candidates_last() && rc == KCRN_OK; ++v) {
             A->gather_lanczos = v;
             float ms = 0.f;
             for (int bt = 0; bt < batches && rc == KCRN_OK; ++bt) {

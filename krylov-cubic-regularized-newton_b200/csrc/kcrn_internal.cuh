@@ -243,6 +243,7 @@ bool lanczos_defer_fits(const kcrn_problem *h);      // small grids only: see kc
 int launch_derive_from_Ax(kcrn_problem *h);
 int tune_plain_sweeps(kcrn_problem *h);               // once per handle, at the end of kcrn_create
 void forced_gather_variants(int *plain, int *lanczos);   // KCRN_GATHER override, -1 = measure
+int gather_candidates_last();                            // last variant the tuners try (the experimental one only on request)
 
 // ----------------------------------------------------------------------------- kcrn_lanczos.cu
 int lanczos_alloc(kcrn_problem *h, int m);

@@ -49,7 +49,12 @@ namespace kcrn {
 //   kGatherAsync    entries in gather order, LDGSTS (8-byte cp.async) straight into the natural slot: no registers
 //                   are held while the gathers are in flight (the Lanczos passes, which carry the most state,
 //                   then compile without spills) and the values are read in their stored order
-enum GatherVariant { kGatherStored = 0, kGatherOrdered = 1, kGatherAsync = 2 };
+//   kGatherStaged   EXPERIMENTAL (never chosen unless KCRN_GATHER=3 / KCRN_GATHER_TRY_STAGED=1; compiled, not yet run
+//                   on a GPU): entries in gather order, the VALUES travel to shared memory in 16-byte cp.async
+//                   (requested before the wait for the previous kernel, no registers), the gathers use LDG; aims at
+//                   the register relief of kGatherAsync without LDGSTS's issue rate
+enum GatherVariant { kGatherStored = 0, kGatherOrdered = 1, kGatherAsync = 2, kGatherStaged = 3 };
+constexpr int kGatherVariants = 4;
 // shared buffer of the per-segment sums; with asynchronous gathers the product buffer is busy receiving them, so
 // the pieces of the deferred sums are staged here instead
 constexpr int kSumCapAsync = kTileSegs + 256;
@@ -208,7 +213,8 @@ int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s) {
     if (A->nnz > 0 && A->ntiles > 0 && gather_len <= ((int64_t)1 << (32 - kSlotBits)) && tile_nnz <= kSortCap &&
         getenv("KCRN_NO_GATHER_ORDER") == nullptr) {
         KCRN_CUDA(cudaMalloc(&A->gidx, sizeof(uint32_t) * (size_t)A->nnz));
-        KCRN_CUDA(cudaMalloc(&A->gval, sizeof(double) * (size_t)A->nnz));
+        KCRN_CUDA(cudaMalloc(&A->gval, sizeof(double) * ((size_t)A->nnz + 2)));      // + 2: 16-byte pairs may straddle the end
+        KCRN_CUDA(cudaMemsetAsync(A->gval + A->nnz, 0, sizeof(double) * 2, s));
         gather_order_kernel<<<(unsigned)A->ntiles, kSweepThreads, 0, s>>>(A->tiles, A->idx, A->val, A->gidx, A->gval);
         KCRN_LAUNCH_CHECK();
     }
@@ -405,9 +411,11 @@ template <int MODE, int kItems, int GATHER>
 __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepParams P) {
     constexpr int kTileNnz = kItems * kSweepThreads;       // non-zeros per CTA tile, kItems per thread
     constexpr bool ordered = GATHER != kGatherStored, kAsyncGather = GATHER == kGatherAsync;
-    __shared__ double sprod[kTileNnz];           // products of the tile
-    __shared__ double ssum[kAsyncGather ? kSumCapAsync : kTileSegs];   // per-segment sums of the tile
-    double *const spieces = kAsyncGather ? ssum : sprod;   // staging of the deferred sums' pieces
+    constexpr bool kStaged = GATHER == kGatherStaged;      // values through shared memory (16-byte cp.async)
+    constexpr bool kBusyProd = kAsyncGather || kStaged;    // the product buffer is in use before the products exist
+    __shared__ alignas(kStaged ? 16 : 8) double sprod[kTileNnz + (kStaged ? 2 : 0)];   // products of the tile
+    __shared__ double ssum[kBusyProd ? kSumCapAsync : kTileSegs];   // per-segment sums of the tile
+    double *const spieces = kBusyProd ? ssum : sprod;      // staging of the deferred sums' pieces
     __shared__ int sptr[kTileSegs + 8];          // segment pointers of the tile
     __shared__ double sred[2 * kSweepWarps];
     __shared__ int s_last;
@@ -430,7 +438,14 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         for (int r = 0; r < kItems; ++r) {
             const int i = r * kSweepThreads + tid;
             ci[r] = i < nk0 ? ld_stream(ip + i) : -1;
-            av[r] = i < nk0 ? ld_stream(vp + i) : 0.0;
+            if constexpr (!kStaged) av[r] = i < nk0 ? ld_stream(vp + i) : 0.0;
+        }
+        if constexpr (kStaged) {
+            // values (gather order) -> sprod[(k0 & 1) + i] in aligned 16-byte pairs; a pair may reach one entry before
+            // or beyond the tile (allocated, never read back)
+            const int off = td.y & 1;
+            const double *v16 = P.gval + (td.y - off);
+            for (int q = 2 * tid; q < nk0 + off; q += 2 * kSweepThreads) cp_async_16(sprod + q, v16 + q);
         }
         if (td.z > 0 && (td.w >> 16) != kSingleTag) {
 #pragma unroll
@@ -596,6 +611,17 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
                 xv[r] = i < nk ? sprod[i] : 0.0;
             }
         }
+        if constexpr (kStaged) {             // the values were copied by other threads of the CTA
+            cp_async_wait_all();
+            __syncthreads();
+            const int off = k0 & 1;
+#pragma unroll
+            for (int r = 0; r < kItems; ++r) {
+                const int i = r * kSweepThreads + tid;
+                av[r] = i < nk ? sprod[off + i] : 0.0;
+            }
+            __syncthreads();                 // all values are in registers: the buffer now takes the products
+        }
         double p[kItems];
 #pragma unroll
         for (int r = 0; r < kItems; ++r) {
@@ -632,7 +658,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
 #pragma unroll
             for (int r = 0; r < kItems; ++r) {
                 const int i = r * kSweepThreads + tid;
-                if (i < nk) sprod[GATHER == kGatherOrdered ? (ci[r] & ((1 << kSlotBits) - 1)) : i] = p[r];   // the natural position
+                if (i < nk) sprod[GATHER == kGatherOrdered || kStaged ? (ci[r] & ((1 << kSlotBits) - 1)) : i] = p[r];   // the natural position
             }
             cp_async_wait_all();
             __syncthreads();
@@ -749,7 +775,8 @@ template <int MODE>
 int launch(kcrn_problem *h, const SegMat &A, SweepParams &P) {
     fill_matrix(P, A);
     const int variant = !A.gidx ? kGatherStored : (MODE == kRowsLanczos || MODE == kColsLanczos ? A.gather_lanczos : A.gather_plain);
-    if (variant == kGatherAsync) KCRN_TRY((launch_variant<MODE, kGatherAsync>(h, A, P)));
+    if (variant == kGatherStaged) KCRN_TRY((launch_variant<MODE, kGatherStaged>(h, A, P)));
+    else if (variant == kGatherAsync) KCRN_TRY((launch_variant<MODE, kGatherAsync>(h, A, P)));
     else if (variant == kGatherOrdered) KCRN_TRY((launch_variant<MODE, kGatherOrdered>(h, A, P)));
     else KCRN_TRY((launch_variant<MODE, kGatherStored>(h, A, P)));
     h->counters[0] += 1;
@@ -786,6 +813,9 @@ int launch_rows_weighted(kcrn_problem *h, const double *v) {
     return launch<kRowsWeighted>(h, h->csr, P);
 }
 
+// the experimental staged variant takes part in the measurement only on request
+int gather_candidates_last() { return getenv("KCRN_GATHER_TRY_STAGED") ? kGatherStaged : kGatherAsync; }
+
 // KCRN_GATHER="p[,l]" forces the gather variant of the plain / Lanczos passes (A/B switch); -1: measure
 void forced_gather_variants(int *plain, int *lanczos) {
     *plain = *lanczos = -1;
@@ -793,8 +823,8 @@ void forced_gather_variants(int *plain, int *lanczos) {
     if (!e) return;
     int a = -1, b = -1;
     const int k = sscanf(e, "%d,%d", &a, &b);
-    if (k >= 1 && a >= 0 && a <= 2) *plain = *lanczos = a;
-    if (k >= 2 && b >= 0 && b <= 2) *lanczos = b;
+    if (k >= 1 && a >= 0 && a < kGatherVariants) *plain = *lanczos = a;
+    if (k >= 2 && b >= 0 && b < kGatherVariants) *lanczos = b;
 }
 
 // Which gather variant serves the passes outside the Lanczos recurrence: measured per matrix on the weighted row
@@ -828,7 +858,7 @@ int tune_plain_sweeps(kcrn_problem *h) {
         int best = kGatherStored;
         float best_ms = 0.f;
         const int batches = A->nnz > 50000000 ? 1 : 3;              // the fastest of a few batches: robust to a stray stall
-        for (int v = kGatherStored; v <= kGatherAsync && rc == KCRN_OK; ++v) {
+        for (int v = kGatherStored; v <= gather_candidates_last() && rc == KCRN_OK; ++v) {
             A->gather_plain = v;
             float ms = 0.f;
             for (int bt = 0; bt < batches && rc == KCRN_OK; ++bt) {
@@ -858,8 +888,8 @@ int tune_plain_sweeps(kcrn_problem *h) {
 bool lanczos_defer_fits(const kcrn_problem *h) {
     auto even = [](int v) { return (v + 1) & ~1; };
     // staged in the CONSUMER's product buffer: row pieces in the column sweep's, column pieces in the row sweep's
-    const bool async_cols = h->csc.gidx && h->csc.gather_lanczos == kGatherAsync;
-    const bool async_rows = h->csr.gidx && h->csr.gather_lanczos == kGatherAsync;
+    const bool async_cols = h->csc.gidx && h->csc.gather_lanczos >= kGatherAsync;     // async / staged: pieces go to the sums buffer
+    const bool async_rows = h->csr.gidx && h->csr.gather_lanczos >= kGatherAsync;
     const int cap_cols = async_cols ? kSumCapAsync : h->csc.items * kSweepThreads;
     const int cap_rows = async_rows ? kSumCapAsync : h->csr.items * kSweepThreads;
     return 2 * even(h->csr.grid) + even(h->csr.nlong) <= cap_cols && even(h->csc.grid) + even(h->csc.nlong) <= cap_rows;
