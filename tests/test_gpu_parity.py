@@ -211,8 +211,10 @@ def test_fused_lanczos_under_process_wide_switches(torch, tmp_path, lanczos_prob
         assert np.allclose(ref[k], got[k], rtol=1e-10, atol=1e-12), k
 
 
-@pytest.mark.xfail(strict=False, reason="experimental gather variant 3 (values staged in shared memory with 16-byte cp.async): "
-                   "compiled, never chosen by default, not yet run on a GPU (round-1 GPU budget spent)")
+@pytest.mark.skipif(__import__("os").environ.get("KCRN_RUN_EXPERIMENTAL") != "1",
+                    reason="gather variant 3 (values staged in shared memory with 16-byte cp.async) is compiled but has never "
+                           "run on a GPU (round-1 budget spent) and is never chosen by default: a kernel in that state "
+                           "stays out of the default suite; KCRN_RUN_EXPERIMENTAL=1 runs this check")
 def test_experimental_staged_gather_variant_same_bits(torch, tmp_path, lanczos_probe_default):
     # in a child process: a kernel that has never run must not be able to poison this process's CUDA context
     ref, got = lanczos_probe_default, _lanczos_probe(tmp_path, "staged", {"KCRN_GATHER": "3"})
