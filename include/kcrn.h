@@ -195,6 +195,14 @@ int kcrn_counters(kcrn_handle h, int64_t *counters8_host, int reset);
  * graph joined by programmatic edges, 20 per graph -- between two CUDA events on the handle's stream; returns the
  * mean duration per launch in microseconds. */
 int kcrn_time_sweep(kcrn_handle h, int which, int reps, double *mean_us_host);
+/* Host-only (no device needed): the tile list the sweeps would use for a matrix with this pointer array (rows of the
+ * CSR copy / columns of the CSC copy) -- no reference counterpart; lets the CPU test suite check the tiling
+ * invariants.  tiles4[i] = {first segment, first entry, z, entries | tag << 16}: z > 0 whole segments (tag 15: one
+ * segment reduced by the whole CTA), z < 0 one piece of long segment -z-1; longtab4[l] = {first partial slot,
+ * pieces, first entry of the segment, segment}.  Arrays are filled only when the capacities suffice; the counts
+ * and the tile size (entries per thread, x 256 threads) are always returned. */
+int kcrn_plan_tiles(const int32_t *indptr_host, int64_t n_segments, int32_t *tiles4_host, int64_t tiles_cap,
+                    int64_t *n_tiles, int32_t *longtab4_host, int64_t long_cap, int64_t *n_long, int *items);
 /* Which gather variant of the sweep kernel was measured fastest for this handle's matrices (no reference
  * counterpart; all variants compute the same bits): out4 = {CSR plain, CSR Lanczos, CSC plain, CSC Lanczos},
  * 0 = entries as stored, 1 = gather-ordered tiles, 2 = gather-ordered tiles with asynchronous (LDGSTS) gathers

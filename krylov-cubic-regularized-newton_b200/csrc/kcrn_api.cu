@@ -900,6 +900,20 @@ int kcrn_counters(kcrn_handle h, int64_t *counters8_host, int reset) {
     return KCRN_OK;
 }
 
+int kcrn_plan_tiles(const int32_t *indptr_host, int64_t n_segments, int32_t *tiles4_host, int64_t tiles_cap,
+                    int64_t *n_tiles, int32_t *longtab4_host, int64_t long_cap, int64_t *n_long, int *items) {
+    if (!indptr_host || n_segments < 0 || !n_tiles || !n_long || !items) { set_error("kcrn_plan_tiles: bad argument"); return KCRN_E_ARG; }
+    std::vector<int32_t> ptr(indptr_host, indptr_host + n_segments + 1);
+    std::vector<int4> tiles, longtab;
+    int npartial = 0;
+    plan_tiles(ptr, n_segments, ptr[(size_t)n_segments], tiles, longtab, npartial, *items);
+    *n_tiles = (int64_t)tiles.size();
+    *n_long = (int64_t)longtab.size();
+    if (tiles4_host && (int64_t)tiles.size() <= tiles_cap) memcpy(tiles4_host, tiles.data(), sizeof(int4) * tiles.size());
+    if (longtab4_host && (int64_t)longtab.size() <= long_cap) memcpy(longtab4_host, longtab.data(), sizeof(int4) * longtab.size());
+    return KCRN_OK;
+}
+
 int kcrn_gather_variants(kcrn_handle h, int *out4_host) {
     if (!h || !out4_host) { set_error("kcrn_gather_variants: null argument"); return KCRN_E_ARG; }
     out4_host[0] = h->csr.gidx ? h->csr.gather_plain : 0;

@@ -231,6 +231,8 @@ int canonical_csc_to_host(const SegMat &csc, int32_t *indptr_host, int32_t *indi
 
 // ----------------------------------------------------------------------------- kcrn_sweep.cu
 int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s);
+void plan_tiles(const std::vector<int32_t> &ptr, int64_t nseg, int64_t nnz, std::vector<int4> &tiles,
+                std::vector<int4> &longtab, int &npartial, int &items);   // host only
 void free_segmat(SegMat *A);
 int launch_forward(kcrn_problem *h, const double *x);                 // A x and everything derived
 int launch_rows_weighted(kcrn_problem *h, const double *v);           // t = D .* (A v)

@@ -159,37 +159,46 @@ __global__ void __launch_bounds__(kSweepThreads) gather_order_kernel(const int4 
 // tiles of 2048 -- two waves on 148 SMs x 4 CTAs, the second one a quarter full -- but 533 tiles of 2816: one wave
 // (measured: 28.4 -> 25.2 us per HVP inside the Lanczos graph).  Among the candidates (8, 11, 12 non-zeros per
 // thread) take the fewest waves, then the smaller tile; matrices of many waves keep 2048.
-int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s) {
-    A->gather_len = gather_len;
-    const int64_t nseg = A->nseg;
-    std::vector<int32_t> ptr((size_t)nseg + 1);
-    KCRN_CUDA(cudaMemcpyAsync(ptr.data(), A->ptr, sizeof(int32_t) * (nseg + 1), cudaMemcpyDeviceToHost, s));
-    KCRN_CUDA(cudaStreamSynchronize(s));
+// Pure host logic (no device): the tile list of one matrix from its pointer array.  Also behind kcrn_plan_tiles, so
+// that the CPU test suite can check its invariants on arbitrary segment-length distributions.
+void plan_tiles(const std::vector<int32_t> &ptr, int64_t nseg, int64_t nnz, std::vector<int4> &tiles,
+                std::vector<int4> &longtab, int &npartial, int &items) {
     const char *env_short = getenv("KCRN_SHORT_SEG");       // tuning knob: longest segment that shares a tile
     const char *env_items = getenv("KCRN_TILE_ITEMS");      // tuning knob: force 8, 11 or 12 non-zeros per thread
     if (env_items && atoi(env_items) == 0) env_items = nullptr;
-    std::vector<int4> tiles, longtab;
-    int npartial = 0;
+    npartial = 0;
     const int cand[3] = {8, 11, 12};
     const int slots = kNumSm * 4 - 32;                      // resident CTAs, minus a margin for the neighbours under PDL
-    int items = 8, short_seg = kShortSeg;
+    int short_seg = kShortSeg;
+    items = 8;
     long best_waves = -1;
     for (int c : cand) {
         if (env_items && atoi(env_items) != c) continue;
         const int tile_nnz = c * kSweepThreads;
         // few waves: also let segments of up to 2048 share tiles (fewer, fuller tiles; measured 24.6 -> 24.0 us per HVP)
         const int ss = env_short ? std::max(1, std::min(tile_nnz, atoi(env_short))) : 2 * kShortSeg;
-        make_tiles(ptr, nseg, A->nnz, tile_nnz, c == 8 && !env_short ? kShortSeg : ss, tiles, longtab, npartial);
+        make_tiles(ptr, nseg, nnz, tile_nnz, c == 8 && !env_short ? kShortSeg : ss, tiles, longtab, npartial);
         long waves = ((long)tiles.size() + slots - 1) / slots;
         if (c == 8 && waves > 4 && !env_items) { items = 8; short_seg = env_short ? ss : kShortSeg; best_waves = waves; break; }
         if (c == 8 && !env_short) {              // the small-matrix packing for the default tile size as well
-            make_tiles(ptr, nseg, A->nnz, tile_nnz, ss, tiles, longtab, npartial);
+            make_tiles(ptr, nseg, nnz, tile_nnz, ss, tiles, longtab, npartial);
             waves = ((long)tiles.size() + slots - 1) / slots;
         }
         if (best_waves < 0 || waves < best_waves) { best_waves = waves; items = c; short_seg = ss; }
     }
+    make_tiles(ptr, nseg, nnz, items * kSweepThreads, short_seg, tiles, longtab, npartial);
+}
+
+int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s) {
+    A->gather_len = gather_len;
+    const int64_t nseg = A->nseg;
+    std::vector<int32_t> ptr((size_t)nseg + 1);
+    KCRN_CUDA(cudaMemcpyAsync(ptr.data(), A->ptr, sizeof(int32_t) * (nseg + 1), cudaMemcpyDeviceToHost, s));
+    KCRN_CUDA(cudaStreamSynchronize(s));
+    std::vector<int4> tiles, longtab;
+    int npartial = 0, items = 8;
+    plan_tiles(ptr, nseg, A->nnz, tiles, longtab, npartial, items);
     const int tile_nnz = items * kSweepThreads;
-    make_tiles(ptr, nseg, A->nnz, tile_nnz, short_seg, tiles, longtab, npartial);
     A->items = items;
     if (getenv("KCRN_VERBOSE"))
         fprintf(stderr, "kcrn: %lld segments, %lld non-zeros -> %zu tiles of %d (%zu long segments)\n", (long long)nseg,

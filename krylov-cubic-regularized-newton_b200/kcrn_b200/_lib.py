@@ -64,6 +64,8 @@ SIGNATURES = {
     "kcrn_counters": (c_int, [c_void_p, POINTER(c_int64), c_int]),
     "kcrn_time_sweep": (c_int, [c_void_p, c_int, c_int, POINTER(c_double)]),
     "kcrn_gather_variants": (c_int, [c_void_p, POINTER(c_int)]),
+    "kcrn_plan_tiles": (c_int, [c_void_p, c_int64, c_void_p, c_int64, POINTER(c_int64), c_void_p, c_int64,
+                                POINTER(c_int64), POINTER(c_int)]),
 }
 
 

@@ -142,3 +142,81 @@ def test_bench_roofline_traffic_comes_from_the_committed_capture():
     assert bench.ncu_traffic(t["workload"], 1) == t["csc_pass_bytes_per_launch"]
     assert bench.ncu_traffic("no-such-workload", 0) is None
     assert os.path.exists(os.path.join(root, t["source"].split(" ")[0]))
+
+
+def _plan_tiles(indptr):
+    from ctypes import byref, c_int, c_int64
+    from kcrn_b200 import _lib
+    lib = _lib.load()
+    indptr = np.ascontiguousarray(indptr, np.int32)
+    nseg = indptr.size - 1
+    nt, nl, items = c_int64(), c_int64(), c_int()
+    _lib.check(lib.kcrn_plan_tiles(indptr.ctypes.data, nseg, None, 0, byref(nt), None, 0, byref(nl), byref(items)))
+    tiles = np.zeros((max(nt.value, 1), 4), np.int32)
+    longtab = np.zeros((max(nl.value, 1), 4), np.int32)
+    _lib.check(lib.kcrn_plan_tiles(indptr.ctypes.data, nseg, tiles.ctypes.data, tiles.shape[0], byref(nt),
+                                   longtab.ctypes.data, longtab.shape[0], byref(nl), byref(items)))
+    return tiles[:nt.value], longtab[:nl.value], items.value
+
+
+def _check_tiling(lengths):
+    lengths = np.asarray(lengths, np.int64)
+    indptr = np.concatenate(([0], np.cumsum(lengths))).astype(np.int32)
+    nseg, nnz = lengths.size, int(indptr[-1])
+    tiles, longtab, items = _plan_tiles(indptr)
+    assert items in (8, 11, 12)
+    tile_nnz = items * 256
+    assert tile_nnz <= 4096                                   # natural positions fit the 12 slot bits of a gather word
+    seg_cover = np.zeros(nseg, np.int64)
+    nnz_cover = np.zeros(nnz, np.int64)
+    pieces_seen = {}
+    for seg0, k0, z, w in tiles.tolist():
+        nk, tag = w & 0xFFFF, w >> 16
+        assert 0 <= nk <= tile_nnz and 0 <= k0 and k0 + nk <= nnz
+        nnz_cover[k0:k0 + nk] += 1
+        if z > 0 and tag != 15:                               # stream tile: z whole segments
+            assert z <= 1024 and 0 <= tag <= 5
+            assert k0 == indptr[seg0] and nk == indptr[seg0 + z] - indptr[seg0]
+            seg_cover[seg0:seg0 + z] += 1
+        elif z > 0:                                           # one medium segment
+            assert z == 1 and k0 == indptr[seg0] and nk == lengths[seg0]
+            seg_cover[seg0] += 1
+        else:                                                 # one piece of a long segment
+            slot0, npieces, first, seg = longtab[-z - 1].tolist()
+            assert seg == seg0 and first == indptr[seg0] and lengths[seg0] > tile_nnz
+            assert npieces == -(-int(lengths[seg0]) // tile_nnz)
+            assert (k0 - first) % tile_nnz == 0 and nk == min(tile_nnz, indptr[seg0 + 1] - k0)
+            pieces_seen.setdefault(seg0, []).append((k0 - first) // tile_nnz)
+    for seg, got in pieces_seen.items():
+        slot0, npieces, first, s = longtab[[i for i in range(len(longtab)) if longtab[i, 3] == seg][0]].tolist()
+        assert sorted(got) == list(range(npieces))
+        seg_cover[seg] += 1
+    assert np.all(nnz_cover == 1) and np.all(seg_cover == 1)  # every entry and every segment (empty ones too) exactly once
+    slots = sorted((int(r[0]), int(r[1])) for r in longtab)   # partial-sum slots of the long segments do not overlap
+    for (a, na), (b, _) in zip(slots, slots[1:]):
+        assert a + na <= b
+
+
+def test_tile_plan_invariants_on_awkward_length_distributions():
+    rng = np.random.default_rng(0)
+    _check_tiling([0])
+    _check_tiling([5])
+    _check_tiling(np.zeros(3000, np.int64))                               # only empty segments
+    _check_tiling([4097, 0, 0, 1, 20000, 3, 2816, 2817, 3072, 3073, 0])   # around every threshold
+    _check_tiling(rng.poisson(74, 20242))                                  # rcv1-like rows
+    _check_tiling(np.clip((rng.pareto(0.9, 47236) * 3).astype(np.int64), 0, 20000))   # power-law columns
+    _check_tiling(rng.integers(0, 3, 200_000))                             # many tiny segments (> 1024 per tile's worth)
+    _check_tiling(np.concatenate((rng.poisson(24, 49749), [49749] * 3)))   # w8a-like with three dense columns
+
+
+def test_tile_plan_invariants_hypothesis():
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    @hyp.settings(max_examples=60, deadline=None)
+    @hyp.given(st.lists(st.one_of(st.integers(0, 40), st.integers(0, 1200), st.integers(2000, 9000)), min_size=1,
+                        max_size=400))
+    def run(lengths):
+        _check_tiling(lengths)
+
+    run()
