@@ -81,8 +81,8 @@ struct SegMat {
     int64_t gather_len = 0;      // length of the vector this matrix gathers from (d for CSR, n for CSC)
     // Gather-ordered copy used by the sweeps (build_tiles): inside every stream tile the non-zeros are sorted by
     // the index they gather with, word = index << kSlotBits | position the entry has in the tile's natural order.
-    // The lanes of a warp then ask L1TEX for far fewer distinct 128-byte lines per load (rcv1 shape: 31.7 -> 15.7
-    // rows, 23.1 -> 11.9 columns); the products go back to their natural positions in shared memory, so every sum
+    // The lanes of a warp then ask L1TEX for far fewer distinct 128-byte lines per load (rcv1 shape: 31.5 -> 15.7
+    // rows, 23.0 -> 11.6 columns); the products go back to their natural positions in shared memory, so every sum
     // keeps its order and its bits.  Null when gather_len does not fit the word (sweeps then use idx / val).
     uint32_t *gidx = nullptr;    // [nnz]
     double *gval = nullptr;      // [nnz] values in the same order
