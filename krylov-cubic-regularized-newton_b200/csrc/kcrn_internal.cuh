@@ -86,6 +86,7 @@ struct SegMat {
     // keeps its order and its bits.  Null when gather_len does not fit the word (sweeps then use idx / val).
     uint32_t *gidx = nullptr;    // [nnz]
     double *gval = nullptr;      // [nnz] values in the same order
+    uint16_t *gslot = nullptr;   // [nnz] natural positions on their own (experimental: gather lengths beyond 2^20), else null
     // which gather variant of the sweep kernel (kcrn_sweep.cu: GatherVariant) serves this matrix, measured at
     // set-up: one choice for the Lanczos passes, one for all others
     int gather_plain = 0, gather_lanczos = 0;

@@ -16,6 +16,7 @@ for g in auto 0 1,2 3 1,3 3,2; do
 done
 unset KCRN_GATHER
 KCRN_GATHER_TRY_STAGED=1 KCRN_VERBOSE=1 timeout 120 python profiles/microbench/variant_time.py rcv1 w8a news20 2>&1 | grep -v "^$"
+KCRN_GATHER_WIDE=1 KCRN_VERBOSE=1 timeout 120 python profiles/microbench/variant_time.py news20 2>&1 | grep -v "^$"
 } > $O/${TAG}_variants.txt
 cat $O/${TAG}_variants.txt
 timeout 200 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err

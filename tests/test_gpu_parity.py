@@ -179,14 +179,14 @@ def test_gather_variants_give_the_same_bits(torch, monkeypatch, name):
             assert torch.equal(a, b)
 
 
-def _lanczos_probe(tmp_path, tag, extra_env):
+def _lanczos_probe(tmp_path, tag, extra_env, name="small"):
     import os, subprocess, sys
     here = os.path.dirname(os.path.abspath(__file__))
     e = {k: v for k, v in os.environ.items() if not k.startswith("KCRN_")}
     e.update(extra_env)
     out = str(tmp_path / f"probe_{tag}.npz")
-    subprocess.run([sys.executable, os.path.join(here, "lanczos_probe.py"), "small", "6", "0", out], env=e, check=True,
-                   timeout=300)
+    subprocess.run([sys.executable, os.path.join(here, "lanczos_probe.py"), name, "6", "0", out], env=e, check=True,
+                   timeout=600)
     with np.load(out) as z:
         return {k: z[k] for k in z.files}
 
@@ -219,6 +219,19 @@ def test_experimental_staged_gather_variant_same_bits(torch, tmp_path, lanczos_p
     # in a child process: a kernel that has never run must not be able to poison this process's CUDA context
     ref, got = lanczos_probe_default, _lanczos_probe(tmp_path, "staged", {"KCRN_GATHER": "3"})
     assert set(got["variants"].tolist()) == {3}
+    for k in ("value", "grad", "hvp", "V", "alphas", "bet"):
+        assert np.array_equal(ref[k], got[k]), k
+
+
+@pytest.mark.skipif(__import__("os").environ.get("KCRN_RUN_EXPERIMENTAL") != "1",
+                    reason="gather-ordered tiles for gather lengths beyond 2^20 (KCRN_GATHER_WIDE=1: index and natural position "
+                           "in separate arrays) are compiled but have never run on a GPU; KCRN_RUN_EXPERIMENTAL=1 runs this check")
+@pytest.mark.parametrize("forced", ["1", "2"])
+def test_experimental_wide_gather_words_same_bits(torch, tmp_path, forced):
+    # news20 shape: d = 1.36 M does not fit the 20-bit index of a packed word, so the CSR pass takes the wide layout
+    ref = _lanczos_probe(tmp_path, "stored", {"KCRN_GATHER": "0"}, name="news20")
+    got = _lanczos_probe(tmp_path, "wide", {"KCRN_GATHER_WIDE": "1", "KCRN_GATHER": forced}, name="news20")
+    assert set(got["variants"].tolist()) == {int(forced)}
     for k in ("value", "grad", "hvp", "V", "alphas", "bet"):
         assert np.array_equal(ref[k], got[k]), k
 
