@@ -113,40 +113,123 @@ def make_shard(workload, rank):
 
 
 def cpu_oracle_run(P, m, steps, warmup, threads):
-    """The CPU restatement of the reference path (oracle/), timed on the host cores: the reported baseline."""
+    """The CPU restatement of the reference path (oracle/), timed on the host cores.  Only used when the reference
+    itself is not installed under baseline/_ref.  BLAS is held to one thread while it runs: the port's sweeps are
+    OpenMP loops and a spinning OpenBLAS pool between them costs a factor of 20 (round-1 finding)."""
     from oracle import oracle as O
-    L = O.OracleLogistic(P.indptr, P.indices, P.data, (P.n, P.d), P.b, threads=threads)
-    opt = O.KrylovCRN(L, subspace_dim=m, tolerance=0)
-    opt.x = np.array(P.x0, copy=True)
-    L.reset()
-    for _ in range(warmup):
-        opt.step()
-    h0 = L.calls["hvp"]
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        opt.step()
-    dt = time.perf_counter() - t0
-    hv = L.calls["hvp"] - h0
+    from threadpoolctl import threadpool_limits
+    with threadpool_limits(limits=1, user_api="blas"):
+        L = O.OracleLogistic(P.indptr, P.indices, P.data, (P.n, P.d), P.b, threads=threads)
+        opt = O.KrylovCRN(L, subspace_dim=m, tolerance=0)
+        opt.x = np.array(P.x0, copy=True)
+        L.reset()
+        for _ in range(warmup):
+            opt.step()
+        h0 = L.calls["hvp"]
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            opt.step()
+        dt = time.perf_counter() - t0
+        hv = L.calls["hvp"] - h0
     return hv / dt, steps / dt, dt, hv
+
+
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def reference_run(P, m, steps, warmup):
+    """The UNMODIFIED reference (baseline/_ref/optimizer = the files of /root/reference/optimizer, installed by
+    __graft_entry__.build()): Cubic_Krylov_LS(...).run(x0, it_max=warmup + steps) through its own public API, exactly
+    as BASELINE.md section 4 prescribes -- matplotlib stubbed (opt_trace.py imports pyplot at module level), a counting
+    wrapper on loss.hess_vec_prod, timing from the reference's own trace.ts (optimizer.py:129,151).  The first
+    `warmup` iterations (they include the numba JIT of logsig) are dropped.  Runs in a child interpreter so that the
+    reference's `optimizer` package and this repository's mirror of the same name never meet."""
+    code = r"""
+import json, os, sys, time, types
+root, ref, m, steps, warmup, workload = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), sys.argv[6]
+mpl, plt = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
+mpl.pyplot = plt
+sys.modules.update({"matplotlib": mpl, "matplotlib.pyplot": plt})
+import importlib.util
+spec = importlib.util.spec_from_file_location("kcrn_synth", os.path.join(root, "krylov-cubic-regularized-newton_b200", "kcrn_b200", "synth.py"))
+synth = importlib.util.module_from_spec(spec); sys.modules["kcrn_synth"] = synth; spec.loader.exec_module(synth)
+sys.path.insert(0, ref)
+import warnings; warnings.filterwarnings("ignore")
+import numpy as np
+import optimizer.cubic as RC
+from optimizer.loss import LogisticRegression
+assert os.path.realpath(RC.__file__).startswith(os.path.realpath(ref)), RC.__file__
+P = synth.make_problem(workload, seed=0)
+loss = LogisticRegression(P.scipy_csr(), P.b, l1=0, l2=0, store_mat_vec_prod=True)
+opt = RC.Cubic_Krylov_LS(loss=loss, reg_coef=1e-3, subspace_dim=m, tolerance=0, label="reference", tqdm=False)
+calls = {}
+inner = loss.hess_vec_prod
+def counted(x, v, *a, **k):
+    calls[opt.it] = calls.get(opt.it, 0) + 1
+    return inner(x, v, *a, **k)
+loss.hess_vec_prod = counted
+import io, contextlib
+with contextlib.redirect_stderr(io.StringIO()), contextlib.redirect_stdout(io.StringIO()):
+    trace = opt.run(P.x0, it_max=warmup + steps)
+its, ts = list(trace.its), list(trace.ts)
+assert its[-1] == warmup + steps and warmup in its, (its[-5:], warmup)
+dt = ts[-1] - ts[its.index(warmup)]
+hv = sum(c for it, c in calls.items() if it >= warmup)
+try:
+    from threadpoolctl import threadpool_info
+    pools = [{k: p.get(k) for k in ("user_api", "internal_api", "num_threads")} for p in threadpool_info()]
+except Exception:
+    pools = None
+print(json.dumps({"hvps": hv, "seconds": dt, "steps": steps, "n": P.n, "d": P.d, "nnz": P.nnz, "pools": pools,
+                  "f_last": float(opt.value), "cpu_count": os.cpu_count()}))
+"""
+    env = dict(os.environ)
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm must see the same thread pools at every N
+    env.pop("OMP_NUM_THREADS", None)
+    out = subprocess.run([sys.executable, "-c", code, ROOT, REF_DIR, str(m), str(steps), str(warmup), P],
+                         capture_output=True, text=True, env=env, timeout=1500)
+    if out.returncode != 0:
+        raise RuntimeError("reference arm failed: " + out.stderr[-800:])
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def cpu_reference(workload, m, steps, warmup):
+    """(value HVP/s, outer it/s, seconds, HVPs, cpu_baseline dict) -- the reference when installed, else the port."""
+    if os.path.isdir(os.path.join(REF_DIR, "optimizer")):
+        r = reference_run(workload, m, steps, warmup)
+        hps, ips = r["hvps"] / r["seconds"], r["steps"] / r["seconds"]
+        blas = max([p["num_threads"] for p in (r["pools"] or []) if p.get("user_api") == "blas"] or [1])
+        cb = {"value": hps, "unit": UNIT, "cores": 1, "kind": "reference", "outer_iters_per_sec": ips,
+              "host_cpus": r["cpu_count"], "threadpools": r["pools"],
+              "sample": f"{r['steps']} outer iterations ({r['hvps']} HVPs) of the same workload after {warmup} warm-up "
+                        f"iterations, unmodified reference Cubic_Krylov_LS.run (baseline/_ref); scipy csr/csc matvec "
+                        f"(~70% of its time) is single-threaded, BLAS pool {blas} threads for the dense vector ops: "
+                        f"effective parallelism ~1 core"}
+        return hps, ips, r["seconds"], r["hvps"], cb, (r["n"], r["d"], r["nnz"])
+    P = make_shard(workload, 0)
+    threads = os.cpu_count() or 1
+    hps, ips, dt, hv = cpu_oracle_run(P, m, steps, warmup, threads)
+    cb = {"value": hps, "unit": UNIT, "cores": threads, "kind": "port", "outer_iters_per_sec": ips,
+          "sample": f"{steps} outer iterations ({hv} HVPs) of the same workload, CPU oracle port (oracle/, OpenMP sweeps, "
+                    f"BLAS held to 1 thread); baseline/_ref is not installed on this box"}
+    return hps, ips, dt, hv, cb, (P.n, P.d, P.nnz)
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    P = make_shard(args.workload, 0)
-    threads = os.cpu_count() or 1
-    steps = max(1, min(args.steps, 40))
-    hps, ips, dt, hv = cpu_oracle_run(P, args.m, steps, max(1, min(args.warmup, 3)), threads)
+    steps, warmup = max(1, min(args.steps, 40)), max(1, min(args.warmup, 5))
+    hps, ips, dt, hv, cb, (n, d, nnz) = cpu_reference(args.workload, args.m, steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": hps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "outer_iters_per_sec": ips,
-        "config": {"workload": f"{args.workload}-shape n={P.n} d={P.d} nnz={P.nnz}, Krylov CRN m={args.m}",
-                   "note": "the reference is pure Python over scipy/numpy and cannot travel to the GPU box; this arm "
-                           "times the CPU oracle port (oracle/, same arithmetic, OpenMP sweeps) on the host cores"},
-        "cpu_baseline": {"value": hps, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{steps} outer iterations ({hv} HVPs) of the same workload"},
+        "config": {"workload": f"{args.workload}-shape n={n} d={d} nnz={nnz}, Krylov CRN m={args.m}, x0=0.5, "
+                               f"reg_coef=1e-3",
+                   "note": "one shard's problem on the host CPU (the reference has no multi-process path); "
+                           "iterations warmup..warmup+steps of Cubic_Krylov_LS.run from x0"},
+        "cpu_baseline": cb,
         "e2e": {"value": hps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -343,14 +426,8 @@ def main():
         "gather_variants": gather_variants,
         "roofline": roofline, "clocks": clocks, "device_loop": device_loop,
     }
-    if rank == 0 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        cs = min(K, 20)
-        hps, ips, dt, hv = cpu_oracle_run(P, args.m, cs, 2, threads)
-        line["cpu_baseline"] = {"value": hps, "unit": UNIT, "cores": threads, "kind": "port",
-                                "outer_iters_per_sec": ips,
-                                "sample": f"{cs} outer iterations ({hv} HVPs) of one rank's shard, CPU oracle port "
-                                          f"(oracle/, OpenMP sweeps)"}
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_reference(args.workload, args.m, min(K, 20), 3)[4]
     if rank == 0:
         print(json.dumps(line), flush=True)
     eng.close()

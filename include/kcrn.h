@@ -79,6 +79,9 @@ int kcrn_csc_view(kcrn_handle h, int32_t *indptr_host, int32_t *indices_host, do
  * residual a-b and the per-sample loss terms.  Replaces the value-equality memo
  * mat_vec_product (loss.py:266-277): the host mirror decides when x changed.            */
 int kcrn_set_x(kcrn_handle h, const double *x_dev);
+/* The iterate changes but the cached A x must stay as it is (update_mat_vec_product overrides it until reset(),
+ * loss.py:279-286): only the copy of x used by the l2 terms of value / partial_gradient (loss.py:217, :247) moves. */
+int kcrn_set_x_only(kcrn_handle h, const double *x_dev);
 /* value at the current x -> *out_dev (1 double).  Oracle._value, loss.py:215-220 (+ logsig :161-176). */
 int kcrn_value(kcrn_handle h, double *out_dev);
 /* gradient at the current x -> out_dev[n_cols] (NULL: keep it in the handle for kcrn_lanczos).
@@ -203,6 +206,13 @@ int kcrn_time_sweep(kcrn_handle h, int which, int reps, double *mean_us_host);
  * and the tile size (entries per thread, x 256 threads) are always returned. */
 int kcrn_plan_tiles(const int32_t *indptr_host, int64_t n_segments, int32_t *tiles4_host, int64_t tiles_cap,
                     int64_t *n_tiles, int32_t *longtab4_host, int64_t long_cap, int64_t *n_long, int *items);
+/* The balanced one-tile-per-SM plan of the persistent recurrence kernel (kcrn_persist.cu) for a matrix with this pointer
+ * array on a device of `grid` SMs -- no reference counterpart; for the CPU test suite.  tiles12[i] = {first entry,
+ * entries, first segment, segments, log2 threads per segment, head cut segment (-1: none), its piece, tail cut
+ * segment, its piece, 0, 0, 0}; longtab4[l] = {first partial slot, pieces, segment, 0}.  *fits = 0: the matrix
+ * needs more than `grid` tiles and the handle would keep the per-pass kernels. */
+int kcrn_plan_persist(const int32_t *indptr_host, int64_t n_segments, int grid, int32_t *tiles12_host, int64_t tiles_cap,
+                      int64_t *n_tiles, int32_t *longtab4_host, int64_t long_cap, int64_t *n_long, int *fits);
 /* Which gather variant of the sweep kernel was measured fastest for this handle's matrices (no reference
  * counterpart; all variants compute the same bits): out4 = {CSR plain, CSR Lanczos, CSC plain, CSC Lanczos},
  * 0 = entries as stored, 1 = gather-ordered tiles, 2 = gather-ordered tiles with asynchronous (LDGSTS) gathers

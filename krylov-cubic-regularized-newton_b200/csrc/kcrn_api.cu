@@ -84,7 +84,9 @@ int enqueue_value(kcrn_problem *h, double *out) {
 }
 
 // the whole m-step recurrence, enqueued on h->stream (captured into a graph by kcrn_lanczos)
-int enqueue_lanczos(kcrn_problem *h, int m, int reorth) {
+int enqueue_lanczos(kcrn_problem *h, int m, int reorth, bool allow_persist = true) {
+    // small single-GPU problems: the whole recurrence is one persistent kernel (kcrn_persist.cu)
+    if (allow_persist && h->persist_ok && !reorth && !h->sharded()) return launch_persist_lanczos(h, m);
     // single GPU: the grid-wide sums (alpha after the row sweep, beta after the column sweep) are finished by the
     // kernel that consumes them -- 2: both, the row sweep also advances the recurrence; 1: alpha only (the
     // re-orthogonalisation kernel owns beta and the advance).  Row-sharded: 0, the exchange kernels own both.
@@ -143,7 +145,7 @@ int tune_lanczos_sweeps(kcrn_problem *h, int m, bool have_g) {
             for (int bt = 0; bt < batches && rc == KCRN_OK; ++bt) {
                 for (int i = (bt == 0 ? -1 : 0); i < reps && rc == KCRN_OK; ++i) {      // one warm-up recurrence first
                     if (i == 0) cudaEventRecord(e0, s);
-                    rc = enqueue_lanczos(h, mt, 0);
+                    rc = enqueue_lanczos(h, mt, 0, false);
                 }
                 cudaEventRecord(e1, s);
                 if (rc == KCRN_OK && cudaEventSynchronize(e1) != cudaSuccess) {
@@ -345,6 +347,8 @@ int read_step_record(kcrn_problem *h, double *rec12_host) {
 
 using namespace kcrn;
 
+static bool tiles4_ok(const void *dst, size_t count, int64_t cap) { return dst && (int64_t)count <= cap; }
+
 extern "C" {
 
 int kcrn_abi_version(void) { return KCRN_ABI_VERSION; }
@@ -423,6 +427,7 @@ int kcrn_create(kcrn_handle *out, int64_t n_rows, int64_t n_cols, int64_t nnz, c
         h->vec_grid = (int)((n_cols + (int64_t)kVecThreads * h->vec_elems - 1) / ((int64_t)kVecThreads * h->vec_elems));
         KCRN_TRY(lanczos_alloc(h, 1));
         KCRN_TRY(tune_plain_sweeps(h));
+        KCRN_TRY(persist_build(h));
         KCRN_CUDA(cudaStreamSynchronize(s));
         return KCRN_OK;
     };
@@ -447,6 +452,7 @@ int kcrn_destroy(kcrn_handle h) {
     cudaFree(h->p2p_recv);
     cudaFree(h->p2p_epoch);
     nccl_destroy(h);
+    persist_free(h);
     free_segmat(&h->csr);
     free_segmat(&h->csc);
     double *bufs[] = {h->b, h->x_base, h->step_params, h->x_cur, h->Ax, h->D, h->resid, h->ell, h->t, h->ypart, h->V, h->w, h->wp, h->g,
@@ -561,6 +567,13 @@ int kcrn_set_x(kcrn_handle h, const double *x_dev) {
     KCRN_TRY(launch_forward(h, h->x_cur));
     h->have_x = true;
     h->have_base = false;
+    return KCRN_OK;
+}
+
+int kcrn_set_x_only(kcrn_handle h, const double *x_dev) {
+    if (!h || !x_dev) { set_error("kcrn_set_x_only: null argument"); return KCRN_E_ARG; }
+    if (x_dev != h->x_cur)
+        KCRN_CUDA(cudaMemcpyAsync(h->x_cur, x_dev, sizeof(double) * h->d, cudaMemcpyDeviceToDevice, h->stream));
     return KCRN_OK;
 }
 
@@ -910,6 +923,22 @@ int kcrn_plan_tiles(const int32_t *indptr_host, int64_t n_segments, int32_t *til
     *n_tiles = (int64_t)tiles.size();
     *n_long = (int64_t)longtab.size();
     if (tiles4_host && (int64_t)tiles.size() <= tiles_cap) memcpy(tiles4_host, tiles.data(), sizeof(int4) * tiles.size());
+    if (longtab4_host && (int64_t)longtab.size() <= long_cap) memcpy(longtab4_host, longtab.data(), sizeof(int4) * longtab.size());
+    return KCRN_OK;
+}
+
+int kcrn_plan_persist(const int32_t *indptr_host, int64_t n_segments, int grid, int32_t *tiles12_host, int64_t tiles_cap,
+                      int64_t *n_tiles, int32_t *longtab4_host, int64_t long_cap, int64_t *n_long, int *fits) {
+    if (!indptr_host || n_segments < 0 || !n_tiles || !n_long || !fits) { set_error("kcrn_plan_persist: bad argument"); return KCRN_E_ARG; }
+    std::vector<int32_t> ptr(indptr_host, indptr_host + n_segments + 1);
+    std::vector<PTile> tiles;
+    std::vector<int4> longtab;
+    int npartial = 0;
+    *fits = plan_persist_tiles(ptr, n_segments, ptr[(size_t)n_segments], grid, tiles, longtab, npartial) ? 1 : 0;
+    *n_tiles = (int64_t)tiles.size();
+    *n_long = (int64_t)longtab.size();
+    static_assert(sizeof(PTile) == 12 * sizeof(int32_t), "PTile = 12 ints");
+    if (tiles4_ok(tiles12_host, tiles.size(), tiles_cap)) memcpy(tiles12_host, tiles.data(), sizeof(PTile) * tiles.size());
     if (longtab4_host && (int64_t)longtab.size() <= long_cap) memcpy(longtab4_host, longtab.data(), sizeof(int4) * longtab.size());
     return KCRN_OK;
 }

@@ -86,7 +86,6 @@ struct SegMat {
     // keeps its order and its bits.  Null when gather_len does not fit the word (sweeps then use idx / val).
     uint32_t *gidx = nullptr;    // [nnz]
     double *gval = nullptr;      // [nnz] values in the same order
-    uint16_t *gslot = nullptr;   // [nnz] natural positions on their own (experimental: gather lengths beyond 2^20), else null
     // which gather variant of the sweep kernel (kcrn_sweep.cu: GatherVariant) serves this matrix, measured at
     // set-up: one choice for the Lanczos passes, one for all others
     int gather_plain = 0, gather_lanczos = 0;
@@ -94,6 +93,37 @@ struct SegMat {
     int32_t *segid = nullptr;    // [nseg] original column of the s-th stored segment (null: natural order)
     int32_t *pos = nullptr;      // [nseg] where column c is stored
     std::vector<int32_t> cptr_host;   // canonical column pointer (natural order), for kcrn_csc_view
+};
+
+// ----------------------------------------------------------------------------- persistent recurrence (kcrn_persist.cu)
+// Small problems (every pass over A is at most one tile per SM): the whole Lanczos recurrence runs as ONE kernel of
+// one 1024-thread CTA per SM; kernel boundaries become grid barriers, the (constant) tile streams arrive by bulk
+// copy (cp.async.bulk + mbarrier) while the previous pass finishes, the recurrence state lives in registers.
+constexpr int kPThreads = 1024;
+constexpr int kPSlotBits = 14;                       // word = gather index << 14 | position inside the tile
+constexpr int kPCap = 12288;                         // entries per tile (capacity; tiles are balanced: about nnz / SMs)
+constexpr int kPSegs = 4096;                         // segments per tile
+constexpr int kPSplit = 1024;                        // segments longer than this may be cut at a tile boundary
+constexpr int kPBig = 1024;                          // local segments longer than this are summed by the whole CTA
+constexpr int kPMaxIndex = 1 << (32 - kPSlotBits);   // gather length the word can address
+
+struct PTile {             // one tile = the entries [e0, e0 + nk) of a matrix in stored order
+    int e0, nk;
+    int seg0, nseg;        // stored segments seg0 .. seg0 + nseg - 1 intersect it (first / last possibly as pieces)
+    int lg;                // log2 of the number of threads that share one short segment
+    int head_long, head_piece;   // >= 0: local segment 0 is piece `head_piece` of cut segment `head_long` (longtab)
+    int tail_long, tail_piece;   // the same for local segment nseg - 1
+    int pad[3];            // [0], [1]: slot of the head / tail piece among the matrix's piece sums
+};
+static_assert(sizeof(PTile) == 48, "tile descriptor = three 16-byte words");
+
+struct PersistMat {
+    PTile *tiles = nullptr;
+    int ntiles = 0;
+    uint32_t *word = nullptr;    // [ntiles][kPCap] words of the tile in gather order
+    double *tval = nullptr;      // [ntiles][kPCap] values in the same order
+    int4 *longtab = nullptr;     // cut segments: {first piece slot, pieces, stored segment, 0}
+    int nlong = 0, npartial = 0; // cut segments, pieces
 };
 
 // Device-resident state of the outer loop (kcrn_krylov_run): what Cubic_Krylov_LS carries from one iteration to
@@ -217,6 +247,15 @@ struct kcrn_problem {
     // the one-GPU test suite
     bool emulate_sharded = false;
     bool sharded() const { return world > 1 || emulate_sharded; }
+    // persistent recurrence (kcrn_persist.cu); persist_ok: both matrices fit one tile per SM
+    kcrn::PersistMat prow, pcol;
+    bool persist_ok = false;
+    int persist_grid = 0;
+    double *gp = nullptr, *wpp = nullptr, *Vp = nullptr;   // gradient, w', basis in the stored column order of the CSC copy
+    uint4 *pslots = nullptr;       // exchange slots {value.lo, epoch, value.hi, epoch}: [2][2][grid] per CTA, [2][piece_cap] per piece
+    int piece_cap = 0;
+    unsigned *pbar = nullptr;      // [0] exchanges done so far (epoch of the slots)
+    long long *ptrace = nullptr;   // KCRN_PERSIST_TRACE=1: SM clock at the marks of the last launch
     bool lanczos_tuned = false;    // the gather variants of the Lanczos passes have been measured (first use)
     bool pdl = false;              // launch with programmatic dependent launch (set while the Lanczos graph is built)
     bool allow_pdl = true;         // KCRN_NO_PDL=1 switches it off
@@ -246,7 +285,7 @@ bool lanczos_defer_fits(const kcrn_problem *h);      // small grids only: see kc
 int launch_derive_from_Ax(kcrn_problem *h);
 int tune_plain_sweeps(kcrn_problem *h);               // once per handle, at the end of kcrn_create
 void forced_gather_variants(int *plain, int *lanczos);   // KCRN_GATHER override, -1 = measure
-int gather_candidates_last();                            // last variant the tuners try (the experimental one only on request)
+int gather_candidates_last();                            // last variant the tuners try
 
 // ----------------------------------------------------------------------------- kcrn_lanczos.cu
 int lanczos_alloc(kcrn_problem *h, int m);
@@ -265,6 +304,14 @@ int launch_sum(kcrn_problem *h, const double *a, int64_t len, double scale, doub
 int launch_axpy_basis(const double *x, const double *V, const double *s, int m, const int32_t *info,
                       int64_t d, double *out, cudaStream_t st, double *partials = nullptr,
                       unsigned *ticket = nullptr, double *step_norm = nullptr);
+
+// ----------------------------------------------------------------------------- kcrn_persist.cu
+int persist_build(kcrn_problem *h);                   // end of kcrn_create: plans the tiles when the problem is small enough
+int persist_alloc(kcrn_problem *h, int m);            // permuted basis for m columns
+void persist_free(kcrn_problem *h);
+int launch_persist_lanczos(kcrn_problem *h, int m);   // the whole m-step recurrence, one kernel
+bool plan_persist_tiles(const std::vector<int32_t> &ptr, int64_t nseg, int64_t nnz, int grid, std::vector<PTile> &tiles,
+                        std::vector<int4> &longtab, int &npartial);   // host only
 
 // ----------------------------------------------------------------------------- kcrn_cubic.cu
 int launch_cubic(const double *alphas, const double *betas, int m, const int32_t *info,

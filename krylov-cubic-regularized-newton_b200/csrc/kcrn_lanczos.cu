@@ -592,6 +592,7 @@ int lanczos_alloc(kcrn_problem *h, int m) {
     const size_t width = (size_t)m + 1;
     const size_t rows = (size_t)std::max(std::max(h->vec_grid, kNumSm * 8), std::max(h->csc.grid, h->csr.grid));
     KCRN_CUDA(cudaMalloc(&h->red_partials, sizeof(double) * rows * width));
+    KCRN_TRY(persist_alloc(h, m));
     h->m_cap = m;
     return KCRN_OK;
 }

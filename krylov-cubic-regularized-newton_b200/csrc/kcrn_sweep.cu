@@ -49,12 +49,11 @@ namespace kcrn {
 //   kGatherAsync    entries in gather order, LDGSTS (8-byte cp.async) straight into the natural slot: no registers
 //                   are held while the gathers are in flight (the Lanczos passes, which carry the most state,
 //                   then compile without spills) and the values are read in their stored order
-//   kGatherStaged   EXPERIMENTAL (never chosen unless KCRN_GATHER=3 / KCRN_GATHER_TRY_STAGED=1; compiled, not yet run
-//                   on a GPU): entries in gather order, the VALUES travel to shared memory in 16-byte cp.async
-//                   (requested before the wait for the previous kernel, no registers), the gathers use LDG; aims at
-//                   the register relief of kGatherAsync without LDGSTS's issue rate
-enum GatherVariant { kGatherStored = 0, kGatherOrdered = 1, kGatherAsync = 2, kGatherStaged = 3 };
-constexpr int kGatherVariants = 4;
+// (Two more were built and measured on a B200 in round 2 and dropped -- profiles/r2a_variants.txt: values staged in
+// shared memory with 16-byte cp.async, 23.8 vs 20.7 us per HVP; separate 16-bit natural positions for gather lengths
+// beyond 2^20, 283 vs 288 us per 4-step recurrence at the news20 shape.)
+enum GatherVariant { kGatherStored = 0, kGatherOrdered = 1, kGatherAsync = 2 };
+constexpr int kGatherVariants = 3;
 // shared buffer of the per-segment sums; with asynchronous gathers the product buffer is busy receiving them, so
 // the pieces of the deferred sums are staged here instead
 constexpr int kSumCapAsync = kTileSegs + 256;
@@ -63,7 +62,7 @@ constexpr int kSumCapAsync = kTileSegs + 256;
 void free_segmat(SegMat *A) {
     cudaFree(A->ptr); cudaFree(A->idx); cudaFree(A->val); cudaFree(A->tiles); cudaFree(A->longtab);
     cudaFree(A->partial); cudaFree(A->longdot); cudaFree(A->ticket); cudaFree(A->segid); cudaFree(A->pos);
-    cudaFree(A->gidx); cudaFree(A->gval); cudaFree(A->gslot);
+    cudaFree(A->gidx); cudaFree(A->gval);
     *A = SegMat();
 }
 
@@ -154,44 +153,6 @@ __global__ void __launch_bounds__(kSweepThreads) gather_order_kernel(const int4 
     }
 }
 
-// The same for gather lengths beyond 2^20 (EXPERIMENTAL, KCRN_GATHER_WIDE=1; compiled, not yet run on a GPU): the
-// index keeps its own 32-bit word and the natural position travels in a separate 16-bit array (+2 B/nnz of traffic
-// for sweeps that are bound by the gathers at these sizes: CSR pass of news20-shaped data, CSC pass of C5).
-__global__ void __launch_bounds__(kSweepThreads) gather_order_wide_kernel(const int4 *__restrict__ tiles,
-                                                                          const int32_t *__restrict__ idx,
-                                                                          const double *__restrict__ val,
-                                                                          uint32_t *__restrict__ gidx,
-                                                                          uint16_t *__restrict__ gslot,
-                                                                          double *__restrict__ gval) {
-    __shared__ unsigned long long key[kSortCap];
-    const int4 td = tiles[blockIdx.x];
-    const int k0 = td.y, nk = td.w & 0xffff, tag = td.w >> 16, tid = threadIdx.x;
-    const bool stream = td.z > 0 && tag != kSingleTag;
-    for (int i = tid; i < kSortCap; i += kSweepThreads)
-        key[i] = i < nk ? ((unsigned long long)(uint32_t)idx[k0 + i] << kSlotBits) | (unsigned long long)i : ~0ull;
-    __syncthreads();
-    if (stream) {
-        int np = 2;
-        while (np < nk) np <<= 1;
-        for (int k = 2; k <= np; k <<= 1)
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int t = tid; t < (np >> 1); t += kSweepThreads) {
-                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
-                    const unsigned long long a = key[i], b = key[l];
-                    if ((a > b) == ((i & k) == 0)) { key[i] = b; key[l] = a; }
-                }
-                __syncthreads();
-            }
-    }
-    for (int i = tid; i < nk; i += kSweepThreads) {
-        const unsigned long long w = key[i];
-        const int slot = (int)(w & (kSortCap - 1));
-        gidx[k0 + i] = (uint32_t)(w >> kSlotBits);
-        gslot[k0 + i] = (uint16_t)slot;
-        gval[k0 + i] = val[k0 + slot];
-    }
-}
-
 // The tile size is picked per matrix.  A sweep over a small (L2-resident) matrix is a handful of waves of CTA
 // tiles, each wave one latency chain long: what counts is the NUMBER OF WAVES, e.g. the rcv1-shape CSR copy is 732
 // tiles of 2048 -- two waves on 148 SMs x 4 CTAs, the second one a quarter full -- but 533 tiles of 2816: one wave
@@ -264,15 +225,6 @@ int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s) {
         KCRN_CUDA(cudaMemsetAsync(A->gval + A->nnz, 0, sizeof(double) * 2, s));
         gather_order_kernel<<<(unsigned)A->ntiles, kSweepThreads, 0, s>>>(A->tiles, A->idx, A->val, A->gidx, A->gval);
         KCRN_LAUNCH_CHECK();
-    } else if (A->nnz > 0 && A->ntiles > 0 && tile_nnz <= kSortCap && getenv("KCRN_GATHER_WIDE") != nullptr &&
-               getenv("KCRN_NO_GATHER_ORDER") == nullptr) {
-        // EXPERIMENTAL: gather lengths beyond 2^20 -- index and natural position in separate arrays
-        KCRN_CUDA(cudaMalloc(&A->gidx, sizeof(uint32_t) * (size_t)A->nnz));
-        KCRN_CUDA(cudaMalloc(&A->gslot, sizeof(uint16_t) * (size_t)A->nnz));
-        KCRN_CUDA(cudaMalloc(&A->gval, sizeof(double) * ((size_t)A->nnz + 2)));
-        KCRN_CUDA(cudaMemsetAsync(A->gval + A->nnz, 0, sizeof(double) * 2, s));
-        gather_order_wide_kernel<<<(unsigned)A->ntiles, kSweepThreads, 0, s>>>(A->tiles, A->idx, A->val, A->gidx, A->gslot, A->gval);
-        KCRN_LAUNCH_CHECK();
     }
     KCRN_CUDA(cudaStreamSynchronize(s));
     return KCRN_OK;
@@ -329,8 +281,6 @@ struct SweepParams {
     int alpha_mode;                // rows-Lanczos: 0 = finish alpha here, 1 = export the raw sums (row-sharded runs)
     double *alpha_raw, *alpha_raw2; // raw sums sum_i t_i (Av)_i (allreduced later) and |v|^2 for alpha_mode 1
     int update_ctl;                // cols-Lanczos: 1 = finish beta and advance the recurrence here
-    const uint16_t *gslot;         // natural positions on their own (wide gather lengths, experimental), else null: packed
-                                   // into gidx.  Last member: the layout the measured kernels were compiled against stays
 };
 
 struct SweepState {
@@ -465,16 +415,14 @@ __device__ __forceinline__ void defer_end(bool two, int n0, int n1, const double
     __syncthreads();      // sbuf (the product buffer of the tile) and sred are free again
 }
 
-template <int MODE, int kItems, int GATHER, bool WIDE = false>
+template <int MODE, int kItems, int GATHER>
 __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepParams P) {
-    static_assert(!WIDE || GATHER == kGatherOrdered || GATHER == kGatherAsync, "wide words: ordered / async variants only");
     constexpr int kTileNnz = kItems * kSweepThreads;       // non-zeros per CTA tile, kItems per thread
     constexpr bool ordered = GATHER != kGatherStored, kAsyncGather = GATHER == kGatherAsync;
-    constexpr bool kStaged = GATHER == kGatherStaged;      // values through shared memory (16-byte cp.async)
-    constexpr bool kBusyProd = kAsyncGather || kStaged;    // the product buffer is in use before the products exist
-    __shared__ alignas(kStaged ? 16 : 8) double sprod[kTileNnz + (kStaged ? 2 : 0)];   // products of the tile
-    __shared__ double ssum[kBusyProd ? kSumCapAsync : kTileSegs];   // per-segment sums of the tile
-    double *const spieces = kBusyProd ? ssum : sprod;      // staging of the deferred sums' pieces
+    __shared__ double sprod[kTileNnz];                     // products of the tile
+    __shared__ double ssum[kAsyncGather ? kSumCapAsync : kTileSegs];   // per-segment sums of the tile
+    double *const spieces = kAsyncGather ? ssum : sprod;   // staging of the deferred sums' pieces (the product buffer is
+                                                           // busy receiving the asynchronous gathers)
     __shared__ int sptr[kTileSegs + 8];          // segment pointers of the tile
     __shared__ double sred[2 * kSweepWarps];
     __shared__ int s_last;
@@ -487,7 +435,6 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
     const int tile = blockIdx.x;
     int4 td = make_int4(0, 0, 0, 0);
     int ci[kItems];                  // index, or gather-ordered word (index << kSlotBits | natural position); -1: none
-    int sl[WIDE ? kItems : 1];       // wide gather lengths: the natural position travels beside the index
     double av[kItems];
     if (tile < P.ntiles) {
         td = __ldg(P.tiles + tile);
@@ -498,15 +445,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         for (int r = 0; r < kItems; ++r) {
             const int i = r * kSweepThreads + tid;
             ci[r] = i < nk0 ? ld_stream(ip + i) : -1;
-            if constexpr (WIDE) sl[r] = i < nk0 ? (int)__ldg(P.gslot + td.y + i) : 0;
-            if constexpr (!kStaged) av[r] = i < nk0 ? ld_stream(vp + i) : 0.0;
-        }
-        if constexpr (kStaged) {
-            // values (gather order) -> sprod[(k0 & 1) + i] in aligned 16-byte pairs; a pair may reach one entry before
-            // or beyond the tile (allocated, never read back)
-            const int off = td.y & 1;
-            const double *v16 = P.gval + (td.y - off);
-            for (int q = 2 * tid; q < nk0 + off; q += 2 * kSweepThreads) cp_async_16(sprod + q, v16 + q);
+            av[r] = i < nk0 ? ld_stream(vp + i) : 0.0;
         }
         if (td.z > 0 && (td.w >> 16) != kSingleTag) {
 #pragma unroll
@@ -531,10 +470,9 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
             if constexpr (kAsyncGather) {
                 const int i = r * kSweepThreads + tid;
                 if (ci[r] != -1)
-                    cp_async_8(sprod + (WIDE ? sl[WIDE ? r : 0] : ordered ? (ci[r] & ((1 << kSlotBits) - 1)) : i),
-                               src + gather_index(ci[r], ordered && !WIDE));
+                    cp_async_8(sprod + (ordered ? (ci[r] & ((1 << kSlotBits) - 1)) : i), src + gather_index(ci[r], ordered));
             } else {
-                xv[r] = ci[r] != -1 ? __ldg(src + gather_index(ci[r], ordered && !WIDE)) : 0.0;
+                xv[r] = ci[r] != -1 ? __ldg(src + gather_index(ci[r], ordered)) : 0.0;
             }
         }
         if constexpr (kAsyncGather) cp_async_commit();
@@ -673,17 +611,6 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
                 xv[r] = i < nk ? sprod[i] : 0.0;
             }
         }
-        if constexpr (kStaged) {             // the values were copied by other threads of the CTA
-            cp_async_wait_all();
-            __syncthreads();
-            const int off = k0 & 1;
-#pragma unroll
-            for (int r = 0; r < kItems; ++r) {
-                const int i = r * kSweepThreads + tid;
-                av[r] = i < nk ? sprod[off + i] : 0.0;
-            }
-            __syncthreads();                 // all values are in registers: the buffer now takes the products
-        }
         double p[kItems];
 #pragma unroll
         for (int r = 0; r < kItems; ++r) {
@@ -720,8 +647,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
 #pragma unroll
             for (int r = 0; r < kItems; ++r) {
                 const int i = r * kSweepThreads + tid;
-                if (i < nk) sprod[WIDE && GATHER == kGatherOrdered ? sl[WIDE ? r : 0]
-                                  : GATHER == kGatherOrdered || kStaged ? (ci[r] & ((1 << kSlotBits) - 1)) : i] = p[r];   // the natural position
+                if (i < nk) sprod[GATHER == kGatherOrdered ? (ci[r] & ((1 << kSlotBits) - 1)) : i] = p[r];   // the natural position
             }
             cp_async_wait_all();
             __syncthreads();
@@ -820,17 +746,9 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
 }
 
 void fill_matrix(SweepParams &P, const SegMat &A) {
-    P.ptr = A.ptr; P.idx = A.idx; P.val = A.val; P.gidx = A.gidx; P.gval = A.gval; P.gslot = A.gslot; P.tiles = A.tiles; P.ntiles = A.ntiles;
+    P.ptr = A.ptr; P.idx = A.idx; P.val = A.val; P.gidx = A.gidx; P.gval = A.gval; P.tiles = A.tiles; P.ntiles = A.ntiles;
     P.longtab = A.longtab; P.segid = A.segid; P.partial = A.partial; P.longdot = A.longdot; P.ticket = A.ticket;
     P.nlong = A.nlong;
-}
-
-template <int MODE, int GATHER>
-int launch_variant_wide(kcrn_problem *h, const SegMat &A, const SweepParams &P) {
-    if (A.items == 11) KCRN_CUDA(launch_kernel(sweep_kernel<MODE, 11, GATHER, true>, dim3(A.grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
-    else if (A.items == 12) KCRN_CUDA(launch_kernel(sweep_kernel<MODE, 12, GATHER, true>, dim3(A.grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
-    else KCRN_CUDA(launch_kernel(sweep_kernel<MODE, 8, GATHER, true>, dim3(A.grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
-    return KCRN_OK;
 }
 
 template <int MODE, int GATHER>
@@ -846,11 +764,7 @@ template <int MODE>
 int launch(kcrn_problem *h, const SegMat &A, SweepParams &P) {
     fill_matrix(P, A);
     const int variant = !A.gidx ? kGatherStored : (MODE == kRowsLanczos || MODE == kColsLanczos ? A.gather_lanczos : A.gather_plain);
-    if (A.gslot && variant != kGatherStored) {       // wide gather lengths (experimental): ordered / async only
-        if (variant == kGatherAsync) KCRN_TRY((launch_variant_wide<MODE, kGatherAsync>(h, A, P)));
-        else KCRN_TRY((launch_variant_wide<MODE, kGatherOrdered>(h, A, P)));
-    } else if (variant == kGatherStaged) KCRN_TRY((launch_variant<MODE, kGatherStaged>(h, A, P)));
-    else if (variant == kGatherAsync) KCRN_TRY((launch_variant<MODE, kGatherAsync>(h, A, P)));
+    if (variant == kGatherAsync) KCRN_TRY((launch_variant<MODE, kGatherAsync>(h, A, P)));
     else if (variant == kGatherOrdered) KCRN_TRY((launch_variant<MODE, kGatherOrdered>(h, A, P)));
     else KCRN_TRY((launch_variant<MODE, kGatherStored>(h, A, P)));
     h->counters[0] += 1;
@@ -871,8 +785,6 @@ __global__ void derive_from_Ax_kernel(const double *__restrict__ Ax, const doubl
 
 }  // namespace
 
-int configure_sweep_kernels() { return KCRN_OK; }
-
 int launch_forward(kcrn_problem *h, const double *x) {
     SweepParams P{};
     P.src = x; P.b = h->b; P.Ax = h->Ax; P.D = h->D; P.resid = h->resid; P.ell = h->ell;
@@ -887,8 +799,7 @@ int launch_rows_weighted(kcrn_problem *h, const double *v) {
     return launch<kRowsWeighted>(h, h->csr, P);
 }
 
-// the experimental staged variant takes part in the measurement only on request
-int gather_candidates_last() { return getenv("KCRN_GATHER_TRY_STAGED") ? kGatherStaged : kGatherAsync; }
+int gather_candidates_last() { return kGatherAsync; }
 
 // KCRN_GATHER="p[,l]" forces the gather variant of the plain / Lanczos passes (A/B switch); -1: measure
 void forced_gather_variants(int *plain, int *lanczos) {

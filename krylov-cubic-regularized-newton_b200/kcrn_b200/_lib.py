@@ -30,6 +30,7 @@ SIGNATURES = {
     "kcrn_p2p_enable": (c_int, [c_void_p, c_int]),
     "kcrn_csc_view": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "kcrn_set_x": (c_int, [c_void_p, c_void_p]),
+    "kcrn_set_x_only": (c_int, [c_void_p, c_void_p]),
     "kcrn_value": (c_int, [c_void_p, c_void_p]),
     "kcrn_gradient": (c_int, [c_void_p, c_void_p]),
     "kcrn_hvp": (c_int, [c_void_p, c_void_p, c_void_p]),
@@ -64,6 +65,8 @@ SIGNATURES = {
     "kcrn_counters": (c_int, [c_void_p, POINTER(c_int64), c_int]),
     "kcrn_time_sweep": (c_int, [c_void_p, c_int, c_int, POINTER(c_double)]),
     "kcrn_gather_variants": (c_int, [c_void_p, POINTER(c_int)]),
+    "kcrn_plan_persist": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, POINTER(c_int64), c_void_p, c_int64,
+                                  POINTER(c_int64), POINTER(c_int)]),
     "kcrn_plan_tiles": (c_int, [c_void_p, c_int64, c_void_p, c_int64, POINTER(c_int64), c_void_p, c_int64,
                                 POINTER(c_int64), POINTER(c_int)]),
 }

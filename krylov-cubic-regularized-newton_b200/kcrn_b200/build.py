@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(PKG))
 CSRC = os.path.join(os.path.dirname(PKG), "csrc")
 OBJ = os.path.join(os.path.dirname(PKG), "build")
 LIB = os.path.join(PKG, "libkcrn.so")
-UNITS = ["kcrn_api", "kcrn_transpose", "kcrn_sweep", "kcrn_lanczos", "kcrn_cubic", "kcrn_config4", "kcrn_nccl", "kcrn_run", "kcrn_batch", "kcrn_svmlight"]
+UNITS = ["kcrn_api", "kcrn_transpose", "kcrn_sweep", "kcrn_lanczos", "kcrn_cubic", "kcrn_config4", "kcrn_nccl", "kcrn_run", "kcrn_batch", "kcrn_svmlight", "kcrn_persist"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]

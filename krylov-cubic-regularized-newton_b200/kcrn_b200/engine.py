@@ -150,6 +150,11 @@ class Engine:
         self._use_stream()
         check(self.lib.kcrn_set_x(self.h, self._vec(x, self.d, "x").data_ptr()))
 
+    def set_x_only(self, x):
+        """x moves, the cached A x does not (update_mat_vec_product overrides it until reset())."""
+        self._use_stream()
+        check(self.lib.kcrn_set_x_only(self.h, self._vec(x, self.d, "x").data_ptr()))
+
     def value_tensor(self, out=None):
         self._use_stream()
         out = self.new_vector(1) if out is None else out

@@ -97,6 +97,7 @@ class LogisticRegression(Oracle):
         self.device = self.engine.device
         self._x_key = None        # identity of the iterate the device caches belong to
         self._x_host = None       # numpy copy of it when the caller works with numpy
+        self._x_ref = None        # the remembered tensor itself: its address cannot be recycled while the key lives
         self.calls = {"value": 0, "gradient": 0, "hess_vec_prod": 0, "forward": 0}
 
     # ------------------------------------------------------------------ iterate handling
@@ -109,26 +110,40 @@ class LogisticRegression(Oracle):
         if self._x_key is None:
             return False
         if _is_tensor(x):
+            # same tensor object's storage, unmodified since it was remembered.  The remembered tensor is kept alive
+            # (self._x_ref), so the caching allocator cannot hand its address to a new temporary while the key lives.
             return self._x_key == (x.data_ptr(), x._version, tuple(x.shape))
         return self._x_host is not None and np.array_equal(x, self._x_host)
 
     def _remember(self, x):
         if _is_tensor(x):
-            self._x_key, self._x_host = (x.data_ptr(), x._version, tuple(x.shape)), None
+            self._x_key, self._x_host, self._x_ref = (x.data_ptr(), x._version, tuple(x.shape)), None, x
         else:
-            self._x_key, self._x_host = ("host",), np.array(x, dtype=np.float64, copy=True)
+            self._x_key, self._x_host, self._x_ref = ("host",), np.array(x, dtype=np.float64, copy=True), None
 
     def _forward(self, x):
-        """Make the device caches (A x, sigmoid, weights, residual, loss terms) belong to x."""
-        if self.reuse or (self.store_mat_vec_prod and self._same_iterate(x)):
+        """Make the device caches (A x, sigmoid, weights, residual, loss terms) belong to x (loss.py:266-277)."""
+        if self.store_mat_vec_prod and self.reuse:
+            # update_mat_vec_product overrides A x until reset(); the l2 terms still use the x passed in
+            # (loss.py:217 value, :247 partial_gradient), so the engine's copy of x follows it
+            if not self._same_iterate(x):
+                self.engine.set_x_only(self.to_device(x).contiguous())
+                self._remember(x)
+            return
+        if self.store_mat_vec_prod and self._same_iterate(x):
             return
         self.engine.set_x(self.to_device(x).contiguous())
         self.calls["forward"] += 1
         self._remember(x)
 
     def adopt_iterate(self, x):
-        """The engine already holds the caches of tensor x (set by a fused step)."""
+        """The engine already holds the caches of tensor x (set by a fused step that wrote x through its raw
+        pointer: the key is taken AFTER that write)."""
         self._remember(x)
+
+    def forget_iterate(self):
+        """The engine's caches no longer belong to any tensor the caller holds (it wrote through a raw pointer)."""
+        self._x_key, self._x_host, self._x_ref = None, None, None
 
     def _out(self, t, like):
         return t if _is_tensor(like) else t.cpu().numpy()
@@ -195,7 +210,7 @@ class LogisticRegression(Oracle):
 
     def reset(self):
         self.reuse = False
-        self._x_key, self._x_host = None, None
+        self._x_key, self._x_host, self._x_ref = None, None, None
 
     # ------------------------------------------------------------------ small helpers of the surface
     @staticmethod

@@ -283,6 +283,63 @@ def trajectories():
         save(f"traj_{name}", **out)
 
 
+# ------------------------------------------------------------------ 5b. C3 (news20-shape, m = 50) and f*
+def formula_point(d, k):
+    """A deterministic non-trivial iterate both sides can rebuild (d = 1.36 M is too large to store)."""
+    i = np.arange(d, dtype=np.float64)
+    return 0.3 * np.cos(1e-3 * i * (k + 1)) + 0.05 * np.sin(0.37 * i)
+
+
+def news20():
+    """BASELINE configs[2]: teacher-forced single steps (from x0 and from two formula points) and a short free-running
+    trajectory with its self-noise envelope, all from the unmodified reference."""
+    P = make_problem("news20", seed=0)
+    m, iters = 50, 8
+    out = {"fp": np.array(P.fingerprint()), "nnz": np.array(P.nnz)}
+    variants = {"ref": run_reference(P, m, iters)[0],
+                "refrev": run_reference(P, m, iters, reverse=True)[0],
+                "ro": run_reference(P, m, iters, reorth=True)[0],
+                "rorev": run_reference(P, m, iters, reorth=True, reverse=True)[0]}
+    for vn, rec in variants.items():
+        for k, arr in rec.items():
+            if k != "x_final":
+                out[f"m{m}_{vn}_{k}"] = arr
+    states = {0: (P.x0, None, 1e-3, 0.1), 1: (formula_point(P.d, 1), None, 1e-5, 0.05),
+              2: (formula_point(P.d, 2), None, 4e-7, 0.01)}
+    for k, (x, val, M, r0) in states.items():
+        loss = LogisticRegression(P.scipy_csr(), P.b, l1=0, l2=0, store_mat_vec_prod=True)
+        opt = ref_cubic.Cubic_Krylov_LS(loss=loss, reg_coef=M, subspace_dim=m, tolerance=1e-9, label="g")
+        opt.init_run(x)
+        opt.value, opt.r0 = val, r0
+        opt.step()
+        out[f"m{m}_state{k}_scal"] = np.array([np.nan, M, r0])
+        out[f"m{m}_state{k}_xnext_norm"] = np.array([np.linalg.norm(opt.x), np.linalg.norm(opt.x - x)])
+        out[f"m{m}_state{k}_next"] = np.array([opt.value, opt.reg_coef, opt.r0, opt.solver_it])
+        print("news20 state", k, out[f"m{m}_state{k}_next"], out[f"m{m}_state{k}_xnext_norm"])
+    save("traj_news20", **out)
+
+
+def fstar():
+    """f* per data set for the suboptimality f(x_k) - f* (SURVEY 8(d) step 3): the minimum over EVERYTHING the
+    reference evaluated on that input (loss.py:70-72 keeps f_opt per oracle; cubic_newton.py:140 takes the minimum
+    over all methods run) -- here every stored variant plus one long re-orthogonalised run, which goes lowest."""
+    out = {}
+    for name, m, iters in (("small", 10, 90), ("w8a", 10, 90), ("rcv1", 50, 100), ("news20", 50, 14)):
+        P = make_problem(name, seed=0)
+        rec, _ = run_reference(P, m, iters, reorth=True)
+        best = float(rec["f_opt"])
+        path = os.path.join(HERE, f"traj_{name}.npz")
+        if os.path.exists(path):
+            with np.load(path) as z:
+                for k in z.files:
+                    if k.endswith("_f_opt"):
+                        best = min(best, float(z[k]))
+        out[name] = np.array(best)
+        out[name + "_long_f"] = rec["f"]
+        print(name, "f* = %.12e after %d iterations" % (best, len(rec["f"])))
+    save("fstar", **out)
+
+
 # ------------------------------------------------------------------ 6. config-4 baselines (cubic.py:115-235, 321-408)
 def config4():
     """SSCN (m = 10, 50) and full-Hessian CRN on the 'small' problem, plus the same runs on row-reversed data
@@ -323,10 +380,12 @@ def config4():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["prims", "oracle_methods", "lanczos", "cubic", "traj", "config4"]
+    which = sys.argv[1:] or ["prims", "oracle_methods", "lanczos", "cubic", "traj", "config4", "news20", "fstar"]
     if "config4" in which: config4()
     if "prims" in which: prims()
     if "oracle_methods" in which: oracle_methods()
     if "lanczos" in which: lanczos_cases()
     if "cubic" in which: cubic_cases()
     if "traj" in which: trajectories()
+    if "news20" in which: news20()
+    if "fstar" in which: fstar()

@@ -124,7 +124,8 @@ def test_bench_reference_arm_prints_the_contract_line():
     line = json.loads(lines[0])
     assert line["impl"] == "reference" and line["metric"] == "krylov_crn_hvps_per_sec" and line["unit"] == "HVP/s"
     assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] == 2
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    installed = os.path.isdir(os.path.join(root, "baseline", "_ref", "optimizer"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if installed else "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"]
@@ -218,5 +219,105 @@ def test_tile_plan_invariants_hypothesis():
                         max_size=400))
     def run(lengths):
         _check_tiling(lengths)
+
+    run()
+
+
+# ------------------------------------------------------------------ balanced one-tile-per-SM plan (kcrn_persist.cu)
+def _plan_persist(indptr, grid):
+    from ctypes import byref, c_int, c_int64
+    from kcrn_b200 import _lib
+    lib = _lib.load()
+    indptr = np.ascontiguousarray(indptr, np.int32)
+    nseg = indptr.size - 1
+    nt, nl, fits = c_int64(), c_int64(), c_int()
+    _lib.check(lib.kcrn_plan_persist(indptr.ctypes.data, nseg, grid, None, 0, byref(nt), None, 0, byref(nl), byref(fits)))
+    tiles = np.zeros((max(nt.value, 1), 12), np.int32)
+    longtab = np.zeros((max(nl.value, 1), 4), np.int32)
+    _lib.check(lib.kcrn_plan_persist(indptr.ctypes.data, nseg, grid, tiles.ctypes.data, tiles.shape[0], byref(nt),
+                                     longtab.ctypes.data, longtab.shape[0], byref(nl), byref(fits)))
+    return tiles[:nt.value], longtab[:nl.value], bool(fits.value)
+
+
+def _check_persist_plan(lengths, grid=148, must_fit=None):
+    lengths = np.asarray(lengths, np.int64)
+    indptr = np.concatenate(([0], np.cumsum(lengths))).astype(np.int32)
+    nseg, nnz = lengths.size, int(indptr[-1])
+    tiles, longtab, fits = _plan_persist(indptr, grid)
+    if must_fit is not None:
+        assert fits == must_fit
+    if not fits:
+        return None
+    assert 1 <= len(tiles) <= grid
+    seg_whole = np.zeros(nseg, np.int64)
+    pieces = {}
+    e = 0
+    for (e0, nk, seg0, ns, lg, hl, hp, tl, tp, *_pad) in tiles.tolist():
+        assert e0 == e and 0 <= nk <= 12288 and 1 <= ns <= 4096 and 0 <= lg <= 5
+        e += nk
+        local = 0
+        for i in range(ns):
+            sg = seg0 + i
+            a, b = max(int(indptr[sg]), e0), min(int(indptr[sg + 1]), e0 + nk)
+            ln = max(0, b - a)
+            local += ln
+            cut = (i == 0 and hl >= 0) or (i == ns - 1 and tl >= 0)
+            if cut:
+                l, p = (hl, hp) if (i == 0 and hl >= 0) else (tl, tp)
+                if i == 0 and hl >= 0 and i == ns - 1 and tl >= 0:
+                    assert (hl, hp) == (tl, tp)                 # a middle piece: the whole tile inside one segment
+                assert longtab[l][2] == sg and lengths[sg] > 1024 and ln > 0
+                pieces.setdefault(l, []).append((p, a, b))
+            else:
+                assert a == indptr[sg] and b == indptr[sg + 1], "an uncut segment lies whole inside its tile"
+                seg_whole[sg] += 1
+        assert local == nk
+    assert e == nnz
+    slots = []
+    for l, (slot0, npieces, sg, _z) in enumerate(longtab.tolist()):
+        got = sorted(pieces[l])
+        assert [p for p, _, _ in got] == list(range(npieces)) and npieces >= 2
+        assert got[0][1] == indptr[sg] and got[-1][2] == indptr[sg + 1]
+        for (_, _, b0), (_, a1, _) in zip(got, got[1:]):
+            assert b0 == a1                                     # the pieces tile the segment in order
+        assert seg_whole[sg] == 0
+        seg_whole[sg] += 1
+        slots.append((slot0, npieces))
+    assert np.all(seg_whole == 1)                               # every segment (empty ones too) exactly once
+    slots.sort()
+    for (a, na), (b, _) in zip(slots, slots[1:]):
+        assert a + na <= b
+    sizes = tiles[:, 1]
+    return int(sizes.max()), int(sizes.min())
+
+
+def test_persist_plan_invariants():
+    rng = np.random.default_rng(1)
+    assert _check_persist_plan([5]) is not None
+    assert _check_persist_plan([0, 0, 3, 0]) is not None
+    _check_persist_plan(np.zeros(10, np.int64), must_fit=False)                         # no entries: per-pass kernels
+    mx, mn = _check_persist_plan(rng.poisson(74, 20242), must_fit=True)                 # rcv1-like rows
+    assert mx - mn <= 1024 and mx <= 10132 + 600
+    cols = np.sort(np.clip((1.33e5 / np.arange(1, 47237)).astype(np.int64), 0, None))   # Zipf columns, shortest first
+    mx, mn = _check_persist_plan(cols, must_fit=True)
+    _check_persist_plan(np.concatenate((rng.poisson(24, 49749), [49749] * 3)), must_fit=True)   # w8a-like + dense columns
+    _check_persist_plan([4000] * 300, must_fit=True)                                    # w8a-like columns: all cut
+    _check_persist_plan(rng.integers(0, 3, 400_000), must_fit=True)                     # tiny segments: the 4096-segment cap
+    _check_persist_plan(rng.integers(0, 3, 1_400_000), must_fit=False)                  # ... which no longer fits 148 tiles
+    _check_persist_plan(rng.poisson(74, 40000), must_fit=False)                         # 3 M entries: too large
+    _check_persist_plan([1_600_000], must_fit=True)                                     # one segment cut into 148 pieces
+    _check_persist_plan([1025, 1024, 1023] * 500, grid=7, must_fit=False)
+    for g in (1, 2, 5, 148):
+        _check_persist_plan(rng.integers(0, 2000, 40), grid=g)
+
+
+def test_persist_plan_hypothesis():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.one_of(st.integers(0, 40), st.integers(0, 3000), st.just(0), st.integers(1000, 30000)),
+                    min_size=1, max_size=300), st.integers(1, 40))
+    def run(lengths, grid):
+        _check_persist_plan(lengths, grid=grid)
 
     run()
