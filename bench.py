@@ -42,14 +42,14 @@ def measured_peak_gbs():
 
 
 def ncu_traffic(workload, which):
-    """DRAM bytes per launch of the CSR (0) / CSC (1) pass from the committed `ncu --set full` capture of this
-    workload (profiles/ncu_traffic.json); None when there is no capture for it."""
+    """DRAM bytes per launch of the CSR (0) / CSC (1) pass, or of the rows-Lanczos + columns-Lanczos pair (2), from the
+    committed `ncu --set full` capture of this workload (profiles/ncu_traffic.json); None when there is no capture."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             t = json.load(f)
         if t.get("workload") != workload:
             return None
-        return int(t["csc_pass_bytes_per_launch" if which else "csr_pass_bytes_per_launch"])
+        return int(t[("csr_pass_bytes_per_launch", "csc_pass_bytes_per_launch", "lanczos_pair_bytes_per_hvp")[which]])
     except Exception:
         return None
 
@@ -235,6 +235,130 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+NVLINK_GBS = 770.0      # measured peer copy per direction per GPU on this pool (B200_PROFILING.md); nominal 900
+
+
+def strong_case(tag, n, d, per_row, m, steps, rank, world, local, peak):
+    """One strong-scaled configuration of BASELINE.json (configs[2] news20-shape, configs[4] 1 B non-zeros): the SAME
+    global problem at every N -- n rows split evenly over the ranks, every rank generates its own rows on its device
+    (one shared column-popularity permutation) -- Krylov-CRN outer iterations with one allreduce of the d-vector per
+    transpose sweep.  Timed with CUDA events over `steps` outer iterations after one warm-up iteration, max over
+    ranks; clocks sampled during the timed region.  The step loop is what Cubic_Krylov_LS.step does
+    (optimizer/cubic.py: M = reg_coef * beta first, trial, M / beta on rejection)."""
+    import torch
+    import torch.distributed as dist
+    from kcrn_b200.dist import join_communicator
+    from kcrn_b200.engine import Engine
+    from kcrn_b200.synth import make_problem_device
+
+    n_loc = n // world
+    indptr, indices, data, b = make_problem_device(n_loc, d, float(per_row), seed=1000 + rank, perm_seed=7)
+    nnz = int(indices.numel())
+    eng = Engine(indptr, indices, data, b, (n_loc, d), n_global=n_loc * world)
+    del indptr, indices, data, b
+    torch.cuda.empty_cache()
+    if world > 1:
+        join_communicator(eng, rank, world)
+    x = torch.full((d,), 0.5, device="cuda", dtype=torch.float64)
+    state = {"x": x, "M": 1e-3, "r0": 0.1, "value": None, "hvps": 0}
+
+    def step():
+        eng.set_x(state["x"]) if state["value"] is None else None
+        if state["value"] is None:
+            state["value"] = eng.value()
+        M, tries, first = state["M"] * 0.5, 0, True
+        while True:
+            x_new = eng.new_vector()
+            val, dec, r, its, status, m_eff, gnorm, hv, dx = eng.krylov_trial(first, m, False, M, state["r0"], 1e-8, 100,
+                                                                               x_out=x_new)
+            if first:
+                state["hvps"] += hv
+            first = False
+            if not (val > state["value"] - dec and tries < 20):
+                break
+            M, tries = M / 0.5, tries + 1
+        state.update(x=x_new, M=M, r0=r, value=val)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    step()                                     # warm-up: captures the graphs, measures the gather variants
+    sync()
+    h0 = state["hvps"]
+    clk = ClockSampler(local)
+    clk.__enter__()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    sync()
+    clk.__exit__(None, None, None)
+    t = torch.tensor([e0.elapsed_time(e1), float(nnz)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms, nnz_total = float(tm[0].item()), int(t[1].item())
+    else:
+        ms, nnz_total = float(t[0].item()), nnz
+    hv = state["hvps"] - h0
+    us_hvp = 1e3 * ms / max(1, hv)             # whole step amortised per HVP (gradient, sub-problem, value included)
+    hbm_bytes = 24 * nnz + 28 * n_loc + 28 * d + 8                       # this rank's two sweeps (SURVEY 8(d))
+    ar_bytes = 2.0 * (world - 1) / world * 8 * d if world > 1 else 0.0    # ring allreduce of the d-vector, per rank
+    roof_us = hbm_bytes / (peak * 1e9) * 1e6 + ar_bytes / (NVLINK_GBS * 1e9) * 1e6
+    out = {"workload": f"{tag}: n={n_loc * world} d={d} nnz={nnz_total}, Krylov CRN m={m}, rows split evenly over {world} GPU(s)",
+           "scaling": "strong", "hvps_per_sec": 1e6 / us_hvp, "outer_iters_per_sec": 1e3 * steps / ms, "steps": steps,
+           "us_per_hvp_in_step": us_hvp, "hvps_per_step": hv / steps,
+           "roofline": {"hbm_bytes_per_rank": hbm_bytes, "allreduce_bytes_per_rank": ar_bytes, "roofline_us": roof_us,
+                        "frac": roof_us / us_hvp, "peak_hbm_gbs": peak, "nvlink_gbs": NVLINK_GBS},
+           "exchange": "NCCL allreduce" if world > 1 else "none", "clocks": clk.summary()}
+    eng.close()
+    del eng
+    torch.cuda.empty_cache()
+    return out
+
+
+def sharded_parity(loss, P, rank, world, workload):
+    """Row-sharded HVP / gradient / value against scipy on the STACKED matrix (rank 0 rebuilds every shard), and the
+    replicas against each other bit for bit."""
+    import scipy.sparse as sp
+    import scipy.special
+    import torch
+    import torch.distributed as dist
+
+    rng = np.random.default_rng(123)
+    x = 0.5 * np.ones(P.d) + 0.01 * rng.standard_normal(P.d)
+    v = rng.standard_normal(P.d)
+    xd, vd = loss.to_device(x), loss.to_device(v)
+    hv = loss.hess_vec_prod(xd, vd)
+    g = loss.gradient(xd)
+    f = torch.tensor([loss.value(xd)], dtype=torch.float64, device="cuda")
+    pack = torch.cat([hv, g, f])
+    every = [torch.empty_like(pack) for _ in range(world)]
+    dist.all_gather(every, pack)
+    if rank != 0:
+        return None
+    same = all(torch.equal(every[0], e) for e in every[1:])
+    shards = [make_shard(workload, r) for r in range(world)]
+    A = sp.vstack([s.scipy_csr() for s in shards]).tocsr()
+    b = (np.concatenate([s.b for s in shards]) + 1) / 2
+    n = A.shape[0]
+    Ax = A @ x
+    a = scipy.special.expit(Ax)
+    hv_ref = A.T @ (a * (1 - a) * (A @ v)) / n
+    g_ref = A.T @ (a - b) / n
+    f_ref = float(np.mean((1 - b) * Ax - np.where(Ax < -33, Ax, -np.log1p(np.exp(-np.clip(Ax, -700, 700))))))
+    got = every[0].cpu().numpy()
+    d = P.d
+    rel = lambda u, w: float(np.linalg.norm(u - w) / np.linalg.norm(w))
+    return {"replicas_bit_equal": bool(same), "hvp_rel_err": rel(got[:d], hv_ref), "grad_rel_err": rel(got[d:2 * d], g_ref),
+            "value_rel_err": abs(got[2 * d] - f_ref) / abs(f_ref), "against": "scipy on the stacked matrix of all shards"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -246,6 +370,8 @@ def main():
     ap.add_argument("--reorth", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-reps", type=int, default=200)
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaled C3 / C5 cases")
+    ap.add_argument("--c5-rows", type=float, default=10e6)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -370,46 +496,70 @@ def main():
     hvps2 = sum(h["hvps"] for h in opt2.history[n2:])
     e2e_value = world * hvps2 / (ms2 * 1e-3)
 
-    # ---------------- roofline of the dominant kernel, timed live (back-to-back launches, CUDA events)
+    # ---------------- roofline, timed live with CUDA events.  The kernels that own ~3/4 of a step are the two Lanczos
+    # instantiations of the sweep kernel (rows-Lanczos + columns-Lanczos = one HVP inside the captured recurrence), so
+    # THEY are the roofline entry; the plain passes (launched back to back as graph nodes) are kept as `other`.
     peak, peak_src = measured_peak_gbs()
     torch.cuda.synchronize()
     us = [eng.time_sweep(w, args.sweep_reps) for w in (0, 1)]
-    dom = int(us[1] >= us[0])
     gbs = [eng.sweep_bytes(w) / (us[w] * 1e-6) / 1e9 for w in (0, 1)]
     step_ms = ms / K
     hvp_us = 1e3 * step_ms / max(1.0, hvps / K)                 # whole step amortised per HVP
-    # the captured m-step Lanczos graph alone (m HVPs + the vector kernels between them), back to back, at x0 (late
+    # the captured m-step recurrence alone (m HVPs + the vector kernels between them), back to back, at x0 (late
     # iterates break down early -- cubic.py:98 -- and the rest of the graph is no-op nodes)
     eng.set_x(loss.to_device(P.x0))
     eng.gradient(keep_internal=True)
-    for _ in range(3):
-        eng.lanczos(args.m, bool(args.reorth))
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 20
-    g0.record()
-    for _ in range(reps):
-        eng.lanczos(args.m, bool(args.reorth))
-    g1.record()
-    torch.cuda.synchronize()
-    graph_us = 1e3 * g0.elapsed_time(g1) / reps
-    graph_hvps = int(eng.lanczos_view()[3][3].item())
+
+    def time_recurrence(m, reorth, reps=20):
+        for _ in range(3):
+            eng.lanczos(m, reorth)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(reps):
+            eng.lanczos(m, reorth)
+        g1.record()
+        torch.cuda.synchronize()
+        return 1e3 * g0.elapsed_time(g1) / reps, int(eng.lanczos_view()[3][3].item())
+
+    graph_us, graph_hvps = time_recurrence(args.m, bool(args.reorth))
     lan_us = graph_us / max(1, graph_hvps)
+    # full re-orthogonalisation (north_star K6; lanczos_update_kernel stages 1-3): cost of the recurrence with it minus
+    # without, against the bytes of V it reads (three passes over V[:j+1] per step as implemented)
+    reorth_info = None
+    if world == 1:
+        reorth_info = {}
+        for mm in sorted({args.m, 50}):
+            t0, h0 = time_recurrence(mm, False, reps=10)
+            t1, h1 = time_recurrence(mm, True, reps=10)
+            vbytes = 3 * 8 * P.d * sum(j + 1 for j in range(mm - 1))
+            extra = max(t1 - t0, 1e-3)
+            reorth_info[f"m{mm}"] = {"recurrence_us": t1, "recurrence_us_without": t0, "hvps": h1,
+                                     "reorth_us_per_step": extra / max(1, mm - 1), "basis_bytes": vbytes,
+                                     "achieved_gbs": vbytes / (extra * 1e-6) / 1e9, "frac": vbytes / (extra * 1e-6) / 1e9 / peak}
+        eng.lanczos(args.m, bool(args.reorth))
     gather_variants = eng.gather_variants()       # which sweep-kernel variant the engine measured fastest per matrix
     clk.__exit__(None, None, None)
     clocks = clk.summary()
+    dom = int(us[1] >= us[0])
     roofline = {
-        "bound": "hbm", "achieved": gbs[dom], "peak": peak, "unit": "GB/s", "frac": gbs[dom] / peak,
-        "traffic": ncu_traffic(args.workload, dom),
-        "kernel": "sweep_kernel<kColsScaled> (CSC pass: A' t)" if dom else "sweep_kernel<kRowsWeighted> (CSR pass: D.*(A v))",
-        "kernel_us": us[dom], "algorithmic_bytes": eng.sweep_bytes(dom), "peak_source": peak_src,
-        "other_pass": {"kernel_us": us[1 - dom], "achieved": gbs[1 - dom], "frac": gbs[1 - dom] / peak},
+        "bound": "hbm", "achieved": eng.hvp_bytes() / (lan_us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+        "frac": eng.hvp_bytes() / (lan_us * 1e-6) / 1e9 / peak,
+        "traffic": ncu_traffic(args.workload, 2),
+        "kernel": "sweep_kernel<kRowsLanczos> + sweep_kernel<kColsLanczos>: one HVP inside the captured Lanczos recurrence "
+                  "(the pair is timed: CUDA events around the graph, divided by its HVPs)",
+        "kernel_us": lan_us, "algorithmic_bytes": eng.hvp_bytes(), "peak_source": peak_src,
+        "other": {"kernel": "plain passes kRowsWeighted / kColsScaled, back to back as graph nodes",
+                  "kernel_us": us, "achieved": gbs, "frac": [g / peak for g in gbs],
+                  "traffic": [ncu_traffic(args.workload, 0), ncu_traffic(args.workload, 1)]},
         "hvp": {"bytes": eng.hvp_bytes(), "us_two_sweeps": us[0] + us[1],
                 "frac_two_sweeps": eng.hvp_bytes() / ((us[0] + us[1]) * 1e-6) / 1e9 / peak,
                 "us_in_lanczos_graph": lan_us, "frac_in_lanczos_graph": eng.hvp_bytes() / (lan_us * 1e-6) / 1e9 / peak,
                 "us_in_step": hvp_us, "frac_in_step": eng.hvp_bytes() / (hvp_us * 1e-6) / 1e9 / peak},
+        "reorth": reorth_info,
         "note": "CSR+CSC of this shape (36 MB) are L2-resident between sweeps, as in the real Lanczos loop; "
                 "fractions are algorithmic bytes over the measured HBM copy peak",
     }
+    parity = sharded_parity(loss, P, rank, world, args.workload) if world > 1 else None
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -426,11 +576,25 @@ def main():
         "gather_variants": gather_variants,
         "roofline": roofline, "clocks": clocks, "device_loop": device_loop,
     }
+    if parity is not None:
+        line["parity"] = parity
+    eng.close()
+    del opt, opt2, loss, eng
+    torch.cuda.empty_cache()
+    if not args.no_strong:
+        # the strong-scaled configurations the north star names, the same global problem at every N
+        strong = {}
+        for tag, n_, d_, per_row, m_, steps_ in (("c3 news20-shape", 19996, 1355191, 450.0, 50, 8),
+                                                  ("c5 1e9 non-zeros", int(args.c5_rows), 1000000, 116.0, 100, 2)):
+            try:
+                strong[tag.split()[0]] = strong_case(tag, n_, d_, per_row, m_, steps_, rank, world, local, peak)
+            except Exception as e:
+                strong[tag.split()[0]] = {"unavailable": f"{type(e).__name__}: {str(e)[:300]}"}
+        line["strong"] = strong
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_reference(args.workload, args.m, min(K, 20), 3)[4]
     if rank == 0:
         print(json.dumps(line), flush=True)
-    eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

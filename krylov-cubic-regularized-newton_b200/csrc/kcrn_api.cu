@@ -58,6 +58,8 @@ int upload(T **dst, const T *src, size_t count, int on_device, cudaStream_t s) {
     return KCRN_OK;
 }
 
+int enqueue_value_slow(kcrn_problem *h, double *out);
+
 int need_x(kcrn_problem *h, const char *what) {
     if (!h) { set_error("%s: null handle", what); return KCRN_E_ARG; }
     if (!h->have_x) { set_error("%s: no current x (call kcrn_set_x first)", what); return KCRN_E_STATE; }
@@ -65,17 +67,28 @@ int need_x(kcrn_problem *h, const char *what) {
 }
 
 // transpose sweep with the 1/n (+ l2 u) epilogue, allreduced when the rows are sharded
-int cols_product(kcrn_problem *h, const double *src, const double *u, double *out) {
+int cols_product(kcrn_problem *h, const double *src, const double *u, double *out, bool for_lanczos = false) {
     if (h->sharded()) {
         KCRN_TRY(launch_cols_raw(h, src, h->ypart));
         if (h->p2p_ready) return launch_scale_peer(h, h->ypart, u, out);     // the sum over the ranks inside
         KCRN_TRY(nccl_allreduce_sum(h, h->ypart, h->d));
         return launch_scale(h, h->ypart, u, out);
     }
-    return launch_cols_scaled(h, src, u, out);
+    // for_lanczos: this is the gradient a fused recurrence starts from -- leave the pieces of |g|^2 for its first sweep
+    return launch_cols_scaled(h, src, u, out, for_lanczos ? h->lan_cols_part : nullptr);
 }
 
-int enqueue_value(kcrn_problem *h, double *out) {
+// with_record: also assemble the 12-double step record (what launch_record does) -- the callers inside the step graphs
+int enqueue_value(kcrn_problem *h, double *out, int with_record = 0) {
+    if (h->fwd_parts_valid && !h->sharded()) {          // the forward sweep left per-tile sums: one kernel
+        if (h->l2 != 0.0) KCRN_TRY(launch_sumsq(h, h->x_cur, h->d, h->scal + 2));
+        return launch_value_record(h, out, with_record && out == h->scal);
+    }
+    KCRN_TRY(enqueue_value_slow(h, out));
+    return with_record ? launch_record(h) : KCRN_OK;
+}
+
+int enqueue_value_slow(kcrn_problem *h, double *out) {
     KCRN_TRY(launch_sum(h, h->ell, h->n, 1.0, h->scal + 1));
     if (h->l2 != 0.0) KCRN_TRY(launch_sumsq(h, h->x_cur, h->d, h->scal + 2));
     if (h->world > 1 && h->p2p_ready) return launch_value_combine_peer(h, out);
@@ -84,7 +97,8 @@ int enqueue_value(kcrn_problem *h, double *out) {
 }
 
 // the whole m-step recurrence, enqueued on h->stream (captured into a graph by kcrn_lanczos)
-int enqueue_lanczos(kcrn_problem *h, int m, int reorth, bool allow_persist = true) {
+// g_pieces: the gradient sweep right in front left the pieces of |g|^2 (cols_product(..., for_lanczos = true))
+int enqueue_lanczos(kcrn_problem *h, int m, int reorth, bool allow_persist = true, bool g_pieces = false) {
     // small single-GPU problems: the whole recurrence is one persistent kernel (kcrn_persist.cu)
     if (allow_persist && h->persist_ok && !reorth && !h->sharded()) return launch_persist_lanczos(h, m);
     // single GPU: the grid-wide sums (alpha after the row sweep, beta after the column sweep) are finished by the
@@ -92,11 +106,12 @@ int enqueue_lanczos(kcrn_problem *h, int m, int reorth, bool allow_persist = tru
     // re-orthogonalisation kernel owns beta and the advance).  Row-sharded: 0, the exchange kernels own both.
     static const bool no_defer = getenv("KCRN_NO_DEFER") != nullptr;                 // A/B switch
     const int defer = (h->sharded() || no_defer || !lanczos_defer_fits(h)) ? 0 : (reorth ? 1 : 2);
-    KCRN_TRY(launch_lanczos_init(h, m));
+    const bool self_init = g_pieces && defer == 2;        // the first row sweep starts the recurrence itself
+    if (!self_init) KCRN_TRY(launch_lanczos_init(h, m));
     for (int slot = 0; slot < m; ++slot) {
         // rows sweep: t = D (A v), basis column, and alpha = v'Hv one sweep early (so that the column sweep can
         // form w' = Hv - beta v_prev - alpha v and beta = |w'| itself: two kernels per Lanczos step)
-        KCRN_TRY(launch_rows_lanczos(h, h->ypart + h->d, slot, defer));
+        KCRN_TRY(launch_rows_lanczos(h, h->ypart + h->d, slot, defer, self_init ? m : 0));
         if (h->sharded()) {
             KCRN_TRY(launch_cols_raw(h, h->t, h->ypart));
             if (h->p2p_ready) {
@@ -275,8 +290,8 @@ int build_run_graph(kcrn_problem *h, int m, int reorth, cudaGraphExec_t *exec_ou
         KCRN_CUDA(cudaGraphConditionalHandleCreate(&trial_loop, outer_body, 1, 0));
         KCRN_TRY(launch_run_begin(h, (unsigned long long)trial_loop));
         KCRN_CUDA(cudaMemcpyAsync(h->x_base, h->x_cur, sizeof(double) * h->d, cudaMemcpyDeviceToDevice, h->stream));
-        KCRN_TRY(cols_product(h, h->resid, h->l2 != 0.0 ? h->x_cur : nullptr, h->g));      // gradient
-        KCRN_TRY(enqueue_lanczos(h, m, reorth));
+        KCRN_TRY(cols_product(h, h->resid, h->l2 != 0.0 ? h->x_cur : nullptr, h->g, true));      // gradient
+        KCRN_TRY(enqueue_lanczos(h, m, reorth, true, true));
         h->counters[2] += m;
         KCRN_TRY(add_while_node(cap[1], trial_loop, &trial_body));
         int64_t outer_part[8];
@@ -292,8 +307,7 @@ int build_run_graph(kcrn_problem *h, int m, int reorth, cudaGraphExec_t *exec_ou
         KCRN_TRY(launch_axpy_basis(h->x_base, h->V, h->sub, m, h->info, h->d, h->x_cur, h->stream, h->red_partials,
                                    h->red_ticket + 5, h->scal + 3));
         KCRN_TRY(launch_forward(h, h->x_cur));
-        KCRN_TRY(enqueue_value(h, h->scal + 0));
-        KCRN_TRY(launch_record(h));
+        KCRN_TRY(enqueue_value(h, h->scal + 0, 1));
         KCRN_TRY(launch_run_decide(h, (unsigned long long)trial_loop));
         for (int i = 0; i < 8; ++i) h->run_delta[2][i] = h->counters[i] - mark[i];
         KCRN_CUDA(cudaStreamEndCapture(cap[2], nullptr));
@@ -398,6 +412,8 @@ int kcrn_create(kcrn_handle *out, int64_t n_rows, int64_t n_cols, int64_t nnz, c
         KCRN_CUDA(cudaMalloc(&h->resid, sizeof(double) * n));
         KCRN_CUDA(cudaMalloc(&h->ell, sizeof(double) * n));
         KCRN_CUDA(cudaMalloc(&h->t, sizeof(double) * n));
+        KCRN_CUDA(cudaMalloc(&h->fwd_part, sizeof(double) * (size_t)std::max(1, h->csr.grid)));
+        KCRN_CUDA(cudaMalloc(&h->fwd_longdot, sizeof(double) * (size_t)std::max(1, h->csr.nlong)));
         KCRN_CUDA(cudaMalloc(&h->ypart, sizeof(double) * (d + 2)));   // + sum_i t_i (Av)_i of the fused Lanczos step (+ pad)
         KCRN_CUDA(cudaMemsetAsync(h->ypart, 0, sizeof(double) * (d + 2), s));
         KCRN_CUDA(cudaMalloc(&h->w, sizeof(double) * d));
@@ -457,7 +473,7 @@ int kcrn_destroy(kcrn_handle h) {
     free_segmat(&h->csc);
     double *bufs[] = {h->b, h->x_base, h->step_params, h->x_cur, h->Ax, h->D, h->resid, h->ell, h->t, h->ypart, h->V, h->w, h->wp, h->g,
                       h->alphas, h->bet, h->coef, h->coef2, h->sub, h->scal, h->red_partials, h->x_stage,
-                      h->v_stage, h->o_stage};
+                      h->v_stage, h->o_stage, h->fwd_part, h->fwd_longdot};
     for (double *p : bufs) cudaFree(p);
     cudaFree(h->ctl); cudaFree(h->lan_rows_part); cudaFree(h->lan_cols_part);
     cudaFree(h->info);
@@ -645,6 +661,7 @@ int kcrn_set_Ax(kcrn_handle h, const double *Ax_dev) {
         KCRN_CUDA(cudaMemcpyAsync(h->Ax, Ax_dev, sizeof(double) * h->n, cudaMemcpyDeviceToDevice, h->stream));
     KCRN_TRY(launch_derive_from_Ax(h));
     h->have_x = true;
+    h->fwd_parts_valid = false;
     return KCRN_OK;
 }
 
@@ -684,8 +701,8 @@ int kcrn_krylov_trial(kcrn_handle h, int first, int m, int reorth, double M, dou
     KCRN_TRY(run_graph(h, first ? 1 : 2, m, reorth, [&]() -> int {
         if (first) {
             KCRN_CUDA(cudaMemcpyAsync(h->x_base, h->x_cur, sizeof(double) * h->d, cudaMemcpyDeviceToDevice, h->stream));
-            KCRN_TRY(cols_product(h, h->resid, h->l2 != 0.0 ? h->x_cur : nullptr, h->g));      // gradient
-            KCRN_TRY(enqueue_lanczos(h, m, reorth));
+            KCRN_TRY(cols_product(h, h->resid, h->l2 != 0.0 ? h->x_cur : nullptr, h->g, true));      // gradient
+            KCRN_TRY(enqueue_lanczos(h, m, reorth, true, true));
         }
         h->counters[0] += 2;
         KCRN_TRY(launch_cubic(h->alphas, h->bet + 1, m, h->info, h->bet, 0.0, 0.0, 0.0, 0.0, 0, h->sub, h->sub + kMaxM,
@@ -693,8 +710,7 @@ int kcrn_krylov_trial(kcrn_handle h, int first, int m, int reorth, double M, dou
         KCRN_TRY(launch_axpy_basis(h->x_base, h->V, h->sub, m, h->info, h->d, h->x_cur, h->stream, h->red_partials,
                                    h->red_ticket + 5, h->scal + 3));
         KCRN_TRY(launch_forward(h, h->x_cur));
-        KCRN_TRY(enqueue_value(h, h->scal + 0));
-        return launch_record(h);
+        return enqueue_value(h, h->scal + 0, 1);
     }));
     if (first) h->counters[2] += m;
     h->have_base = true;
@@ -903,6 +919,7 @@ int kcrn_partial_hessian(kcrn_handle h, const int64_t *I_dev, int m, double *out
 }
 int kcrn_update_Ax(kcrn_handle h, const int64_t *I_dev, const double *delta_dev, int m) {
     KCRN_TRY(need_x(h, "kcrn_update_Ax"));
+    h->fwd_parts_valid = false;
     return config4_update_Ax(h, I_dev, delta_dev, m);
 }
 

@@ -24,52 +24,65 @@ namespace kcrn {
 
 namespace {
 
-struct Tri {
-    double *a, *b;      // diagonal, off-diagonal
-    double *l, *e;      // Cholesky factor: diagonal, sub-diagonal
-    double *li;         // 1 / l (IEEE), so that the solves divide with three fused operations
-    double *s, *q;      // s_lam and (T + lam I)^-1 s_lam
-    int m;
-};
+// The arrays live in shared memory and are handed to the helpers as __restrict__ pointers: the compiler may then fetch
+// a[j + 1], b[j + 1], the factor's entries ... ahead of the dependent chain instead of serialising every load behind
+// the previous step's store.  The arithmetic stays the Cholesky sequence of LAPACK's dpotf2 / dpotrs on the two
+// diagonals (what the reference's dposv performs on this matrix): an L D L' variant with one division per row was
+// measured 3x faster but rounds differently, and the chaotic tails of two trajectory cases then left the 10x envelope
+// (profiles/r2i_pytest.log) -- parity first.
 
-// Cholesky of T + lam I; false when a pivot is not positive.
-__device__ bool factor(const Tri &t, double lam) {
-    double prev_e = 0.0;
-    for (int j = 0; j < t.m; ++j) {
-        double piv = t.a[j] + lam;
+// Cholesky of T + lam I fused with the forward substitution of (T + lam I) y = gnorm e1 (two independent chains in one
+// loop).  False when a pivot is not positive.
+__device__ __forceinline__ bool factor_forward(const double *__restrict__ a, const double *__restrict__ b,
+                                               double *__restrict__ l, double *__restrict__ li, double *__restrict__ e,
+                                               double *__restrict__ y, int m, double lam, double gnorm) {
+    double prev_e = 0.0, prev_y = 0.0;
+    for (int j = 0; j < m; ++j) {
+        double piv = a[j] + lam;
         piv = __dsub_rn(piv, __dmul_rn(prev_e, prev_e));
         if (!(piv > 0.0)) return false;
         const double lj = sqrt(piv);
         const double rj = 1.0 / lj;
-        t.l[j] = lj;
-        t.li[j] = rj;
-        if (j + 1 < t.m) {
-            prev_e = quotient(t.b[j], lj, rj);
-            t.e[j] = prev_e;
+        l[j] = lj;
+        li[j] = rj;
+        double v = j == 0 ? gnorm : 0.0;
+        if (j > 0) v = __dsub_rn(v, __dmul_rn(prev_e, prev_y));     // e[j - 1] * y[j - 1]
+        prev_y = quotient(v, lj, rj);
+        y[j] = prev_y;
+        if (j + 1 < m) {
+            prev_e = quotient(b[j], lj, rj);
+            e[j] = prev_e;
         }
     }
     return true;
 }
 
-// out = (T + lam I)^-1 rhs using the factor; rhs may alias out
-__device__ void solve(const Tri &t, const double *rhs, double *out) {
+// forward substitution with a general right-hand side
+__device__ __forceinline__ void forward(const double *__restrict__ l, const double *__restrict__ li,
+                                        const double *__restrict__ e, const double *__restrict__ rhs,
+                                        double *__restrict__ out, int m) {
     double prev = 0.0;
-    for (int j = 0; j < t.m; ++j) {
+    for (int j = 0; j < m; ++j) {
         double v = rhs[j];
-        if (j > 0) v = __dsub_rn(v, __dmul_rn(t.e[j - 1], prev));
-        prev = quotient(v, t.l[j], t.li[j]);
-        out[j] = prev;
-    }
-    prev = 0.0;
-    for (int j = t.m - 1; j >= 0; --j) {
-        double v = out[j];
-        if (j + 1 < t.m) v = __dsub_rn(v, __dmul_rn(t.e[j], prev));
-        prev = quotient(v, t.l[j], t.li[j]);
+        if (j > 0) v = __dsub_rn(v, __dmul_rn(e[j - 1], prev));
+        prev = quotient(v, l[j], li[j]);
         out[j] = prev;
     }
 }
 
-__device__ double sumsq(const double *x, int m) {
+// backward substitution in place; negate: the result is stored with its sign flipped (s = -(T + lam I)^-1 g)
+__device__ __forceinline__ void backward(const double *__restrict__ l, const double *__restrict__ li,
+                                         const double *__restrict__ e, double *__restrict__ x, int m, bool negate) {
+    double prev = 0.0;
+    for (int j = m - 1; j >= 0; --j) {
+        double v = x[j];
+        if (j + 1 < m) v = __dsub_rn(v, __dmul_rn(e[j], prev));
+        prev = quotient(v, l[j], li[j]);
+        x[j] = negate ? -prev : prev;
+    }
+}
+
+__device__ __forceinline__ double sumsq(const double *__restrict__ x, int m) {
     double acc = 0.0;
     for (int j = 0; j < m; ++j) acc = __dadd_rn(acc, __dmul_rn(x[j], x[j]));
     return acc;
@@ -94,20 +107,17 @@ __global__ void __launch_bounds__(32) cubic_kernel(const double *__restrict__ al
     double r = r0, dec = 0.0;
     int its = 0, status = 0;
     if (threadIdx.x == 0) {
-        Tri t{sa, sb, sl, se, sli, ss, sq, m};
         double p0 = r0, p = r0;
         bool finished = false;
         for (int itr = 0; itr < it_max && !finished; ++itr) {
-            if (!factor(t, p0)) { status = KCRN_E_NOTPD; r = p0; its = itr; finished = true; break; }
             // s = -(T + p0 I)^-1 g with g = gnorm e1
-            for (int j = 0; j < m; ++j) ss[j] = 0.0;
-            ss[0] = gnorm;
-            solve(t, ss, ss);
-            for (int j = 0; j < m; ++j) ss[j] = -ss[j];
+            if (!factor_forward(sa, sb, sl, sli, se, ss, m, p0, gnorm)) { status = KCRN_E_NOTPD; r = p0; its = itr; finished = true; break; }
+            backward(sl, sli, se, ss, m, true);
             const double ns = sqrt(sumsq(ss, m));
             const double fval = __dsub_rn(__dmul_rn(p0, p0), __dmul_rn(__dmul_rn(M, M), __dmul_rn(ns, ns)));
             if (fval == 0.0) { r = p0; its = itr; finished = true; break; }
-            solve(t, ss, sq);
+            forward(sl, sli, se, ss, sq, m);
+            backward(sl, sli, se, sq, m, false);
             double sdot = 0.0;
             for (int j = 0; j < m; ++j) sdot = __dadd_rn(sdot, __dmul_rn(ss[j], sq[j]));
             // 2 lam - M^2 * (-2 s.q)
@@ -119,13 +129,10 @@ __global__ void __launch_bounds__(32) cubic_kernel(const double *__restrict__ al
         }
         if (!finished) { r = p; its = it_max; }
         if (status == 0) {
-            if (!factor(t, r)) status = KCRN_E_NOTPD;
+            if (!factor_forward(sa, sb, sl, sli, se, ss, m, r, gnorm)) status = KCRN_E_NOTPD;
         }
         if (status == 0) {
-            for (int j = 0; j < m; ++j) ss[j] = 0.0;
-            ss[0] = gnorm;
-            solve(t, ss, ss);
-            for (int j = 0; j < m; ++j) ss[j] = -ss[j];
+            backward(sl, sli, se, ss, m, true);
             const double ns = sqrt(sumsq(ss, m));
             // r/2 |s|^2 - M/3 |s|^3 - <g, s>/2
             dec = (r / 2.0) * (ns * ns) - (M / 3.0) * (ns * ns * ns) - (gnorm * ss[0]) / 2.0;

@@ -206,6 +206,10 @@ struct kcrn_problem {
     unsigned *batch_ticket = nullptr;
     int batch_grid = 0;
     double *Ax = nullptr, *D = nullptr, *resid = nullptr, *ell = nullptr;  // [n]
+    // per-tile sums of the loss terms left by the forward sweep (+ the shares of long rows), added in tile order by
+    // value_record_kernel; invalid after kcrn_set_Ax / kcrn_update_Ax (those derive the terms without a sweep)
+    double *fwd_part = nullptr, *fwd_longdot = nullptr;
+    bool fwd_parts_valid = false;
     // sweep temporaries
     double *t = nullptr;        // [n]   D .* (A v)
     double *ypart = nullptr;    // [d]   local A' t before the allreduce (row-sharded runs)
@@ -276,10 +280,10 @@ void plan_tiles(const std::vector<int32_t> &ptr, int64_t nseg, int64_t nnz, std:
 void free_segmat(SegMat *A);
 int launch_forward(kcrn_problem *h, const double *x);                 // A x and everything derived
 int launch_rows_weighted(kcrn_problem *h, const double *v);           // t = D .* (A v)
-int launch_rows_lanczos(kcrn_problem *h, double *alpha_raw, int slot, int defer);          // same, source picked by ctl; sharded runs:
+int launch_rows_lanczos(kcrn_problem *h, double *alpha_raw, int slot, int defer, int init_m = 0);   // init_m > 0 (slot 0): starts the recurrence itself          // same, source picked by ctl; sharded runs:
                                                                       // raw alpha sum -> alpha_raw[0]
 int launch_cols_raw(kcrn_problem *h, const double *src, double *out); // out = A' src
-int launch_cols_scaled(kcrn_problem *h, const double *src, const double *u, double *out);  // A' src / n + l2 u
+int launch_cols_scaled(kcrn_problem *h, const double *src, const double *u, double *out, double *sq_part = nullptr);  // A' src / n + l2 u
 int launch_cols_lanczos(kcrn_problem *h, int update_ctl, int slot, int defer);
 bool lanczos_defer_fits(const kcrn_problem *h);      // small grids only: see kcrn_sweep.cu             // w' and beta fused
 int launch_derive_from_Ax(kcrn_problem *h);
@@ -301,6 +305,7 @@ int launch_run_commit(kcrn_problem *h, unsigned long long outer_loop);
 int launch_lanczos_post_peer(kcrn_problem *h, const double *y_partial, int reorth);
 int launch_normalise_current(kcrn_problem *h);        // V[col] = src / bet[col] outside the fused sweep
 int launch_sum(kcrn_problem *h, const double *a, int64_t len, double scale, double *out);  // deterministic sum
+int launch_value_record(kcrn_problem *h, double *out, int with_record);   // value from the forward sweep's tile sums (+ record)
 int launch_axpy_basis(const double *x, const double *V, const double *s, int m, const int32_t *info,
                       int64_t d, double *out, cudaStream_t st, double *partials = nullptr,
                       unsigned *ticket = nullptr, double *step_norm = nullptr);

@@ -461,6 +461,41 @@ __global__ void record_kernel(const double *__restrict__ scal, const double *__r
     }
 }
 
+// value (loss.py:215-220) straight from the forward sweep's per-tile sums -- tiles in tile order, then the shares of the
+// long rows: one kernel instead of reduce + combine (+ record)
+__global__ void __launch_bounds__(kVecThreads) value_record_kernel(const double *__restrict__ part, int count,
+                                                                   const double *__restrict__ longdot, int nlong,
+                                                                   const double *__restrict__ scal_in, double n_samples,
+                                                                   double l2, double *__restrict__ out,
+                                                                   const double *__restrict__ sub_tail,
+                                                                   const double *__restrict__ bet,
+                                                                   const int32_t *__restrict__ info, double *__restrict__ scal,
+                                                                   double *__restrict__ rec) {
+    __shared__ double sh[kVecThreads / 32];
+    pdl_wait();
+    double x = 0.0;
+    for (int i = threadIdx.x; i < count; i += kVecThreads) x += __ldcg(part + i);
+    for (int i = threadIdx.x; i < nlong; i += kVecThreads) x += __ldcg(longdot + i);
+    x = warp_sum(x);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < kVecThreads / 32; ++w) tot += sh[w];
+        double v = tot / n_samples;
+        if (l2 != 0.0) {
+            const double nx = sqrt(scal_in[2]);
+            v = __dadd_rn(v, __dmul_rn(l2 / 2.0, __dmul_rn(nx, nx)));
+        }
+        out[0] = v;
+        if (rec) {
+            rec[0] = v; rec[1] = sub_tail[1]; rec[2] = sub_tail[0]; rec[3] = sub_tail[2]; rec[4] = sub_tail[3];
+            rec[5] = (double)info[0]; rec[6] = bet[0]; rec[7] = (double)info[3]; rec[8] = scal[3];
+            rec[9] = (double)info[1]; rec[10] = (double)info[2]; rec[11] = 0.0;
+        }
+    }
+}
+
 // out = y / n + l2 u   (after the allreduce of a row-sharded transpose sweep)
 __global__ void scale_kernel(const double *__restrict__ y, const double *__restrict__ u, int64_t d,
                              double n_samples, double l2, double *__restrict__ out) {
@@ -699,6 +734,15 @@ int launch_sumsq(kcrn_problem *h, const double *a, int64_t len, double *out) {
 int launch_value_combine(kcrn_problem *h, double *out) {
     value_combine_kernel<<<1, 32, 0, h->stream>>>(h->scal, (double)h->n_global, h->l2, out);
     KCRN_LAUNCH_CHECK();
+    h->counters[0] += 1;
+    return KCRN_OK;
+}
+
+int launch_value_record(kcrn_problem *h, double *out, int with_record) {
+    KCRN_CUDA(launch_kernel(value_record_kernel, dim3(1), dim3(kVecThreads), 0, h->stream, h->pdl, (const double *)h->fwd_part,
+                            h->csr.grid, (const double *)h->fwd_longdot, h->csr.nlong, (const double *)h->scal,
+                            (double)h->n_global, h->l2, out, (const double *)(h->sub + kMaxM), (const double *)h->bet,
+                            (const int32_t *)h->info, h->scal, with_record ? h->scal + 4 : (double *)nullptr));
     h->counters[0] += 1;
     return KCRN_OK;
 }

@@ -281,6 +281,9 @@ struct SweepParams {
     int alpha_mode;                // rows-Lanczos: 0 = finish alpha here, 1 = export the raw sums (row-sharded runs)
     double *alpha_raw, *alpha_raw2; // raw sums sum_i t_i (Av)_i (allreduced later) and |v|^2 for alpha_mode 1
     int update_ctl;                // cols-Lanczos: 1 = finish beta and advance the recurrence here
+    // fused single-GPU loop (defer = 2) only:
+    int init_here, m_init;         // rows-Lanczos, first pass: |g| is still in the pieces the gradient sweep left; the
+                                   // recurrence state of an m_init-step run starts here (no separate init kernel)
 };
 
 struct SweepState {
@@ -308,7 +311,11 @@ __device__ __forceinline__ void finish_segment(const SweepParams &P, const Sweep
         P.Ax[seg] = sum;
         P.D[seg] = __dmul_rn(a, 1.0 - a);
         P.resid[seg] = a - op0;
-        P.ell[seg] = __dsub_rn(__dmul_rn(1.0 - op0, sum), log_sigmoid(sum));
+        const double el = __dsub_rn(__dmul_rn(1.0 - op0, sum), log_sigmoid(sum));
+        P.ell[seg] = el;
+        // share of the value (loss.py:215-220): summed per tile here, tiles in tile order by value_record_kernel
+        if (lseg >= 0) P.longdot[lseg] = el;
+        else acc += el;
     } else if constexpr (MODE == kRowsWeighted) {
         P.out[seg] = __dmul_rn(op0, sum);
     } else if constexpr (MODE == kRowsLanczos) {
@@ -324,6 +331,11 @@ __device__ __forceinline__ void finish_segment(const SweepParams &P, const Sweep
         double y = quotient(sum, P.n_samples, P.inv_n);
         if (P.add_l2) y = __dadd_rn(y, __dmul_rn(P.l2, op0));
         P.out[seg] = y;
+        if (P.red_partials) {                   // the gradient in front of a recurrence: pieces of |g|^2
+            const double prod = __dmul_rn(y, y);
+            if (lseg >= 0) P.longdot[lseg] = prod;
+            else acc += prod;
+        }
     } else {  // kColsLanczos
         double hv = __dadd_rn(quotient(sum, P.n_samples, P.inv_n), __dmul_rn(P.l2, op0));
         if (S.subtract) hv = __dsub_rn(hv, __dmul_rn(S.beta_prev, op1));
@@ -480,23 +492,45 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
     bool alpha_pending = false;
     LanczosCtl st_cols;
     if constexpr (MODE == kRowsLanczos) {
-        LanczosCtl st = *P.ctl_in;
         const bool scribe = blockIdx.x == 0 && tid == 0;      // the one thread that persists what all compute
-        if (st.done) {
-            if (scribe && P.ctl != P.ctl_in) *P.ctl = st;      // keep the pair in step
-            return;
-        }
-        if (P.advance_here) {
-            // beta = |w'| of the column sweep before us is still in pieces.  While they travel, gather from w'
-            // -- the source unless the recurrence breaks down right now, which the sum will tell
+        // Requests that do not depend on the control block go first: the pieces of the sum this kernel has to finish
+        // (beta = |w'| of the column sweep before us, or |g| of the gradient sweep).  (Starting the gathers here as
+        // well, speculatively from the vector the host knows, was measured: no gain, profiles/r2g_ab.txt.)
+        const bool pieces = P.advance_here || P.init_here;
+        if (pieces) {
             defer_begin(P.prev_part, false, P.prev_count, P.prev_longdot, P.prev_nlong, spieces);
             if constexpr (kAsyncGather) cp_async_commit();
-            gather_from(P.wp);
-            gathered = true;
-            double bsq, unused;
-            defer_end<kAsyncGather>(false, P.prev_count, P.prev_nlong, spieces, sred, bsq, unused);
-            lanczos_advance(&st, scribe ? P.bet : nullptr, sqrt(bsq));     // cubic.py:98-109, in registers
-            if (st.redo) {                                     // breakdown: the operator is re-applied to V[col]
+        }
+        LanczosCtl st;
+        if (P.init_here) {
+            // a fresh recurrence (what lanczos_init_kernel does): bet[0] = |g|, everything else reset
+            if (!gathered) { gather_from(P.g); gathered = true; }
+            double gsq, unused;
+            defer_end<kAsyncGather>(false, P.prev_count, P.prev_nlong, spieces, sred, gsq, unused);
+            const double gn = sqrt(gsq);
+            st.col = 0; st.redo = 0; st.final_ = (P.m_init == 1); st.done = 0; st.m_eff = P.m_init; st.nvalid = 1;
+            st.store_idx = P.m_init - 1; st.m = P.m_init; st.broke = 0; st.hvps = 0; st.last_beta = 0.0;
+            st.cur_beta = gn; st.cur_alpha = 0.0;
+            if (blockIdx.x == 0) {
+                for (int i = tid; i < P.m_init; i += kSweepThreads) { P.alphas[i] = 0.0; P.bet[i + 1] = 0.0; }
+                if (tid == 0) P.bet[0] = gn;
+            }
+        } else {
+            st = *P.ctl_in;
+            if (st.done) {
+                cp_async_wait_all();                           // nothing may still be on its way into this CTA's shared memory
+                if (scribe && P.ctl != P.ctl_in) *P.ctl = st;      // keep the pair in step
+                return;
+            }
+            if (P.advance_here) {
+                // beta = |w'| of the column sweep before us is still in pieces.  While they travel, gather from w'
+                // -- the source unless the recurrence breaks down right now, which the sum will tell
+                if (!gathered) { gather_from(P.wp); gathered = true; }
+                double bsq, unused;
+                defer_end<kAsyncGather>(false, P.prev_count, P.prev_nlong, spieces, sred, bsq, unused);
+                lanczos_advance(&st, scribe ? P.bet : nullptr, sqrt(bsq));     // cubic.py:98-109, in registers
+            }
+            if (st.redo && gathered) {                         // breakdown: the operator is re-applied to V[col]
                 gathered = false;
                 if constexpr (kAsyncGather) { cp_async_wait_all(); __syncthreads(); }   // the slots are written again
             }
@@ -515,18 +549,20 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         }
     }
     if constexpr (MODE == kColsLanczos) {
-        st_cols = *P.ctl_in;
-        if (st_cols.done) return;
-        col = st_cols.col;
+        // first what does not depend on the control block: the pieces of alpha = v'Hv the row sweep before us left (needed
+        // by the epilogue only)
         if (P.defer) {
-            // alpha = v'Hv of the row sweep before us is still in pieces; it is needed by the epilogue only
             defer_begin(P.prev_part, true, P.prev_count, P.prev_longdot, P.prev_nlong, spieces);
             if constexpr (kAsyncGather) cp_async_commit();
             alpha_pending = true;
+        }
+        st_cols = *P.ctl_in;
+        if (st_cols.done) { cp_async_wait_all(); return; }
+        col = st_cols.col;
+        if (P.defer) {
             if (st_cols.final_) {                              // cubic.py:109: the last alpha needs no further vector
                 double s1, s2;
-                if constexpr (kAsyncGather) cp_async_commit();        // an (empty) last group for defer_end to leave behind
-                defer_end<kAsyncGather>(true, P.prev_count, P.prev_nlong, spieces, sred, s1, s2);
+                defer_end<false>(true, P.prev_count, P.prev_nlong, spieces, sred, s1, s2);      // waits for everything in flight
                 if (blockIdx.x == 0 && tid == 0) {
                     const double alpha = __dadd_rn(quotient(s1, P.n_samples, P.inv_n), __dmul_rn(P.l2, s2));
                     P.alphas[st_cols.store_idx] = alpha;
@@ -678,6 +714,20 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
     // become resident and start its own (matrix-only) loads while they run -- it still waits for our completion.
     pdl_trigger();
 
+    if constexpr (MODE == kColsScaled) {
+        if (P.red_partials) {
+            __syncthreads();
+            const double mine = cta_sum_to_thread0(acc, sred);
+            if (tid == 0) P.red_partials[blockIdx.x] = mine;
+        }
+    }
+
+    if constexpr (MODE == kRowsForward) {
+        __syncthreads();
+        const double mine = cta_sum_to_thread0(acc, sred);
+        if (tid == 0) P.red_partials[blockIdx.x] = mine;
+    }
+
     if constexpr (MODE == kRowsLanczos) {
         // alpha = v'Hv: threads -> tile (fixed order) -> tiles in tile order, by the consumer (deferred) or by the
         // last CTA here
@@ -761,8 +811,9 @@ int launch_variant(kcrn_problem *h, const SegMat &A, const SweepParams &P) {
 
 // The gather variant is a property of (matrix, class of pass): the Lanczos passes carry more state than the others
 template <int MODE>
-int launch(kcrn_problem *h, const SegMat &A, SweepParams &P) {
+int launch(kcrn_problem *h, const SegMat &A, SweepParams &P, double *longdot = nullptr) {
     fill_matrix(P, A);
+    if (longdot) P.longdot = longdot;      // the forward sweep keeps its long-segment shares apart from the Lanczos passes'
     const int variant = !A.gidx ? kGatherStored : (MODE == kRowsLanczos || MODE == kColsLanczos ? A.gather_lanczos : A.gather_plain);
     if (variant == kGatherAsync) KCRN_TRY((launch_variant<MODE, kGatherAsync>(h, A, P)));
     else if (variant == kGatherOrdered) KCRN_TRY((launch_variant<MODE, kGatherOrdered>(h, A, P)));
@@ -788,8 +839,10 @@ __global__ void derive_from_Ax_kernel(const double *__restrict__ Ax, const doubl
 int launch_forward(kcrn_problem *h, const double *x) {
     SweepParams P{};
     P.src = x; P.b = h->b; P.Ax = h->Ax; P.D = h->D; P.resid = h->resid; P.ell = h->ell;
+    P.red_partials = h->fwd_part;
     h->counters[3] += 1;
-    return launch<kRowsForward>(h, h->csr, P);
+    h->fwd_parts_valid = true;
+    return launch<kRowsForward>(h, h->csr, P, h->fwd_longdot);
 }
 
 int launch_rows_weighted(kcrn_problem *h, const double *v) {
@@ -849,7 +902,7 @@ int tune_plain_sweeps(kcrn_problem *h) {
             for (int bt = 0; bt < batches && rc == KCRN_OK; ++bt) {
                 for (int i = (bt == 0 ? -2 : 0); i < reps && rc == KCRN_OK; ++i) {      // two warm-up launches first
                     if (i == 0) cudaEventRecord(e0, s);
-                    rc = which == 0 ? launch_rows_weighted(h, h->x_cur) : launch_cols_scaled(h, h->t, nullptr, h->o_stage);
+                    rc = which == 0 ? launch_rows_weighted(h, h->x_cur) : launch_cols_scaled(h, h->t, nullptr, h->o_stage, nullptr);
                 }
                 cudaEventRecord(e1, s);
                 if (cudaEventSynchronize(e1) != cudaSuccess) { set_error("tune_plain_sweeps: %s", cudaGetErrorString(cudaGetLastError())); rc = KCRN_E_CUDA; }
@@ -883,7 +936,7 @@ bool lanczos_defer_fits(const kcrn_problem *h) {
 // slot = position of the step in the captured recurrence; defer = 1 (single-GPU fused loop): grid-wide sums are
 // finished by the consumer kernel and the control block ping-pongs between h->ctl[0] and h->ctl[1] so that the
 // row sweep can advance the recurrence in registers while other CTAs still read the old state.
-int launch_rows_lanczos(kcrn_problem *h, double *alpha_raw, int slot, int defer) {
+int launch_rows_lanczos(kcrn_problem *h, double *alpha_raw, int slot, int defer, int init_m) {
     SweepParams P{};
     P.D = h->D; P.out = h->t; P.V = h->V; P.g = h->g; P.wp = h->wp; P.bet = h->bet; P.d = h->d;
     P.alphas = h->alphas; P.n_samples = (double)h->n_global; P.inv_n = 1.0 / P.n_samples; P.l2 = h->l2;
@@ -893,6 +946,7 @@ int launch_rows_lanczos(kcrn_problem *h, double *alpha_raw, int slot, int defer)
         P.ctl_in = h->ctl + (slot & 1); P.ctl = h->ctl + ((slot + 1) & 1);
         P.advance_here = slot > 0;
         P.prev_part = h->lan_cols_part; P.prev_count = h->csc.grid; P.prev_longdot = h->csc.longdot; P.prev_nlong = h->csc.nlong;
+        if (slot == 0 && init_m > 0) { P.init_here = 1; P.m_init = init_m; }
     } else {
         P.ctl_in = P.ctl = h->ctl;
     }
@@ -908,10 +962,11 @@ int launch_cols_raw(kcrn_problem *h, const double *src, double *out) {
     return launch<kColsRaw>(h, h->csc, P);
 }
 
-int launch_cols_scaled(kcrn_problem *h, const double *src, const double *u, double *out) {
+int launch_cols_scaled(kcrn_problem *h, const double *src, const double *u, double *out, double *sq_part) {
     SweepParams P{};
     P.src = src; P.out = out; P.u = u; P.n_samples = (double)h->n_global; P.inv_n = 1.0 / P.n_samples; P.l2 = h->l2;
     P.add_l2 = u != nullptr;
+    P.red_partials = sq_part;              // pieces of |out|^2 per tile (+ csc.longdot), for the recurrence that follows
     h->counters[4] += 1;
     return launch<kColsScaled>(h, h->csc, P);
 }

@@ -132,11 +132,13 @@ def balanced_row_cuts(indptr: np.ndarray, parts: int) -> np.ndarray:
     return np.maximum.accumulate(np.minimum(cuts, n))
 
 
-def make_problem_device(n: int, d: int, nnz_per_row: float, zipf_a: float = 1.0, seed: int = 0, device="cuda"):
+def make_problem_device(n: int, d: int, nnz_per_row: float, zipf_a: float = 1.0, seed: int = 0, device="cuda",
+                        perm_seed: int | None = None):
     """Large synthetic problem generated ON the GPU with torch (BASELINE config 5 scale: host generation of 1e9
     non-zeros is impractical).  Same recipe as ``make_problem`` -- Poisson row lengths, power-law column popularity
     under a random permutation, distinct sorted columns per row, lognormal values with unit-L2 rows -- but not
-    bit-identical to it.  Returns (indptr int32 [n+1], indices int32 [nnz], data float64 [nnz], labels01 float64 [n])
+    bit-identical to it.  ``perm_seed``: seed of the column-popularity permutation when several shards of one matrix are
+    generated with different ``seed``s.  Returns (indptr int32 [n+1], indices int32 [nnz], data float64 [nnz], labels01 float64 [n])
     as CUDA tensors."""
     import torch
 
@@ -152,7 +154,14 @@ def make_problem_device(n: int, d: int, nnz_per_row: float, zipf_a: float = 1.0,
         rank = ((u * ((d + 1.0) ** e - 1.0) + 1.0) ** (1.0 / e)) - 1.0
     del u
     rank = rank.to(torch.int64).clamp_(0, d - 1)
-    perm = torch.randperm(d, device=device, generator=gen)
+    if perm_seed is None:
+        perm = torch.randperm(d, device=device, generator=gen)
+    else:
+        # row shards of ONE matrix (every rank generates its own rows): the popularity of a column is a property of the
+        # whole matrix, so all shards must draw it from the same permutation
+        pg = torch.Generator(device=device)
+        pg.manual_seed(perm_seed)
+        perm = torch.randperm(d, device=device, generator=pg)
     key = rows * d + perm[rank]
     del rows, rank
     key = torch.unique(key)                                           # sorted, duplicates inside a row removed

@@ -445,8 +445,11 @@ def test_free_running_trajectory_vs_reference(torch, golden, name, m, iters, reo
     print(f"\nTRAJ {name} m={m} reorth={reorth}: envelope <= 1e-8 for the first {prefix}/{k} iterations; on that prefix "
           f"max dev {dev[:prefix].max() if prefix else 0:.3e}; beyond it max dev/envelope "
           f"{(dev[prefix:] / env[prefix:]).max() if prefix < k else 0:.3g} (max dev {dev.max():.3e}, max envelope {env.max():.3e})")
-    assert np.all(dev[:prefix] <= 1e-8), dev[:prefix]
-    assert np.all(dev[prefix:] <= 10 * env[prefix:]), (dev[prefix:], env[prefix:])
+    # what the comparison can resolve at all: f is a double, so f(x_k) - f* carries a few ulp(f) of rounding -- a relative
+    # 8 eps f / (f - f*), which exceeds 1e-8 once the suboptimality falls below ~1e-7 f (w8a, re-orthogonalised, last steps)
+    floor = 8 * np.finfo(float).eps * np.abs(ref[:k]) / (ref[:k] - fstar)
+    assert np.all(dev[:prefix] <= 1e-8 + floor[:prefix]), dev[:prefix]
+    assert np.all(dev[prefix:] <= 10 * env[prefix:] + floor[prefix:]), (dev[prefix:], env[prefix:], floor[prefix:])
     # the iteration stays a descent method and ends where the reference ends (loose, chaos-proof)
     assert np.all(np.diff(f) <= 1e-12)
     assert f[-1] <= ref[0]
