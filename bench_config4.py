@@ -39,6 +39,9 @@ def main():
     loss = LogisticRegression(P.scipy_csr(), P.b, l1=0, l2=0, store_mat_vec_prod=True)
     x = torch.as_tensor(P.x0, device="cuda")
     out = {"workload": f"{args.workload}-shape n={P.n} d={P.d} nnz={P.nnz}", "dtype": "f64"}
+    from bench import ClockSampler
+    clk = ClockSampler(0)
+    clk.__enter__()
 
     # ---- dense Hessian
     H = torch.empty((P.d, P.d), dtype=torch.float64, device="cuda")
@@ -89,6 +92,10 @@ def main():
         torch.cuda.synchronize()
         out["full_crn"] = {"seconds_per_outer_iteration": (time.perf_counter() - t0) / args.crn_iters,
                            "newton_iterations": opt.solver_it, "f": opt.value}
+    clk.__exit__(None, None, None)
+    out["clocks"] = clk.summary()
+    out["reference_cpu_sscn_iters_per_sec"] = {"10": 165, "50": 128, "100": 84, "500": 11.0,
+                                               "source": "BASELINE.md section 2 (unmodified reference, survey container, 8 cores)"}
     print(json.dumps(out), flush=True)
 
 

@@ -147,6 +147,12 @@ int kcrn_lanczos_feed(kcrn_handle h, const double *hv_dev, int *finished_host);
  * out_dev[0..m) = s, out_dev[m..m+4) = {r, model_decrease, iterations, status}. */
 int kcrn_cubic_tridiag(const double *alphas_dev, const double *betas_dev, int m, double gnorm,
                        double M, double r0, double eps, int it_max, double *out_dev, void *stream);
+/* The same sub-problem for a DENSE symmetric block H[m][m] (row-major) and a general g[m], m <= 64 -- what SSCN passes
+ * to cubic_solver_root (optimizer/cubic.py:374-389; reference solves with scipy.linalg.solve(assume_a='pos') = dposv).
+ * One kernel: Cholesky of H + lam I, both solves, norms and the Newton loop of scipy's scalar `newton`.
+ * out_dev[m + 4] = {s[0..m), r, model decrease, Newton iterations, status (0 or KCRN_E_NOTPD)}. */
+int kcrn_cubic_dense(const double *H_dev, const double *g_dev, int m, double M, double r0, double eps, int it_max,
+                     double *out_dev, void *stream);
 /* Same, on the handle's Lanczos result (m_eff and |g| read on the device). */
 int kcrn_cubic_from_lanczos(kcrn_handle h, double M, double r0, double eps, int it_max);
 

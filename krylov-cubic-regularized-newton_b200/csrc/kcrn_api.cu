@@ -473,7 +473,7 @@ int kcrn_destroy(kcrn_handle h) {
     free_segmat(&h->csc);
     double *bufs[] = {h->b, h->x_base, h->step_params, h->x_cur, h->Ax, h->D, h->resid, h->ell, h->t, h->ypart, h->V, h->w, h->wp, h->g,
                       h->alphas, h->bet, h->coef, h->coef2, h->sub, h->scal, h->red_partials, h->x_stage,
-                      h->v_stage, h->o_stage, h->fwd_part, h->fwd_longdot};
+                      h->v_stage, h->o_stage, h->fwd_part, h->fwd_longdot, h->panel_x, h->panel_y, h->splitk_part};
     for (double *p : bufs) cudaFree(p);
     cudaFree(h->ctl); cudaFree(h->lan_rows_part); cudaFree(h->lan_cols_part);
     cudaFree(h->info);
@@ -870,6 +870,12 @@ int kcrn_cubic_tridiag(const double *alphas_dev, const double *betas_dev, int m,
     if (!alphas_dev || !out_dev || (m > 1 && !betas_dev)) { set_error("kcrn_cubic_tridiag: null argument"); return KCRN_E_ARG; }
     return launch_cubic(alphas_dev, betas_dev, m, nullptr, nullptr, gnorm, M, r0, eps, it_max, out_dev, out_dev + m,
                         (cudaStream_t)stream, nullptr);
+}
+
+int kcrn_cubic_dense(const double *H_dev, const double *g_dev, int m, double M, double r0, double eps, int it_max,
+                     double *out_dev, void *stream) {
+    if (!H_dev || !g_dev || !out_dev) { set_error("kcrn_cubic_dense: null argument"); return KCRN_E_ARG; }
+    return launch_cubic_dense(H_dev, g_dev, m, M, r0, eps, it_max, out_dev, (cudaStream_t)stream);
 }
 
 int kcrn_cubic_from_lanczos(kcrn_handle h, double M, double r0, double eps, int it_max) {

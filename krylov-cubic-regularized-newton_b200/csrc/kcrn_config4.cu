@@ -38,7 +38,10 @@ __device__ __forceinline__ void dmma_8x8x4(double &d0, double &d1, double a, dou
 __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_tn_kernel(const double *__restrict__ X,
                                                                   const double *__restrict__ Y, int K, int ld,
                                                                   int p, int q, double n_samples, double l2,
-                                                                  double *__restrict__ C, int ldc, int tri) {
+                                                                  double *__restrict__ C, int ldc, int tri,
+                                                                  int ksplit, double *__restrict__ part) {
+    // ksplit > 1 (few output tiles: SSCN blocks): blockIdx.y = which slice of K this CTA contracts; the raw
+    // accumulators go to part[slice][tile][128 x 128] and splitk_reduce_kernel adds the slices in order
     extern __shared__ double smem[];
     int ti, tj;
     if (tri) {
@@ -52,6 +55,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_tn_kernel(const double 
         ti = blockIdx.y;
         tj = blockIdx.x;
     }
+    const int split = tri ? blockIdx.y : 0;
     const int I = ti * BM, J = tj * BN;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3;
@@ -76,17 +80,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_tn_kernel(const double 
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-    const int nk = K / BK;
+    const int nk_all = K / BK, per = (nk_all + ksplit - 1) / ksplit;
+    const int kbase = split * per, nk = max(0, min(per, nk_all - kbase));      // this CTA's slice of the K steps
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < nk) load_stage(s, s * BK);
+        if (s < nk) load_stage(s, (kbase + s) * BK);
         cp_async_commit();
     }
     for (int kc = 0; kc < nk; ++kc) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
         const int nxt = kc + STAGES - 1;
-        if (nxt < nk) load_stage(nxt % STAGES, nxt * BK);
+        if (nxt < nk) load_stage(nxt % STAGES, (kbase + nxt) * BK);
         cp_async_commit();
         const double *xs = stage_x(kc % STAGES), *ys = stage_y(kc % STAGES);
 #pragma unroll
@@ -112,6 +117,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_tn_kernel(const double 
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int c = J + wn * 32 + nt * 8 + tig * 2 + e;
+                if (ksplit > 1) {
+                    part[((size_t)split * gridDim.x + blockIdx.x) * (BM * BN) + (size_t)(r - I) * BN + (c - J)] = acc[mt][nt][e];
+                    continue;
+                }
                 if (r < p && c < q) {
                     double v = acc[mt][nt][e] / n_samples;
                     if (r == c && l2 != 0.0) v = __dadd_rn(v, l2);
@@ -138,18 +147,24 @@ __global__ void densify_rows_kernel(const int32_t *__restrict__ ptr, const int32
     }
 }
 
-// dense copy of the selected columns: Y[row, j] = A[row, I[j]], X = diag(w) Y.  One thread per column.
+// dense copy of the selected columns: Y[row, j] = A[row, I[j]], X = diag(w) Y.  One warp per column (a popular column of
+// the rcv1-shaped matrix holds 1e5 entries); duplicate entries of one (row, column) add up through the atomic -- the
+// sum of two is order-free, canonical matrices have none -- and X is formed once Y is final.
 __global__ void densify_cols_kernel(const int32_t *__restrict__ cptr, const int32_t *__restrict__ cidx,
                                     const double *__restrict__ cval, const double *__restrict__ w,
                                     const int64_t *__restrict__ I, int m, int ld, double *__restrict__ X,
                                     double *__restrict__ Y, const int32_t *__restrict__ pos) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (j >= m) return;
     const int64_t c = pos ? pos[I[j]] : I[j];
-    for (int k = cptr[c]; k < cptr[c + 1]; ++k) {
+    const int a = cptr[c], b = cptr[c + 1];
+    for (int k = a + lane; k < b; k += 32) atomicAdd(Y + (size_t)cidx[k] * ld + j, cval[k]);
+    if (!X) return;
+    __threadfence();
+    __syncwarp();
+    for (int k = a + lane; k < b; k += 32) {
         const size_t o = (size_t)cidx[k] * ld + j;
-        Y[o] += cval[k];
-        if (X) X[o] = __dmul_rn(w[cidx[k]], Y[o]);
+        X[o] = __dmul_rn(w[cidx[k]], __ldcg(Y + o));
     }
 }
 
@@ -194,17 +209,38 @@ __global__ void add_inplace_kernel(double *__restrict__ a, const double *__restr
     if (i < n) a[i] = a[i] + b[i];
 }
 
-int run_gemm(const double *X, const double *Y, int K, int ld, int p, double n_samples, double l2, double *C,
-             int ldc, cudaStream_t s) {
-    static bool attr = false;
-    if (!attr) {
-        KCRN_CUDA(cudaFuncSetAttribute(dgemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-        attr = true;
+// C = (sum over the K slices, in slice order) / n (+ l2 on the diagonal), mirrored below the diagonal
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const double *__restrict__ part, int ksplit, int tiles, int p,
+                                                            double n_samples, double l2, double *__restrict__ C, int ldc) {
+    const int tile = blockIdx.x, T = (p + BM - 1) / BM;
+    int rem = tile, ti = 0;
+    while (rem >= T - ti) { rem -= T - ti; ++ti; }
+    const int tj = ti + rem;
+    for (int e = blockIdx.y * 256 + threadIdx.x; e < BM * BN; e += gridDim.y * 256) {
+        const int r = ti * BM + e / BN, c = tj * BN + e % BN;
+        if (r >= p || c >= p) continue;
+        double acc = 0.0;
+        for (int sp = 0; sp < ksplit; ++sp) acc += part[((size_t)sp * tiles + tile) * (BM * BN) + e];
+        double v = acc / n_samples;
+        if (r == c && l2 != 0.0) v = __dadd_rn(v, l2);
+        C[(size_t)r * ldc + c] = v;
+        if (ti != tj) C[(size_t)c * ldc + r] = v;
     }
+}
+
+int run_gemm(const double *X, const double *Y, int K, int ld, int p, double n_samples, double l2, double *C,
+             int ldc, cudaStream_t s, double *part = nullptr, int ksplit = 1) {
+    // the attribute is per device: set it every time (a process may drive several GPUs)
+    KCRN_CUDA(cudaFuncSetAttribute(dgemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     const int T = (p + BM - 1) / BM;
     const int64_t tiles = (int64_t)T * (T + 1) / 2;
-    dgemm_tn_kernel<<<(unsigned)tiles, GEMM_THREADS, GEMM_SMEM, s>>>(X, Y, K, ld, p, p, n_samples, l2, C, ldc, 1);
+    dgemm_tn_kernel<<<dim3((unsigned)tiles, (unsigned)ksplit), GEMM_THREADS, GEMM_SMEM, s>>>(X, Y, K, ld, p, p, n_samples, l2, C, ldc,
+                                                                                              1, ksplit, part);
     KCRN_LAUNCH_CHECK();
+    if (ksplit > 1) {
+        splitk_reduce_kernel<<<dim3((unsigned)tiles, 16), 256, 0, s>>>(part, ksplit, (int)tiles, p, n_samples, l2, C, ldc);
+        KCRN_LAUNCH_CHECK();
+    }
     return KCRN_OK;
 }
 
@@ -262,16 +298,38 @@ int config4_partial_hessian(kcrn_problem *h, const int64_t *I, int m, double *ou
     const int K = (int)((n + BK - 1) / BK * BK);
     const size_t bytes = sizeof(double) * (size_t)K * (size_t)ld;
     cudaStream_t s = h->stream;
-    double *X = nullptr, *Y = nullptr;
-    KCRN_CUDA(cudaMallocAsync(&X, bytes, s));
-    KCRN_CUDA(cudaMallocAsync(&Y, bytes, s));
+    // the two dense panels live in the handle (SSCN asks for a block every step): grown on demand, never shrunk
+    if (bytes > h->panel_bytes) {
+        KCRN_CUDA(cudaStreamSynchronize(s));
+        cudaFree(h->panel_x);
+        cudaFree(h->panel_y);
+        h->panel_x = h->panel_y = nullptr;
+        h->panel_bytes = 0;
+        KCRN_CUDA(cudaMalloc(&h->panel_x, bytes));
+        KCRN_CUDA(cudaMalloc(&h->panel_y, bytes));
+        h->panel_bytes = bytes;
+    }
+    double *X = h->panel_x, *Y = h->panel_y;
     KCRN_CUDA(cudaMemsetAsync(X, 0, bytes, s));
     KCRN_CUDA(cudaMemsetAsync(Y, 0, bytes, s));
-    densify_cols_kernel<<<(m + 127) / 128, 128, 0, s>>>(h->csc.ptr, h->csc.idx, h->csc.val, h->D, I, m, ld, X, Y, h->csc.pos);
+    densify_cols_kernel<<<(m * 32 + 127) / 128, 128, 0, s>>>(h->csc.ptr, h->csc.idx, h->csc.val, h->D, I, m, ld, X, Y, h->csc.pos);
     KCRN_LAUNCH_CHECK();
-    KCRN_TRY(run_gemm(X, Y, K, ld, m, (double)h->n_global, h->l2, out, m, s));
-    KCRN_CUDA(cudaFreeAsync(X, s));
-    KCRN_CUDA(cudaFreeAsync(Y, s));
+    // a block of m <= 128 columns is ONE output tile: split the contraction over the samples across the SMs (a single
+    // CTA walking 20 k rows took 2.5 ms), slices added in order by the reduce kernel
+    const int T = (m + BM - 1) / BM, tiles = T * (T + 1) / 2;
+    int ksplit = std::max(1, std::min(kNumSm / tiles, (K / BK) / 4));
+    if (ksplit > 1) {
+        const size_t pbytes = sizeof(double) * (size_t)ksplit * tiles * BM * BN;
+        if (pbytes > h->splitk_bytes) {
+            KCRN_CUDA(cudaStreamSynchronize(s));
+            cudaFree(h->splitk_part);
+            h->splitk_part = nullptr;
+            h->splitk_bytes = 0;
+            KCRN_CUDA(cudaMalloc(&h->splitk_part, pbytes));
+            h->splitk_bytes = pbytes;
+        }
+    }
+    KCRN_TRY(run_gemm(X, Y, K, ld, m, (double)h->n_global, h->l2, out, m, s, h->splitk_part, ksplit));
     h->counters[0] += 2;
     return KCRN_OK;
 }

@@ -150,7 +150,140 @@ __global__ void __launch_bounds__(32) cubic_kernel(const double *__restrict__ al
     }
 }
 
+// ----------------------------------------------------------------------------- dense blocks (SSCN, config 4)
+// The same Newton iteration for a DENSE symmetric m x m block (cubic.py:40-75 as SSCN calls it, :374-389: general g,
+// epsilon = machine eps), m <= 64: the whole loop -- Cholesky of H + lam I (left-looking, column by column), the two
+// triangular solves per evaluation, the norms and the stopping rule -- runs in ONE kernel of 64 threads on data in
+// shared memory.  Round 1 drove it from Python with a cuSOLVER factorisation and three host round trips per
+// evaluation: 2-3 ms per SSCN step, slower than the reference's CPU at m = 10 and 50.
+constexpr int kDenseMax = 64;
+
+struct DenseWork {
+    const double *H;                 // the block in global memory (row-major, read-only: L1/L2 serve the re-reads)
+    double (*L)[kDenseMax + 1];
+    double *col;
+};
+
+// L L' = A + lam I.  Thread i owns row i.  False (in every thread) when a pivot is not positive.
+__device__ bool dense_factor(const DenseWork &w, int m, double lam) {
+    const int i = threadIdx.x;
+    __shared__ int s_bad;
+    if (i == 0) s_bad = 0;
+    for (int j = 0; j < m; ++j) {
+        if (i >= j && i < m) {
+            double dot = 0.0;
+            for (int k = 0; k < j; ++k) dot = fma(w.L[i][k], w.L[j][k], dot);
+            w.col[i] = (__ldg(w.H + (size_t)i * m + j) + (i == j ? lam : 0.0)) - dot;
+        }
+        __syncthreads();
+        const double pj = w.col[j];
+        if (!(pj > 0.0)) { if (i == 0) s_bad = 1; break; }            // uniform: every thread reads the same pj
+        const double ljj = sqrt(pj);
+        if (i == j) w.L[j][j] = ljj;
+        else if (i > j && i < m) w.L[i][j] = w.col[i] / ljj;
+        __syncthreads();
+    }
+    __syncthreads();
+    return s_bad == 0;
+}
+
+// x = (L L')^-1 rhs, in place in x (x holds rhs on entry).  Column-oriented substitutions, thread i owns x[i].
+__device__ void dense_solve(const DenseWork &w, int m, double *x) {
+    const int i = threadIdx.x;
+    for (int j = 0; j < m; ++j) {                    // L y = rhs
+        if (i == j) x[j] = x[j] / w.L[j][j];
+        __syncthreads();
+        if (i > j && i < m) x[i] = fma(-w.L[i][j], x[j], x[i]);
+        __syncthreads();
+    }
+    for (int j = m - 1; j >= 0; --j) {               // L' x = y
+        if (i == j) x[j] = x[j] / w.L[j][j];
+        __syncthreads();
+        if (i < j) x[i] = fma(-w.L[j][i], x[j], x[i]);
+        __syncthreads();
+    }
+}
+
+// fixed-order sum over the m entries (thread 0 walks them: m <= 64)
+__device__ double dense_dot(const double *a, const double *b, int m) {
+    double acc = 0.0;
+    for (int k = 0; k < m; ++k) acc = __dadd_rn(acc, __dmul_rn(a[k], b[k]));
+    return acc;
+}
+
+__global__ void __launch_bounds__(kDenseMax) cubic_dense_kernel(const double *__restrict__ H, const double *__restrict__ g,
+                                                                int m, double M, double r0, double eps, int it_max,
+                                                                double *__restrict__ out) {
+    __shared__ double sL[kDenseMax][kDenseMax + 1];
+    __shared__ double scol[kDenseMax], sg[kDenseMax], ss[kDenseMax], sq[kDenseMax];
+    __shared__ double s_p0, s_p;
+    __shared__ int s_state;                          // 0: iterate, 1: converged, 2: not positive definite
+    const int i = threadIdx.x;
+    DenseWork w{H, sL, scol};
+    if (i < m) sg[i] = g[i];
+    if (i == 0) { s_p0 = r0; s_p = r0; s_state = 0; }
+    __syncthreads();
+    int its = it_max;
+    for (int itr = 0; itr < it_max; ++itr) {
+        const double p0 = s_p0;
+        if (!dense_factor(w, m, p0)) { if (i == 0) { s_state = 2; s_p = p0; } its = itr; __syncthreads(); break; }
+        if (i < m) ss[i] = -sg[i];
+        __syncthreads();
+        dense_solve(w, m, ss);                       // s = -(H + p0 I)^-1 g
+        if (i < m) sq[i] = ss[i];
+        __syncthreads();
+        dense_solve(w, m, sq);                       // (H + p0 I)^-1 s
+        if (i == 0) {
+            const double ns = sqrt(dense_dot(ss, ss, m));
+            const double fval = p0 * p0 - M * M * ns * ns;
+            if (fval == 0.0) { s_p = p0; s_state = 1; s_p0 = (double)itr; }
+            else {
+                const double fder = 2.0 * p0 + 2.0 * M * M * dense_dot(ss, sq, m);
+                if (fder == 0.0) { s_p = p0; s_state = 1; s_p0 = (double)(itr + 1); }
+                else {
+                    const double p = p0 - fval / fder;
+                    s_p = p;
+                    if (fabs(p - p0) <= eps) { s_state = 1; s_p0 = (double)(itr + 1); }
+                    else s_p0 = p;
+                }
+            }
+        }
+        __syncthreads();
+        if (s_state == 1) { its = (int)s_p0; break; }
+    }
+    __syncthreads();
+    const double r = s_p;
+    double dec = 0.0;
+    int status = s_state == 2 ? KCRN_E_NOTPD : 0;
+    if (status == 0 && !dense_factor(w, m, r)) status = KCRN_E_NOTPD;
+    if (status == 0) {
+        if (i < m) ss[i] = -sg[i];
+        __syncthreads();
+        dense_solve(w, m, ss);
+        if (i == 0) {
+            const double ns = sqrt(dense_dot(ss, ss, m));
+            dec = r / 2.0 * (ns * ns) - M / 3.0 * (ns * ns * ns) - dense_dot(sg, ss, m) / 2.0;
+        }
+    } else if (i < m) {
+        ss[i] = 0.0;
+    }
+    __syncthreads();
+    if (i < m) out[i] = ss[i];
+    if (i == 0) { out[m] = r; out[m + 1] = dec; out[m + 2] = (double)its; out[m + 3] = (double)status; }
+}
+
 }  // namespace
+
+int launch_cubic_dense(const double *H, const double *g, int m, double M, double r0, double eps, int it_max, double *out,
+                       cudaStream_t st) {
+    if (m < 1 || m > kDenseMax) {
+        set_error("dense cubic sub-problem: m = %d outside [1, %d]", m, kDenseMax);
+        return KCRN_E_ARG;
+    }
+    cubic_dense_kernel<<<1, kDenseMax, 0, st>>>(H, g, m, M, r0, eps, it_max, out);
+    KCRN_LAUNCH_CHECK();
+    return KCRN_OK;
+}
 
 int launch_cubic(const double *alphas, const double *betas, int m, const int32_t *info, const double *gnorm_dev,
                  double gnorm, double M, double r0, double eps, int it_max, double *s_out, double *scal_out,

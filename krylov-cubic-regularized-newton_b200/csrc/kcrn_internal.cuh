@@ -210,6 +210,11 @@ struct kcrn_problem {
     // value_record_kernel; invalid after kcrn_set_Ax / kcrn_update_Ax (those derive the terms without a sweep)
     double *fwd_part = nullptr, *fwd_longdot = nullptr;
     bool fwd_parts_valid = false;
+    // config 4: dense panels of the selected columns for kcrn_partial_hessian (kept across SSCN steps)
+    double *panel_x = nullptr, *panel_y = nullptr;
+    size_t panel_bytes = 0;
+    double *splitk_part = nullptr;     // per-slice accumulators of the split-K block Hessian
+    size_t splitk_bytes = 0;
     // sweep temporaries
     double *t = nullptr;        // [n]   D .* (A v)
     double *ypart = nullptr;    // [d]   local A' t before the allreduce (row-sharded runs)
@@ -322,6 +327,9 @@ bool plan_persist_tiles(const std::vector<int32_t> &ptr, int64_t nseg, int64_t n
 int launch_cubic(const double *alphas, const double *betas, int m, const int32_t *info,
                  const double *gnorm_dev, double gnorm, double M, double r0, double eps, int it_max,
                  double *s_out, double *scal_out, cudaStream_t st, const double *params_dev);
+
+int launch_cubic_dense(const double *H, const double *g, int m, double M, double r0, double eps, int it_max, double *out,
+                       cudaStream_t st);
 
 // ----------------------------------------------------------------------------- kcrn_nccl.cu
 int nccl_unique_id(void *out128);

@@ -52,6 +52,7 @@ SIGNATURES = {
     "kcrn_lanczos_feed": (c_int, [c_void_p, c_void_p, POINTER(c_int)]),
     "kcrn_cubic_tridiag": (c_int, [c_void_p, c_void_p, c_int, c_double, c_double, c_double, c_double, c_int,
                                    c_void_p, c_void_p]),
+    "kcrn_cubic_dense": (c_int, [c_void_p, c_void_p, c_int, c_double, c_double, c_double, c_int, c_void_p, c_void_p]),
     "kcrn_cubic_from_lanczos": (c_int, [c_void_p, c_double, c_double, c_double, c_int]),
     "kcrn_axpy_basis": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "kcrn_trial_point": (c_int, [c_void_p, c_void_p, c_void_p]),

@@ -401,3 +401,22 @@ def cubic_tridiag(alphas, betas, gnorm, M, r0=0.1, eps=1e-8, it_max=100, device=
                                  int(it_max), out.data_ptr(), torch.cuda.current_stream().cuda_stream))
     tail = out[m:].cpu().numpy()
     return out[:m], float(tail[0]), float(tail[1]), int(tail[2]), int(tail[3])
+
+
+DENSE_KERNEL_MAX = 64
+
+
+def cubic_dense_small(H, g, M, r0=0.1, eps=1e-8, it_max=100):
+    """Dense m x m sub-problem, m <= 64, in one kernel (kcrn_cubic_dense).  H [m, m] and g [m] are float64 CUDA tensors.
+    Returns (s tensor [m], r, model_decrease, newton_iterations, status) after ONE device-to-host copy."""
+    import torch
+
+    lib = _lib.load()
+    m = int(g.numel())
+    H = H.contiguous()
+    g = g.contiguous()
+    out = torch.empty(m + 4, dtype=torch.float64, device=g.device)
+    check(lib.kcrn_cubic_dense(H.data_ptr(), g.data_ptr(), m, float(M), float(r0), float(eps), int(it_max), out.data_ptr(),
+                               torch.cuda.current_stream().cuda_stream))
+    tail = out[m:].cpu().numpy()
+    return out[:m], float(tail[0]), float(tail[1]), int(tail[2]), int(tail[3])

@@ -11,6 +11,8 @@ from __future__ import annotations
 
 import numpy as np
 
+from kcrn_b200.engine import DENSE_KERNEL_MAX, cubic_dense_small
+
 
 def newton_scalar(func, fprime, x0, tol, maxiter):
     """Newton-Raphson as scipy's scalar ``newton`` iterates it for root_scalar(method='newton', xtol=tol)
@@ -41,6 +43,12 @@ def cubic_solver_dense(g, H, M, it_max=100, epsilon=1e-8, r0=0.1):
     Ht = torch.as_tensor(np.ascontiguousarray(H, np.float64), device=dev) if not hasattr(H, "data_ptr") else H
     m = gt.numel()
     Ht = Ht.reshape(m, m)
+    if m <= DENSE_KERNEL_MAX:
+        # small blocks (SSCN m = 10, 50): the whole Newton loop in one kernel, one device-to-host copy
+        s, r, dec, its, status = cubic_dense_small(Ht, gt, float(M), r0=float(r0), eps=float(epsilon), it_max=int(it_max))
+        if status != 0:
+            raise np.linalg.LinAlgError("H + r I is not positive definite")
+        return (s.cpu().numpy() if as_numpy else s), its, r, dec
     diag0 = Ht.diagonal().clone()
     work = Ht if not as_numpy and Ht.numel() > (1 << 26) else Ht.clone()   # huge H: shift its diagonal in place
 
@@ -60,13 +68,21 @@ def cubic_solver_dense(g, H, M, it_max=100, epsilon=1e-8, r0=0.1):
     p0 = p = float(r0)
     its, done = it_max, False
     for itr in range(it_max):
-        L = factor(p0)
+        # one host round trip per evaluation: factorisation status, |s|^2 and s.(H + p0 I)^-1 s travel together
+        work.diagonal().copy_(diag0 + p0)
+        L, info = torch.linalg.cholesky_ex(work)
         s = -solve(L, gt)
-        fval = p0 ** 2 - M ** 2 * float(s.norm().item()) ** 2
+        q = solve(L, s)
+        bad, ns2, sdot = torch.stack([info.to(torch.float64).reshape(()), s @ s, s @ q]).tolist()
+        if bad != 0:
+            if work is Ht:
+                work.diagonal().copy_(diag0)
+            raise np.linalg.LinAlgError("H + r I is not positive definite")
+        fval = p0 ** 2 - M ** 2 * float(np.sqrt(ns2)) ** 2
         if fval == 0:
             p, its, done = p0, itr, True
             break
-        fder = 2 * p0 + 2 * M ** 2 * float((s @ solve(L, s)).item())
+        fder = 2 * p0 + 2 * M ** 2 * sdot
         if fder == 0:
             p, its, done = p0, itr + 1, True
             break

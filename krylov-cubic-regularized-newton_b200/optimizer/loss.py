@@ -188,7 +188,10 @@ class LogisticRegression(Oracle):
         return self._out(self.engine.hessian_dense(), x)
 
     def _index_tensor(self, I):
-        return self.torch.as_tensor(np.ascontiguousarray(np.asarray(I), np.int64), device=self.device)
+        I = np.ascontiguousarray(np.asarray(I), np.int64)
+        if I.size and (I.min() < 0 or I.max() >= self.dim):
+            raise IndexError(f"coordinate block outside [0, {self.dim})")      # the kernels do not range-check
+        return self.torch.as_tensor(I, device=self.device)
 
     def partial_gradient(self, x, I):
         self._forward(x)
