@@ -310,7 +310,27 @@ def strong_case(tag, n, d, per_row, m, steps, rank, world, local, peak):
     hbm_bytes = 24 * nnz + 28 * n_loc + 28 * d + 8                       # this rank's two sweeps
     ar_bytes = 2.0 * (world - 1) / world * 8 * d if world > 1 else 0.0    # ring allreduce of the d-vector, per rank
     roof_us = hbm_bytes / (peak * 1e9) * 1e6 + ar_bytes / (NVLINK_GBS * 1e9) * 1e6
+    reorth = None
+    if world == 1 and d > 1000000 and nnz < 50000000:
+        # north_star K6 where it is bandwidth-bound (d = 1.36 M: V[:j+1] is j x 10.8 MB): the recurrence with full
+        # re-orthogonalisation minus the one without, against three reads of V[:j+1] per step
+        def rec_ms(ro):
+            eng.lanczos(m, ro)
+            torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(2):
+                eng.lanczos(m, ro)
+            b_.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b_) / 2
+        eng.gradient(keep_internal=True)
+        t_no, t_ro = rec_ms(False), rec_ms(True)
+        vbytes = 3 * 8 * d * sum(j + 1 for j in range(m - 1))
+        reorth = {"recurrence_ms": t_ro, "recurrence_ms_without": t_no, "basis_bytes": vbytes,
+                  "achieved_gbs": vbytes / ((t_ro - t_no) * 1e-3) / 1e9, "frac": vbytes / ((t_ro - t_no) * 1e-3) / 1e9 / peak}
     out = {"workload": f"{tag}: n={n_loc * world} d={d} nnz={nnz_total}, Krylov CRN m={m}, rows split evenly over {world} GPU(s)",
+           "reorth": reorth,
            "scaling": "strong", "hvps_per_sec": 1e6 / us_hvp, "outer_iters_per_sec": 1e3 * steps / ms, "steps": steps,
            "us_per_hvp_in_step": us_hvp, "hvps_per_step": hv / steps,
            "roofline": {"hbm_bytes_per_rank": hbm_bytes, "allreduce_bytes_per_rank": ar_bytes, "roofline_us": roof_us,

@@ -12,6 +12,31 @@ namespace kcrn {
 
 static thread_local char g_error[512] = "";
 
+Switches read_switches() {
+    Switches w;
+    auto on = [](const char *name) { const char *e = getenv(name); return e != nullptr; };
+    auto num = [](const char *name) { const char *e = getenv(name); return e ? atoi(e) : 0; };
+    w.verbose = on("KCRN_VERBOSE");
+    w.no_pdl = on("KCRN_NO_PDL");
+    w.no_defer = on("KCRN_NO_DEFER");
+    w.emulate_sharded = on("KCRN_EMULATE_SHARDED");
+    w.no_p2p = on("KCRN_NO_P2P");
+    w.no_gather_order = on("KCRN_NO_GATHER_ORDER");
+    w.natural_csc = on("KCRN_NATURAL_CSC");
+    if (const char *e = getenv("KCRN_GATHER")) {         // "p[,l]": plain / Lanczos passes
+        int a = -1, b = -1;
+        const int k = sscanf(e, "%d,%d", &a, &b);
+        if (k >= 1 && a >= 0 && a < 3) w.gather_plain = w.gather_lanczos = a;
+        if (k >= 2 && b >= 0 && b < 3) w.gather_lanczos = b;
+    }
+    w.short_seg = num("KCRN_SHORT_SEG");
+    w.tile_items = num("KCRN_TILE_ITEMS");
+    w.persist = num("KCRN_PERSIST") != 0;
+    w.persist_trace = on("KCRN_PERSIST_TRACE");
+    w.persist_flags = num("KCRN_PERSIST_FLAGS");
+    return w;
+}
+
 void set_error(const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -104,8 +129,7 @@ int enqueue_lanczos(kcrn_problem *h, int m, int reorth, bool allow_persist = tru
     // single GPU: the grid-wide sums (alpha after the row sweep, beta after the column sweep) are finished by the
     // kernel that consumes them -- 2: both, the row sweep also advances the recurrence; 1: alpha only (the
     // re-orthogonalisation kernel owns beta and the advance).  Row-sharded: 0, the exchange kernels own both.
-    static const bool no_defer = getenv("KCRN_NO_DEFER") != nullptr;                 // A/B switch
-    const int defer = (h->sharded() || no_defer || !lanczos_defer_fits(h)) ? 0 : (reorth ? 1 : 2);
+    const int defer = (h->sharded() || h->sw.no_defer || !lanczos_defer_fits(h)) ? 0 : (reorth ? 1 : 2);
     const bool self_init = g_pieces && defer == 2;        // the first row sweep starts the recurrence itself
     if (!self_init) KCRN_TRY(launch_lanczos_init(h, m));
     for (int slot = 0; slot < m; ++slot) {
@@ -136,8 +160,7 @@ int enqueue_lanczos(kcrn_problem *h, int m, int reorth, bool allow_persist = tru
 int tune_lanczos_sweeps(kcrn_problem *h, int m, bool have_g) {
     if (h->lanczos_tuned) return KCRN_OK;
     h->lanczos_tuned = true;
-    int fp, fl;
-    forced_gather_variants(&fp, &fl);
+    const int fl = h->sw.gather_lanczos;
     if (fl >= 0 || h->sharded() || (!h->csr.gidx && !h->csc.gidx) || h->nnz == 0) return KCRN_OK;
     int64_t saved[8];
     memcpy(saved, h->counters, sizeof(saved));
@@ -172,7 +195,7 @@ int tune_lanczos_sweeps(kcrn_problem *h, int m, bool have_g) {
                 if (bt == 0 || t < ms) ms = t;
             }
             if (v == 0 || ms < best_ms) { best = v; best_ms = ms; }
-            if (getenv("KCRN_VERBOSE"))
+            if (h->sw.verbose)
                 fprintf(stderr, "kcrn: Lanczos %s pass, gather variant %d: %.2f us per %d-step recurrence\n",
                         A == &h->csr ? "row" : "column", v, 1e3 * ms / reps, mt);
         }
@@ -389,6 +412,7 @@ int kcrn_create(kcrn_handle *out, int64_t n_rows, int64_t n_cols, int64_t nnz, c
     kcrn_problem *h = new kcrn_problem();
     h->n = n_rows; h->d = n_cols; h->nnz = nnz; h->n_global = n_global > 0 ? n_global : n_rows; h->l2 = l2;
     h->stream = (cudaStream_t)stream;
+    h->sw = read_switches();
     cudaStream_t s = h->stream;
     int rc = KCRN_OK;
     auto run = [&]() -> int {
@@ -398,11 +422,11 @@ int kcrn_create(kcrn_handle *out, int64_t n_rows, int64_t n_cols, int64_t nnz, c
         KCRN_TRY(upload(&h->csr.val, data, (size_t)nnz, arrays_on_device, s));
         KCRN_TRY(upload(&h->b, labels01, (size_t)n_rows, arrays_on_device, s));
         h->counters[6] += arrays_on_device ? 0 : (int64_t)(sizeof(int32_t) * (n_rows + 1 + nnz) + sizeof(double) * (nnz + n_rows));
-        KCRN_TRY(build_csc(h->csr, n_cols, &h->csc, s));
-        KCRN_TRY(build_tiles(&h->csr, n_cols, s));   // row sweeps gather a d-vector
-        KCRN_TRY(build_tiles(&h->csc, n_rows, s));   // column sweeps gather an n-vector
-        h->allow_pdl = getenv("KCRN_NO_PDL") == nullptr;
-        h->emulate_sharded = getenv("KCRN_EMULATE_SHARDED") != nullptr;   // programmatic dependent launch inside the captured graphs
+        KCRN_TRY(build_csc(h->csr, n_cols, &h->csc, s, h->sw.natural_csc));
+        KCRN_TRY(build_tiles(&h->csr, n_cols, s, h->sw));   // row sweeps gather a d-vector
+        KCRN_TRY(build_tiles(&h->csc, n_rows, s, h->sw));   // column sweeps gather an n-vector
+        h->allow_pdl = !h->sw.no_pdl;                       // programmatic dependent launch inside the captured graphs
+        h->emulate_sharded = h->sw.emulate_sharded;
         const size_t n = (size_t)n_rows, d = (size_t)n_cols;
         KCRN_CUDA(cudaMalloc(&h->x_cur, sizeof(double) * d));
         KCRN_CUDA(cudaMalloc(&h->x_base, sizeof(double) * d));
@@ -555,7 +579,7 @@ int kcrn_p2p_attach(kcrn_handle h, const void *all_handles_host) {
         KCRN_CUDA(cudaIpcOpenMemHandle(&pr, hr, cudaIpcMemLazyEnablePeerAccess));
         h->peer_recv[k] = (uint4 *)pr;
     }
-    h->p2p_ready = getenv("KCRN_NO_P2P") == nullptr;
+    h->p2p_ready = !h->sw.no_p2p;
     return KCRN_OK;
 }
 
@@ -942,7 +966,7 @@ int kcrn_plan_tiles(const int32_t *indptr_host, int64_t n_segments, int32_t *til
     std::vector<int32_t> ptr(indptr_host, indptr_host + n_segments + 1);
     std::vector<int4> tiles, longtab;
     int npartial = 0;
-    plan_tiles(ptr, n_segments, ptr[(size_t)n_segments], tiles, longtab, npartial, *items);
+    plan_tiles(ptr, n_segments, ptr[(size_t)n_segments], tiles, longtab, npartial, *items, read_switches());
     *n_tiles = (int64_t)tiles.size();
     *n_long = (int64_t)longtab.size();
     if (tiles4_host && (int64_t)tiles.size() <= tiles_cap) memcpy(tiles4_host, tiles.data(), sizeof(int4) * tiles.size());

@@ -45,6 +45,24 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// ----------------------------------------------------------------------------- process switches
+// Every KCRN_* environment switch is read in ONE place, read_switches() in kcrn_api.cu, once per
+// handle at kcrn_create (kcrn_plan_tiles, which has no handle, reads them per call); nothing else calls getenv.
+struct Switches {
+    bool verbose = false;          // KCRN_VERBOSE
+    bool no_pdl = false;           // KCRN_NO_PDL: no programmatic dependent launch inside the captured graphs
+    bool no_defer = false;         // KCRN_NO_DEFER: grid-wide sums of the fused recurrence finished by a last-CTA tail
+    bool emulate_sharded = false;  // KCRN_EMULATE_SHARDED: a one-GPU handle takes the row-sharded code path
+    bool no_p2p = false;           // KCRN_NO_P2P: NCCL allreduce even where the NVLink peer exchange fits
+    bool no_gather_order = false;  // KCRN_NO_GATHER_ORDER: sweeps read the entries as stored
+    bool natural_csc = false;      // KCRN_NATURAL_CSC: CSC copy in the scipy column order (no length classes)
+    int gather_plain = -1, gather_lanczos = -1;   // KCRN_GATHER=p[,l]: forced gather variants (-1: measure)
+    int short_seg = 0, tile_items = 0;            // KCRN_SHORT_SEG, KCRN_TILE_ITEMS: tiling knobs (0: default)
+    bool persist = false, persist_trace = false;  // KCRN_PERSIST, KCRN_PERSIST_TRACE: one-kernel recurrence (opt-in)
+    int persist_flags = 0;                        // KCRN_PERSIST_FLAGS: its measured experiments
+};
+Switches read_switches();
+
 // ----------------------------------------------------------------------------- geometry
 constexpr int kTileNnz = 2048;     // non-zeros per CTA tile at the default 8 per thread (11 or 12 per thread for small matrices, see build_tiles)
 constexpr int kTileSegs = 1024;    // at most this many segments (rows / columns) per stream tile
@@ -265,6 +283,7 @@ struct kcrn_problem {
     int piece_cap = 0;
     unsigned *pbar = nullptr;      // [0] exchanges done so far (epoch of the slots)
     long long *ptrace = nullptr;   // KCRN_PERSIST_TRACE=1: SM clock at the marks of the last launch
+    kcrn::Switches sw;             // environment switches as they were at kcrn_create
     bool lanczos_tuned = false;    // the gather variants of the Lanczos passes have been measured (first use)
     bool pdl = false;              // launch with programmatic dependent launch (set while the Lanczos graph is built)
     bool allow_pdl = true;         // KCRN_NO_PDL=1 switches it off
@@ -273,15 +292,15 @@ struct kcrn_problem {
 namespace kcrn {
 
 // ----------------------------------------------------------------------------- kcrn_transpose.cu
-int build_csc(const SegMat &csr, int64_t n_cols, SegMat *csc, cudaStream_t s);
+int build_csc(const SegMat &csr, int64_t n_cols, SegMat *csc, cudaStream_t s, bool natural_order);
 int exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t len, cudaStream_t s);
 int canonical_csc_to_host(const SegMat &csc, int32_t *indptr_host, int32_t *indices_host, double *data_host,
                           cudaStream_t s);
 
 // ----------------------------------------------------------------------------- kcrn_sweep.cu
-int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s);
+int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s, const Switches &sw);
 void plan_tiles(const std::vector<int32_t> &ptr, int64_t nseg, int64_t nnz, std::vector<int4> &tiles,
-                std::vector<int4> &longtab, int &npartial, int &items);   // host only
+                std::vector<int4> &longtab, int &npartial, int &items, const Switches &sw);   // host only
 void free_segmat(SegMat *A);
 int launch_forward(kcrn_problem *h, const double *x);                 // A x and everything derived
 int launch_rows_weighted(kcrn_problem *h, const double *v);           // t = D .* (A v)
@@ -293,7 +312,6 @@ int launch_cols_lanczos(kcrn_problem *h, int update_ctl, int slot, int defer);
 bool lanczos_defer_fits(const kcrn_problem *h);      // small grids only: see kcrn_sweep.cu             // w' and beta fused
 int launch_derive_from_Ax(kcrn_problem *h);
 int tune_plain_sweeps(kcrn_problem *h);               // once per handle, at the end of kcrn_create
-void forced_gather_variants(int *plain, int *lanczos);   // KCRN_GATHER override, -1 = measure
 int gather_candidates_last();                            // last variant the tuners try
 
 // ----------------------------------------------------------------------------- kcrn_lanczos.cu

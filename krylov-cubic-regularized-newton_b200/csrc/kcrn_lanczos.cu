@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P
     __shared__ double sh[kVecThreads / 32];
     __shared__ int s_last;
     __shared__ double sdots[kVecThreads / 32][kMaxM];
+    __shared__ double scoef[kMaxM];
     if (P.ctl->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int col = P.ctl->col;
@@ -305,6 +306,8 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P
             x[e] = c < P.d ? __dsub_rn(P.w_in[c], __dmul_rn(alpha, v[c])) : 0.0;
         }
     } else {
+        // w' -= V[:, :nv] c: the coefficients come from shared memory and the basis entries are fetched eight columns
+        // at a time, so that eight loads are in flight per thread instead of one dependent load per column
         double s[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) {
@@ -312,14 +315,24 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P
             x[e] = c < P.d ? P.wp[c] : 0.0;
             s[e] = 0.0;
         }
-        for (int i = 0; i < nv; ++i) {
-            const double ci = P.coef_in[i];
-            const double *vi = P.V + (size_t)i * P.d;
+        for (int i = threadIdx.x; i < nv; i += blockDim.x) scoef[i] = P.coef_in[i];
+        __syncthreads();
+        for (int i0 = 0; i0 < nv; i0 += 8) {
+            double vv[8][E];
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const int64_t c = base + (int64_t)e * kVecThreads;
-                if (c < P.d) s[e] = fma(ci, vi[c], s[e]);
-            }
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int64_t c = base + (int64_t)e * kVecThreads;
+                    vv[u][e] = (i0 + u < nv && c < P.d) ? P.V[(size_t)(i0 + u) * P.d + c] : 0.0;
+                }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (i0 + u < nv) {
+                    const double ci = scoef[i0 + u];
+#pragma unroll
+                    for (int e = 0; e < E; ++e) s[e] = fma(ci, vv[u][e], s[e]);
+                }
         }
 #pragma unroll
         for (int e = 0; e < E; ++e) x[e] -= s[e];
@@ -340,17 +353,26 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P
         return;
     }
 
-    // stages 1, 2: dots of the updated vector with every basis column built so far
-    for (int i = 0; i < nv; ++i) {
-        const double *vi = P.V + (size_t)i * P.d;
-        double loc = 0.0;
+    // stages 1, 2: dots of the updated vector with every basis column built so far (eight columns per batch)
+    for (int i0 = 0; i0 < nv; i0 += 8) {
+        double vv[8][E];
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const int64_t c = base + (int64_t)e * kVecThreads;
-            if (c < P.d) loc = fma(vi[c], x[e], loc);
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int64_t c = base + (int64_t)e * kVecThreads;
+                vv[u][e] = (i0 + u < nv && c < P.d) ? P.V[(size_t)(i0 + u) * P.d + c] : 0.0;
+            }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (i0 + u < nv) {
+                double loc = 0.0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) loc = fma(vv[u][e], x[e], loc);
+                loc = warp_sum(loc);
+                if (lane == 0) sdots[warp][i0 + u] = loc;
+            }
         }
-        loc = warp_sum(loc);
-        if (lane == 0) sdots[warp][i] = loc;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < nv; i += blockDim.x) {

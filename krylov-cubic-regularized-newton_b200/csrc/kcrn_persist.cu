@@ -759,7 +759,7 @@ __global__ void __launch_bounds__(kPThreads) persist_words_kernel(const PTile *_
     }
 }
 
-int build_persist_mat(const SegMat &A, const int32_t *renumber, int grid, PersistMat *M, cudaStream_t s, bool *ok) {
+int build_persist_mat(const SegMat &A, const int32_t *renumber, int grid, PersistMat *M, cudaStream_t s, bool *ok, bool verbose) {
     *ok = false;
     std::vector<int32_t> ptr((size_t)A.nseg + 1);
     KCRN_CUDA(cudaMemcpyAsync(ptr.data(), A.ptr, sizeof(int32_t) * (A.nseg + 1), cudaMemcpyDeviceToHost, s));
@@ -784,7 +784,7 @@ int build_persist_mat(const SegMat &A, const int32_t *renumber, int grid, Persis
     persist_words_kernel<<<(unsigned)tiles.size(), kPThreads, smem, s>>>(M->tiles, A.idx, A.val, renumber, M->word, M->tval);
     KCRN_LAUNCH_CHECK();
     KCRN_CUDA(cudaStreamSynchronize(s));
-    if (getenv("KCRN_VERBOSE"))
+    if (verbose)
         fprintf(stderr, "kcrn: persistent tiles: %lld segments, %lld non-zeros -> %d tiles (%d cut segments, %d pieces)\n",
                 (long long)A.nseg, (long long)A.nnz, M->ntiles, M->nlong, npartial);
     *ok = true;
@@ -811,8 +811,7 @@ int persist_build(kcrn_problem *h) {
     h->persist_ok = false;
     // Opt-in (KCRN_PERSIST=1): measured on a B200 it is correct but slower than the graph of per-pass kernels at the
     // rcv1 shape (27 vs 20.7 us per HVP; DESIGN.md section 3.4 has the per-phase trace and why)
-    const char *on = getenv("KCRN_PERSIST");
-    if (!on || atoi(on) == 0 || h->sharded() || h->nnz <= 0) return KCRN_OK;
+    if (!h->sw.persist || h->sharded() || h->nnz <= 0) return KCRN_OK;
     if (h->d >= kPMaxIndex - 1 || h->n >= kPMaxIndex - 1) return KCRN_OK;
     int dev = 0, sms = 0, per_sm = 0;
     KCRN_CUDA(cudaGetDevice(&dev));
@@ -822,8 +821,8 @@ int persist_build(kcrn_problem *h) {
     if (per_sm < 1 || sms < 1) return KCRN_OK;
     const int grid = sms;                      // one CTA per SM: the barrier needs all of them resident
     bool okr = false, okc = false;
-    KCRN_TRY(build_persist_mat(h->csr, h->csc.pos, grid, &h->prow, h->stream, &okr));     // rows gather stored positions
-    if (okr) KCRN_TRY(build_persist_mat(h->csc, nullptr, grid, &h->pcol, h->stream, &okc));
+    KCRN_TRY(build_persist_mat(h->csr, h->csc.pos, grid, &h->prow, h->stream, &okr, h->sw.verbose));     // rows gather stored positions
+    if (okr) KCRN_TRY(build_persist_mat(h->csc, nullptr, grid, &h->pcol, h->stream, &okc, h->sw.verbose));
     if (!okr || !okc) { persist_free(h); return KCRN_OK; }
     h->persist_grid = grid;
     KCRN_CUDA(cudaMalloc(&h->gp, sizeof(double) * h->d));
@@ -835,7 +834,7 @@ int persist_build(kcrn_problem *h) {
     KCRN_CUDA(cudaMalloc(&h->pbar, sizeof(unsigned) * 2));
     KCRN_CUDA(cudaMemsetAsync(h->pbar, 0, sizeof(unsigned) * 2, h->stream));
     KCRN_CUDA(cudaStreamSynchronize(h->stream));
-    if (getenv("KCRN_PERSIST_TRACE")) {
+    if (h->sw.persist_trace) {
         KCRN_CUDA(cudaMalloc(&h->ptrace, sizeof(long long) * (size_t)grid * kPTraceCap));
         KCRN_CUDA(cudaMemset(h->ptrace, 0, sizeof(long long) * (size_t)grid * kPTraceCap));
     }
@@ -914,7 +913,7 @@ int launch_persist_lanczos(kcrn_problem *h, int m) {
     P.cta_slots = h->pslots; P.piece_slots = h->pslots + (size_t)2 * 2 * h->persist_grid; P.piece_cap = h->piece_cap;
     P.epoch_base = h->pbar;
     P.trace = h->ptrace;
-    P.flags = getenv("KCRN_PERSIST_FLAGS") ? atoi(getenv("KCRN_PERSIST_FLAGS")) : 0;
+    P.flags = h->sw.persist_flags;
     // no programmatic launch attribute: all CTAs must become resident, nothing may be waiting for this kernel's
     // trigger on the SMs it needs
     KCRN_CUDA(launch_kernel(persist_lanczos_kernel, dim3(h->persist_grid), dim3(kPThreads), kPSmemBytes, h->stream, false, P));

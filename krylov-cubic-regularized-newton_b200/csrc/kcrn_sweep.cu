@@ -161,10 +161,9 @@ __global__ void __launch_bounds__(kSweepThreads) gather_order_kernel(const int4 
 // Pure host logic (no device): the tile list of one matrix from its pointer array.  Also behind kcrn_plan_tiles, so
 // that the CPU test suite can check its invariants on arbitrary segment-length distributions.
 void plan_tiles(const std::vector<int32_t> &ptr, int64_t nseg, int64_t nnz, std::vector<int4> &tiles,
-                std::vector<int4> &longtab, int &npartial, int &items) {
-    const char *env_short = getenv("KCRN_SHORT_SEG");       // tuning knob: longest segment that shares a tile
-    const char *env_items = getenv("KCRN_TILE_ITEMS");      // tuning knob: force 8, 11 or 12 non-zeros per thread
-    if (env_items && atoi(env_items) == 0) env_items = nullptr;
+                std::vector<int4> &longtab, int &npartial, int &items, const Switches &sw) {
+    const bool env_short = sw.short_seg > 0;                // tuning knob: longest segment that shares a tile
+    const bool env_items = sw.tile_items > 0;               // tuning knob: force 8, 11 or 12 non-zeros per thread
     npartial = 0;
     const int cand[3] = {8, 11, 12};
     const int slots = kNumSm * 4 - 32;                      // resident CTAs, minus a margin for the neighbours under PDL
@@ -172,10 +171,10 @@ void plan_tiles(const std::vector<int32_t> &ptr, int64_t nseg, int64_t nnz, std:
     items = 8;
     long best_waves = -1;
     for (int c : cand) {
-        if (env_items && atoi(env_items) != c) continue;
+        if (env_items && sw.tile_items != c) continue;
         const int tile_nnz = c * kSweepThreads;
         // few waves: also let segments of up to 2048 share tiles (fewer, fuller tiles; measured 24.6 -> 24.0 us per HVP)
-        const int ss = env_short ? std::max(1, std::min(tile_nnz, atoi(env_short))) : 2 * kShortSeg;
+        const int ss = env_short ? std::max(1, std::min(tile_nnz, sw.short_seg)) : 2 * kShortSeg;
         make_tiles(ptr, nseg, nnz, tile_nnz, c == 8 && !env_short ? kShortSeg : ss, tiles, longtab, npartial);
         long waves = ((long)tiles.size() + slots - 1) / slots;
         if (c == 8 && waves > 4 && !env_items) { items = 8; short_seg = env_short ? ss : kShortSeg; best_waves = waves; break; }
@@ -188,7 +187,7 @@ void plan_tiles(const std::vector<int32_t> &ptr, int64_t nseg, int64_t nnz, std:
     make_tiles(ptr, nseg, nnz, items * kSweepThreads, short_seg, tiles, longtab, npartial);
 }
 
-int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s) {
+int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s, const Switches &sw) {
     A->gather_len = gather_len;
     const int64_t nseg = A->nseg;
     std::vector<int32_t> ptr((size_t)nseg + 1);
@@ -196,10 +195,10 @@ int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s) {
     KCRN_CUDA(cudaStreamSynchronize(s));
     std::vector<int4> tiles, longtab;
     int npartial = 0, items = 8;
-    plan_tiles(ptr, nseg, A->nnz, tiles, longtab, npartial, items);
+    plan_tiles(ptr, nseg, A->nnz, tiles, longtab, npartial, items, sw);
     const int tile_nnz = items * kSweepThreads;
     A->items = items;
-    if (getenv("KCRN_VERBOSE"))
+    if (sw.verbose)
         fprintf(stderr, "kcrn: %lld segments, %lld non-zeros -> %zu tiles of %d (%zu long segments)\n", (long long)nseg,
                 (long long)A->nnz, tiles.size(), tile_nnz, longtab.size());
     A->ntiles = (int)tiles.size();
@@ -219,7 +218,7 @@ int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s) {
         KCRN_CUDA(cudaMemcpyAsync(A->longtab, longtab.data(), sizeof(int4) * longtab.size(), cudaMemcpyHostToDevice, s));
     // gather-ordered copy for the sweeps (KCRN_NO_GATHER_ORDER=1: A/B switch, sweeps read idx / val as stored)
     if (A->nnz > 0 && A->ntiles > 0 && gather_len <= ((int64_t)1 << (32 - kSlotBits)) && tile_nnz <= kSortCap &&
-        getenv("KCRN_NO_GATHER_ORDER") == nullptr) {
+        !sw.no_gather_order) {
         KCRN_CUDA(cudaMalloc(&A->gidx, sizeof(uint32_t) * (size_t)A->nnz));
         KCRN_CUDA(cudaMalloc(&A->gval, sizeof(double) * ((size_t)A->nnz + 2)));      // + 2: 16-byte pairs may straddle the end
         KCRN_CUDA(cudaMemsetAsync(A->gval + A->nnz, 0, sizeof(double) * 2, s));
@@ -854,24 +853,12 @@ int launch_rows_weighted(kcrn_problem *h, const double *v) {
 
 int gather_candidates_last() { return kGatherAsync; }
 
-// KCRN_GATHER="p[,l]" forces the gather variant of the plain / Lanczos passes (A/B switch); -1: measure
-void forced_gather_variants(int *plain, int *lanczos) {
-    *plain = *lanczos = -1;
-    const char *e = getenv("KCRN_GATHER");
-    if (!e) return;
-    int a = -1, b = -1;
-    const int k = sscanf(e, "%d,%d", &a, &b);
-    if (k >= 1 && a >= 0 && a < kGatherVariants) *plain = *lanczos = a;
-    if (k >= 2 && b >= 0 && b < kGatherVariants) *lanczos = b;
-}
-
 // Which gather variant serves the passes outside the Lanczos recurrence: measured per matrix on the weighted row
 // pass / the scaled column pass, a few back-to-back launches each (the operands are zeroed scratch; all variants
 // compute the same bits, so the choice never shows in a result).  The Lanczos passes are measured at their first
 // use (kcrn_api.cu: tune_lanczos_sweeps), when a gradient to start the recurrence from exists.
 int tune_plain_sweeps(kcrn_problem *h) {
-    int fp, fl;
-    forced_gather_variants(&fp, &fl);
+    const int fp = h->sw.gather_plain, fl = h->sw.gather_lanczos;      // KCRN_GATHER (A/B switch); -1: measure
     for (SegMat *A : {&h->csr, &h->csc}) {
         A->gather_plain = A->gather_lanczos = kGatherStored;
         if (!A->gidx) continue;
@@ -911,7 +898,7 @@ int tune_plain_sweeps(kcrn_problem *h) {
                 if (bt == 0 || t < ms) ms = t;
             }
             if (v == kGatherStored || ms < best_ms) { best = v; best_ms = ms; }
-            if (getenv("KCRN_VERBOSE"))
+            if (h->sw.verbose)
                 fprintf(stderr, "kcrn: %s pass, gather variant %d: %.2f us\n", which == 0 ? "row" : "column", v, 1e3 * ms / reps);
         }
         A->gather_plain = best;

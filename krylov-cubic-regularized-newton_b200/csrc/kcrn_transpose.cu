@@ -249,7 +249,7 @@ int exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t len, cudaStream_
     return KCRN_OK;
 }
 
-int build_csc(const SegMat &csr, int64_t n_cols, SegMat *csc, cudaStream_t s) {
+int build_csc(const SegMat &csr, int64_t n_cols, SegMat *csc, cudaStream_t s, bool natural_order) {
     const int64_t nnz = csr.nnz, n_rows = csr.nseg;
     csc->nseg = n_cols;
     csc->nnz = nnz;
@@ -275,7 +275,7 @@ int build_csc(const SegMat &csr, int64_t n_cols, SegMat *csc, cudaStream_t s) {
         KCRN_CUDA(cudaMemcpyAsync(cnt.data(), counts, sizeof(int32_t) * n_cols, cudaMemcpyDeviceToHost, s));
         KCRN_CUDA(cudaStreamSynchronize(s));
         cudaFree(counts);
-        const bool natural = getenv("KCRN_NATURAL_CSC") != nullptr;   // A/B switch: keep the scipy column order
+        const bool natural = natural_order;   // A/B switch: keep the scipy column order
         auto cls = [natural](int len) { return natural ? 0 : len <= 8 ? 0 : len <= 32 ? 1 : len <= 128 ? 2 : len <= 512 ? 3 : len <= kTileNnz ? 4 : 5; };
         int64_t start[7] = {0, 0, 0, 0, 0, 0, 0};
         for (int64_t c = 0; c < n_cols; ++c) start[cls(cnt[c]) + 1] += 1;

@@ -49,7 +49,10 @@ def join_communicator(engine, rank: int, world: int, peer_exchange: bool = True)
 
 
 def shard_rows(P, rank: int, world: int):
-    """Contiguous row block of problem P for this rank, balanced by non-zeros."""
+    """Contiguous row block of problem P for this rank, balanced by non-zeros.
+
+    Labels: build every shard's oracle with ``LogisticRegression(shard, shard_b, label_encoding=label_encoding(P.b))``
+    (optimizer.loss) -- the {0, 1} encoding is a property of the GLOBAL label vector (reference loss.py:190-207)."""
     from .synth import balanced_row_cuts
 
     cuts = balanced_row_cuts(P.indptr, world)

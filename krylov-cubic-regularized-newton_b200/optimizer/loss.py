@@ -28,10 +28,27 @@ def _is_tensor(x) -> bool:
     return hasattr(x, "data_ptr")
 
 
-def map_labels(b):
-    """Binary labels -> {0, 1} the way the reference does it (loss.py:190-207)."""
+def label_encoding(b):
+    """The {0, 1} encoding the reference picks for a label vector (loss.py:190-207), as a plain tuple -- compute it ONCE
+    on the global labels of a row-sharded problem and hand it to every shard's LogisticRegression(label_encoding=...):
+    a shard that holds a single class, or whose first label differs from the global first label, would otherwise encode
+    differently from its peers."""
     b = np.asarray(b)
     classes = np.unique(b)
+    if classes.size > 2:
+        raise ValueError("The number of classes must be no more than 2 for binary classification.")
+    return (tuple(float(c) for c in classes), float(b[0]) if b.size else 0.0)
+
+
+def map_labels(b, encoding=None):
+    """Binary labels -> {0, 1} the way the reference does it (loss.py:190-207); `encoding` = label_encoding(global b)."""
+    b = np.asarray(b)
+    if encoding is None:
+        classes, first = np.unique(b), (b[0] if b.size else 0.0)
+    else:
+        classes, first = np.asarray(encoding[0]), encoding[1]
+        if np.setdiff1d(np.unique(b), classes).size:
+            raise ValueError("labels outside the given encoding")
     if classes.size == 1:
         warnings.warn("The labels have only one unique value.")
     if classes.size > 2:
@@ -41,7 +58,7 @@ def map_labels(b):
             return (b - 1).astype(np.float64)
         if np.array_equal(classes, [-1, 1]):
             return ((b + 1) / 2).astype(np.float64)
-        return 1.0 * (b == b[0])
+        return 1.0 * (b == first)
     return b.astype(np.float64)
 
 
@@ -79,7 +96,7 @@ class Oracle:
 class LogisticRegression(Oracle):
     """f(x) = mean((1 - b) .* Ax - logsig(Ax)) + l2/2 |x|^2 on a sparse A, evaluated on the GPU."""
 
-    def __init__(self, A, b, store_mat_vec_prod=False, *args, device=None, n_global=None, **kwargs):
+    def __init__(self, A, b, store_mat_vec_prod=False, *args, device=None, n_global=None, label_encoding=None, **kwargs):
         super().__init__(*args, **kwargs)
         import scipy.sparse as sp
 
@@ -87,7 +104,7 @@ class LogisticRegression(Oracle):
         if A.dtype != np.float64:
             A = A.astype(np.float64)
         self.A = A
-        self.b = map_labels(b)
+        self.b = map_labels(b, label_encoding)      # row shards: pass label_encoding(global labels)
         self.store_mat_vec_prod = store_mat_vec_prod
         self.reuse = False
         self.n, self.dim = A.shape

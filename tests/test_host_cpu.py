@@ -56,6 +56,13 @@ def test_label_mapping_matches_reference(golden):
         assert np.array_equal(map_labels(g[f"label_in{i}"]), g[f"label_out{i}"])
     with pytest.raises(ValueError):
         map_labels(np.array([0., 1., 2.]))
+    # row shards take the encoding of the GLOBAL labels: a single-class shard and a shard starting with the other label
+    from optimizer.loss import label_encoding
+    b = np.array([3., 5., 5., 3., 5., 5.])
+    enc = label_encoding(b)
+    assert np.array_equal(np.concatenate([map_labels(b[:4], enc), map_labels(b[4:], enc)]), map_labels(b))
+    b = np.array([-1., 1., 1., 1.])
+    assert np.array_equal(map_labels(b[1:], label_encoding(b)), map_labels(b)[1:])
 
 
 class _QuadLoss:
