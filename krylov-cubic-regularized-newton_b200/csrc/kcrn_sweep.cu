@@ -600,28 +600,22 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         const int seg0 = td.x, k0 = td.y, z = td.z, nk = td.w & 0xffff, tag = td.w >> 16;
         const bool stream = z > 0 && tag != kSingleTag;
         int4 lt = make_int4(0, 1, 0, 0);
-        // epilogue operands to registers: in flight while the gathers run
-        double o0[NOP > 0 ? kSegRounds : 1], o1[NOP > 1 ? kSegRounds : 1];
+        // epilogue operands of the FIRST segment round to registers: in flight while the gathers run.  (Tiles of more
+        // than 256 segments -- runs of tiny columns -- fetch the operands of their later rounds when they need them:
+        // four rounds of prefetched operands cost the Lanczos passes 9 to 15 registers they do not have.)
+        double o0 = 0.0, o1 = 0.0;
         double e0 = 0.0, e1 = 0.0;           // operands of a single-segment tile (thread 0)
-        int sid[kSegRounds];
-        sid[0] = seg0;
+        int sid0 = seg0;
         if (stream) {
-#pragma unroll
-            for (int r = 0; r < kSegRounds; ++r) {
-                const int sg = r * kSweepThreads + tid;
-                if (sg < z) {
-                    sid[r] = P.segid ? __ldg(P.segid + seg0 + sg) : seg0 + sg;
-                    double a0, a1;
-                    load_operands<MODE>(P, S, sid[r], a0, a1);
-                    if constexpr (NOP > 0) o0[r] = a0;
-                    if constexpr (NOP > 1) o1[r] = a1;
-                }
+            if (tid < z) {
+                sid0 = P.segid ? __ldg(P.segid + seg0 + tid) : seg0 + tid;
+                load_operands<MODE>(P, S, sid0, o0, o1);
             }
         } else {
             if (z < 0) lt = __ldg(P.longtab + (-z - 1));
             if (tid == 0) {
-                if (P.segid) sid[0] = __ldg(P.segid + seg0);
-                load_operands<MODE>(P, S, sid[0], e0, e1);
+                if (P.segid) sid0 = __ldg(P.segid + seg0);
+                load_operands<MODE>(P, S, sid0, e0, e1);
             }
         }
         if (!gathered) gather_from(S.src);
@@ -660,7 +654,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
             for (int r = 0; r < kItems; ++r) s += p[r];
             const double tot = cta_sum_to_thread0(s, sred);
             if (z > 0) {
-                if (tid == 0) finish_segment<MODE>(P, S, sid[0], tot, -1, e0, e1, acc);
+                if (tid == 0) finish_segment<MODE>(P, S, sid0, tot, -1, e0, e1, acc);
             } else {
                 const int lseg = -z - 1;
                 if (tid == 0) {
@@ -675,7 +669,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
                     for (int i = lane; i < lt.y; i += 32) all += __ldcg(P.partial + lt.x + i);
                     all = warp_sum(all);
                     // thread 0 holds the operands
-                    if (tid == 0) finish_segment<MODE>(P, S, sid[0], all, lseg, e0, e1, acc);
+                    if (tid == 0) finish_segment<MODE>(P, S, sid0, all, lseg, e0, e1, acc);
                 }
             }
         } else {
@@ -703,7 +697,13 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
             for (int r = 0; r < kSegRounds; ++r) {
                 const int sg = r * kSweepThreads + tid;
                 if (sg < z) {
-                    finish_segment<MODE>(P, S, sid[r], ssum[sg], -1, NOP > 0 ? o0[r] : 0.0, NOP > 1 ? o1[r] : 0.0, acc);
+                    int sidr = sid0;
+                    double a0 = o0, a1 = o1;
+                    if (r > 0) {
+                        sidr = P.segid ? __ldg(P.segid + seg0 + sg) : seg0 + sg;
+                        load_operands<MODE>(P, S, sidr, a0, a1);
+                    }
+                    finish_segment<MODE>(P, S, sidr, ssum[sg], -1, a0, a1, acc);
                 }
             }
         }
