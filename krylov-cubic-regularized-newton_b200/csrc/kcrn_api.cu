@@ -465,6 +465,10 @@ int kcrn_create(kcrn_handle *out, int64_t n_rows, int64_t n_cols, int64_t nnz, c
         KCRN_CUDA(cudaMallocHost(&h->rec_host, sizeof(double) * 16));
         h->vec_elems = n_cols > (int64_t)kNumSm * kVecThreads * 4 ? 4 : 1;
         h->vec_grid = (int)((n_cols + (int64_t)kVecThreads * h->vec_elems - 1) / ((int64_t)kVecThreads * h->vec_elems));
+#ifdef KCRN_SWEEP_TRACE
+        KCRN_CUDA(cudaMalloc(&h->sweep_trace, sizeof(unsigned long long) * 64 * 1024 * 12));
+        KCRN_CUDA(cudaMemset(h->sweep_trace, 0, sizeof(unsigned long long) * 64 * 1024 * 12));
+#endif
         KCRN_TRY(lanczos_alloc(h, 1));
         KCRN_TRY(tune_plain_sweeps(h));
         KCRN_TRY(persist_build(h));
@@ -480,9 +484,47 @@ int kcrn_create(kcrn_handle *out, int64_t n_rows, int64_t n_cols, int64_t nnz, c
     return KCRN_OK;
 }
 
+#ifdef KCRN_SWEEP_TRACE
+// where the time of the LAST captured recurrence went: per pass (slot), the marks of thread 0 of every CTA
+static void print_sweep_trace(kcrn_problem *h) {
+    const int slots = 20;
+    std::vector<unsigned long long> T((size_t)slots * 1024 * 12);
+    if (cudaMemcpy(T.data(), h->sweep_trace, sizeof(unsigned long long) * T.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    const char *name[9] = {"entry -> loads requested", "wait for predecessor", "control block (+ deferred sum)", "basis column, operands",
+                           "gathers land", "multiply, scatter", "segment sums", "epilogue", "tail sums"};
+    unsigned long long prev_end = 0;
+    for (int sl = 0; sl < slots; ++sl) {
+        const int grid = sl % 2 == 0 ? h->csr.grid : h->csc.grid;
+        unsigned long long t0min = ~0ull, t9max = 0, t2min = ~0ull;
+        double sum[9] = {0}, mx[9] = {0};
+        int cnt = 0;
+        for (int c = 0; c < grid && c < 1024; ++c) {
+            const unsigned long long *t = T.data() + ((size_t)sl * 1024 + c) * 12;
+            if (t[0] == 0 || t[9] == 0) continue;
+            ++cnt;
+            t0min = std::min(t0min, t[0]); t9max = std::max(t9max, t[9]); t2min = std::min(t2min, t[2]);
+            for (int k = 0; k < 9; ++k) {
+                const double d = t[k + 1] >= t[k] && t[k + 1] != 0 && t[k] != 0 ? (double)(t[k + 1] - t[k]) : 0.0;
+                sum[k] += d; mx[k] = std::max(mx[k], d);
+            }
+        }
+        if (!cnt) continue;
+        fprintf(stderr, "kcrn: sweep trace slot %2d (%s, %d CTAs): first entry -> last end %6.0f ns; gap after previous pass %6.0f ns; first entry -> first released %5.0f ns\n",
+                sl, sl % 2 == 0 ? "rows" : "cols", cnt, (double)(t9max - t0min), prev_end ? (double)t0min - (double)prev_end : 0.0, (double)(t2min - t0min));
+        if (sl == 6 || sl == 7)
+            for (int k = 0; k < 9; ++k) fprintf(stderr, "kcrn:     %-32s mean %6.0f  max %6.0f ns\n", name[k], sum[k] / cnt, mx[k]);
+        prev_end = t9max;
+    }
+}
+#endif
+
 int kcrn_destroy(kcrn_handle h) {
     if (!h) return KCRN_OK;
     cudaStreamSynchronize(h->stream);
+#ifdef KCRN_SWEEP_TRACE
+    if (h->sweep_trace) print_sweep_trace(h);
+    cudaFree(h->sweep_trace);
+#endif
     // captured graphs hold NCCL work: they must be gone before the communicator is torn down
     for (auto &ge : h->graphs) cudaGraphExecDestroy(ge.exec);
     h->graphs.clear();

@@ -284,6 +284,7 @@ struct kcrn_problem {
     unsigned *pbar = nullptr;      // [0] exchanges done so far (epoch of the slots)
     long long *ptrace = nullptr;   // KCRN_PERSIST_TRACE=1: SM clock at the marks of the last launch
     kcrn::Switches sw;             // environment switches as they were at kcrn_create
+    unsigned long long *sweep_trace = nullptr;   // -DKCRN_SWEEP_TRACE builds only: %globaltimer marks of the Lanczos passes
     bool lanczos_tuned = false;    // the gather variants of the Lanczos passes have been measured (first use)
     bool pdl = false;              // launch with programmatic dependent launch (set while the Lanczos graph is built)
     bool allow_pdl = true;         // KCRN_NO_PDL=1 switches it off

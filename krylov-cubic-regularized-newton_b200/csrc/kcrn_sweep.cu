@@ -39,6 +39,29 @@
 #include "kcrn_device.cuh"
 #include "kcrn_internal.cuh"
 
+// timing probe only (profiles/microbench/build_variants.sh -DKCRN_PROBE_NOSCATTER): products stay at their gather-order
+// position -- wrong sums, conflict-free shared-memory writes: what the bank conflicts of the scatter cost
+#ifdef KCRN_PROBE_NOSCATTER
+#define KCRN_SLOT(slot, pos) (pos)
+#else
+#define KCRN_SLOT(slot, pos) (slot)
+#endif
+
+// timing probe only (-DKCRN_SWEEP_TRACE, profiles/microbench/build_variants.sh): thread 0 of every CTA of the Lanczos
+// passes leaves %globaltimer at the phase boundaries; kcrn_destroy prints where a pass's time goes
+#ifdef KCRN_SWEEP_TRACE
+#define KTRACE(k)                                                                                                   \
+    do {                                                                                                            \
+        if (P.trace && threadIdx.x == 0) {                                                                          \
+            unsigned long long t_;                                                                                  \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                                  \
+            P.trace[((size_t)P.trace_slot * 1024 + blockIdx.x) * 12 + (k)] = t_;                                    \
+        }                                                                                                           \
+    } while (0)
+#else
+#define KTRACE(k)
+#endif
+
 namespace kcrn {
 
 // How the gathered values of a tile travel (template parameter GATHER of the sweep kernel; all three give the same
@@ -281,6 +304,10 @@ struct SweepParams {
     double *alpha_raw, *alpha_raw2; // raw sums sum_i t_i (Av)_i (allreduced later) and |v|^2 for alpha_mode 1
     int update_ctl;                // cols-Lanczos: 1 = finish beta and advance the recurrence here
     // fused single-GPU loop (defer = 2) only:
+#ifdef KCRN_SWEEP_TRACE
+    unsigned long long *trace;     // [slots][1024 CTAs][12 marks]
+    int trace_slot;
+#endif
     int init_here, m_init;         // rows-Lanczos, first pass: |g| is still in the pieces the gradient sweep left; the
                                    // recurrence state of an m_init-step run starts here (no separate init kernel)
 };
@@ -444,6 +471,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
     // of the stream: with programmatic dependent launch this CTA may already be resident while that kernel is
     // still finishing, so the descriptor -> (index, value) part of the latency chain overlaps with its tail.
     const int tile = blockIdx.x;
+    KTRACE(0);                       // kernel entry
     int4 td = make_int4(0, 0, 0, 0);
     int ci[kItems];                  // index, or gather-ordered word (index << kSlotBits | natural position); -1: none
     double av[kItems];
@@ -466,7 +494,9 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
             }
         }
     }
+    KTRACE(1);                       // matrix-only loads requested
     pdl_wait();      // the previous kernel's results (control block, vectors) are complete and visible from here on
+    KTRACE(2);                       // predecessor complete
 
     SweepState S;
     S.src = P.src;
@@ -481,7 +511,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
             if constexpr (kAsyncGather) {
                 const int i = r * kSweepThreads + tid;
                 if (ci[r] != -1)
-                    cp_async_8(sprod + (ordered ? (ci[r] & ((1 << kSlotBits) - 1)) : i), src + gather_index(ci[r], ordered));
+                    cp_async_8(sprod + KCRN_SLOT(ordered ? (ci[r] & ((1 << kSlotBits) - 1)) : i, i), src + gather_index(ci[r], ordered));
             } else {
                 xv[r] = ci[r] != -1 ? __ldg(src + gather_index(ci[r], ordered)) : 0.0;
             }
@@ -582,6 +612,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         }
     }
 
+    KTRACE(3);                       // control block known (and the sum this kernel had to finish)
     double acc = 0.0;
     double vsq = 0.0;
     if constexpr (MODE == kRowsLanczos) {
@@ -618,6 +649,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
                 load_operands<MODE>(P, S, sid0, e0, e1);
             }
         }
+        KTRACE(4);                   // basis column stored, operands requested
         if (!gathered) gather_from(S.src);
         if constexpr (MODE == kColsLanczos) {
             if (alpha_pending) {                 // the gathers above are in flight while the pieces are added
@@ -640,6 +672,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
                 xv[r] = i < nk ? sprod[i] : 0.0;
             }
         }
+        KTRACE(5);                   // gathered values have arrived (and alpha, columns)
         double p[kItems];
 #pragma unroll
         for (int r = 0; r < kItems; ++r) {
@@ -676,10 +709,11 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
 #pragma unroll
             for (int r = 0; r < kItems; ++r) {
                 const int i = r * kSweepThreads + tid;
-                if (i < nk) sprod[GATHER == kGatherOrdered ? (ci[r] & ((1 << kSlotBits) - 1)) : i] = p[r];   // the natural position
+                if (i < nk) sprod[KCRN_SLOT(GATHER == kGatherOrdered ? (ci[r] & ((1 << kSlotBits) - 1)) : i, i)] = p[r];   // the natural position
             }
             cp_async_wait_all();
             __syncthreads();
+            KTRACE(6);               // products in their natural slots
             // phase A: every group of G threads sums one segment from shared memory, left to right
             const int G = 1 << tag, groups = kSweepThreads >> tag, gid = tid >> tag, gl = tid & (G - 1);
             for (int sb = 0; sb < z; sb += groups) {
@@ -692,6 +726,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
                 if (sg < z && gl == 0) ssum[sg] = sum;
             }
             __syncthreads();
+            KTRACE(7);               // segment sums
             // phase B: one thread per segment applies the epilogue, coalesced
 #pragma unroll
             for (int r = 0; r < kSegRounds; ++r) {
@@ -711,6 +746,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
 
     // The tile is done: from here on only the short reduction tails remain, so the next kernel of the stream may
     // become resident and start its own (matrix-only) loads while they run -- it still waits for our completion.
+    KTRACE(8);                       // epilogue stored
     pdl_trigger();
 
     if constexpr (MODE == kColsScaled) {
@@ -737,7 +773,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
             P.red_partials[blockIdx.x] = mine;
             P.red_partials[((gridDim.x + 1) & ~1u) + blockIdx.x] = mine2;      // even stride: 16-byte copies later
         }
-        if (P.defer) return;
+        if (P.defer) { KTRACE(9); return; }
         if (tid == 0) {
             __threadfence();
             s_last = atomicInc(P.red_ticket, gridDim.x - 1) == gridDim.x - 1;
@@ -776,7 +812,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         __syncthreads();
         const double mine = cta_sum_to_thread0(acc, sred);
         if (tid == 0) P.red_partials[blockIdx.x] = mine;
-        if (P.defer) return;
+        if (P.defer) { KTRACE(9); return; }
         if (tid == 0) {
             __threadfence();
             s_last = atomicInc(P.red_ticket, gridDim.x - 1) == gridDim.x - 1;
@@ -792,6 +828,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
             if (tid == 0) lanczos_advance(P.ctl, P.bet, sqrt(bsq));
         }
     }
+    KTRACE(9);                       // tail sums written
 }
 
 void fill_matrix(SweepParams &P, const SegMat &A) {
@@ -938,6 +975,9 @@ int launch_rows_lanczos(kcrn_problem *h, double *alpha_raw, int slot, int defer,
         P.ctl_in = P.ctl = h->ctl;
     }
     P.red_partials = defer ? h->lan_rows_part : h->red_partials; P.red_ticket = h->red_ticket + 7;
+#ifdef KCRN_SWEEP_TRACE
+    P.trace = h->sweep_trace; P.trace_slot = 2 * slot;
+#endif
     h->counters[3] += 1;
     return launch<kRowsLanczos>(h, h->csr, P);
 }
@@ -969,6 +1009,9 @@ int launch_cols_lanczos(kcrn_problem *h, int update_ctl, int slot, int defer) {
         P.prev_part = h->lan_rows_part; P.prev_count = h->csr.grid; P.prev_longdot = h->csr.longdot; P.prev_nlong = h->csr.nlong;
     }
     P.red_partials = defer ? h->lan_cols_part : h->red_partials; P.red_ticket = h->red_ticket + 0;
+#ifdef KCRN_SWEEP_TRACE
+    P.trace = h->sweep_trace; P.trace_slot = 2 * slot + 1;
+#endif
     h->counters[4] += 1;
     return launch<kColsLanczos>(h, h->csc, P);
 }
