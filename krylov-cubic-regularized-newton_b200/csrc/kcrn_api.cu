@@ -129,8 +129,14 @@ int enqueue_lanczos(kcrn_problem *h, int m, int reorth, bool allow_persist = tru
     // single GPU: the grid-wide sums (alpha after the row sweep, beta after the column sweep) are finished by the
     // kernel that consumes them -- 2: both, the row sweep also advances the recurrence; 1: alpha only (the
     // re-orthogonalisation kernel owns beta and the advance).  Row-sharded: 0, the exchange kernels own both.
-    const int defer = (h->sharded() || h->sw.no_defer || !lanczos_defer_fits(h)) ? 0 : (reorth ? 1 : 2);
-    const bool self_init = g_pieces && defer == 2;        // the first row sweep starts the recurrence itself
+    // Row-sharded with the peer exchange (or the one-GPU emulation of that path), no re-orthogonalisation: 2 as well -- the
+    // epilogue kernel after the exchange adds the alpha pieces of the row sweep, the next row sweep the beta pieces of the
+    // epilogue kernel (round 1 finished both with last-CTA tails: two fences + an atomic + a serial sum per HVP).  With
+    // NCCL in front of the epilogue the alpha piece must be inside the allreduced buffer: 0.
+    const bool shard_defer = h->sharded() && !reorth && (h->p2p_ready || h->world == 1);
+    const int defer = ((h->sharded() && !shard_defer) || h->sw.no_defer || !lanczos_defer_fits(h)) ? 0 : (reorth ? 1 : 2);
+    const bool self_init = g_pieces && defer == 2 && !h->sharded();   // the first row sweep starts the recurrence itself
+                                                                      // (a row-sharded gradient leaves no pieces of |g|^2)
     if (!self_init) KCRN_TRY(launch_lanczos_init(h, m));
     for (int slot = 0; slot < m; ++slot) {
         // rows sweep: t = D (A v), basis column, and alpha = v'Hv one sweep early (so that the column sweep can
@@ -138,19 +144,21 @@ int enqueue_lanczos(kcrn_problem *h, int m, int reorth, bool allow_persist = tru
         KCRN_TRY(launch_rows_lanczos(h, h->ypart + h->d, slot, defer, self_init ? m : 0));
         if (h->sharded()) {
             KCRN_TRY(launch_cols_raw(h, h->t, h->ypart));
+            const int dslot = defer == 2 ? slot : -1;
             if (h->p2p_ready) {
                 // small d: the sum over the ranks happens inside the epilogue kernel, over NVLink peer memory
-                KCRN_TRY(launch_lanczos_post_peer(h, h->ypart, reorth));
+                KCRN_TRY(launch_lanczos_post_peer(h, h->ypart, reorth, dslot));
             } else {
                 KCRN_TRY(nccl_allreduce_sum(h, h->ypart, (h->d + 2) & ~(int64_t)1));   // even count: 16-byte multiple
-                KCRN_TRY(launch_lanczos_post_sharded(h, h->ypart, reorth));
+                KCRN_TRY(launch_lanczos_post_sharded(h, h->ypart, reorth, dslot));
             }
         } else if (slot + 1 < m) {
             KCRN_TRY(launch_cols_lanczos(h, reorth ? 0 : 1, slot, defer));
         }
         if (reorth && slot + 1 < m) KCRN_TRY(launch_lanczos_update(h, 1, 1));
     }
-    return launch_lanczos_finish(h, m, defer);
+    // row-sharded deferral: the last epilogue kernel has finished the last alpha; only the state moves to ctl[0]
+    return launch_lanczos_finish(h, m, defer == 2 && h->sharded() ? 3 : defer);
 }
 
 // Which gather variant serves the two Lanczos passes: measured once per handle, right before the first recurrence is
@@ -465,6 +473,7 @@ int kcrn_create(kcrn_handle *out, int64_t n_rows, int64_t n_cols, int64_t nnz, c
         KCRN_CUDA(cudaMallocHost(&h->rec_host, sizeof(double) * 16));
         h->vec_elems = n_cols > (int64_t)kNumSm * kVecThreads * 4 ? 4 : 1;
         h->vec_grid = (int)((n_cols + (int64_t)kVecThreads * h->vec_elems - 1) / ((int64_t)kVecThreads * h->vec_elems));
+        KCRN_CUDA(cudaMalloc(&h->post_part, sizeof(double) * ((size_t)std::max(1, h->vec_grid) + 4)));
 #ifdef KCRN_SWEEP_TRACE
         KCRN_CUDA(cudaMalloc(&h->sweep_trace, sizeof(unsigned long long) * 64 * 1024 * 12));
         KCRN_CUDA(cudaMemset(h->sweep_trace, 0, sizeof(unsigned long long) * 64 * 1024 * 12));
@@ -541,7 +550,7 @@ int kcrn_destroy(kcrn_handle h) {
                       h->alphas, h->bet, h->coef, h->coef2, h->sub, h->scal, h->red_partials, h->x_stage,
                       h->v_stage, h->o_stage, h->fwd_part, h->fwd_longdot, h->panel_x, h->panel_y, h->splitk_part};
     for (double *p : bufs) cudaFree(p);
-    cudaFree(h->ctl); cudaFree(h->lan_rows_part); cudaFree(h->lan_cols_part);
+    cudaFree(h->ctl); cudaFree(h->lan_rows_part); cudaFree(h->lan_cols_part); cudaFree(h->post_part);
     cudaFree(h->info);
     cudaFree(h->red_ticket);
     cudaFreeHost(h->rec_host);

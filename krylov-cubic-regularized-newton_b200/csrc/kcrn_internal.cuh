@@ -243,6 +243,7 @@ struct kcrn_problem {
     double *alphas = nullptr, *bet = nullptr, *coef = nullptr, *coef2 = nullptr;  // [kMaxM + 1]
     kcrn::LanczosCtl *ctl = nullptr;               // [2]: deferred mode ping-pongs between them, everything else uses [0]
     double *lan_rows_part = nullptr, *lan_cols_part = nullptr;   // per-CTA pieces of alpha (2 x csr.grid) / beta^2 (csc.grid)
+    double *post_part = nullptr;                                 // row-sharded fused loop: per-CTA pieces of beta^2 left by the epilogue kernel
     int32_t *info = nullptr;    // [8]
     int cur_m = 0, cur_reorth = 0;
     // sub-problem result {s[kMaxM], r, model_decrease, iterations, status}
@@ -320,13 +321,13 @@ int lanczos_alloc(kcrn_problem *h, int m);
 int launch_lanczos_init(kcrn_problem *h, int m);      // ctl, alphas, bet reset; bet[0] = |g|
 int launch_lanczos_post(kcrn_problem *h, const double *hv_or_raw, int raw);  // epilogue after allreduce / generic feed
 int launch_lanczos_update(kcrn_problem *h, int reorth, int fused);
-int launch_lanczos_post_sharded(kcrn_problem *h, const double *y_allreduced, int reorth);
+int launch_lanczos_post_sharded(kcrn_problem *h, const double *y_allreduced, int reorth, int slot = -1);   // slot >= 0: deferred sums
 int values_batch(kcrn_problem *h, const double *X, int k, double *out);
 int launch_run_init(kcrn_problem *h);
 int launch_run_begin(kcrn_problem *h, unsigned long long trial_loop);
 int launch_run_decide(kcrn_problem *h, unsigned long long trial_loop);
 int launch_run_commit(kcrn_problem *h, unsigned long long outer_loop);
-int launch_lanczos_post_peer(kcrn_problem *h, const double *y_partial, int reorth);
+int launch_lanczos_post_peer(kcrn_problem *h, const double *y_partial, int reorth, int slot = -1);
 int launch_normalise_current(kcrn_problem *h);        // V[col] = src / bet[col] outside the fused sweep
 int launch_sum(kcrn_problem *h, const double *a, int64_t len, double scale, double *out);  // deterministic sum
 int launch_value_record(kcrn_problem *h, double *out, int with_record);   // value from the forward sweep's tile sums (+ record)

@@ -55,6 +55,12 @@ struct VecParams {
     PeerSet peer;
     double n_samples, l2;
     int32_t *info;
+    // row-sharded fused loop with deferred sums (defer_slot >= 0): the alpha pieces the row sweep left (2 x rows_count, +
+    // the shares of its long rows), where this kernel leaves its own pieces of |w'|^2
+    int defer_slot;
+    const double *rows_part, *rows_longdot;
+    int rows_count, rows_nlong;
+    double *post_part;
 };
 
 // Sum `v` over the whole grid.  Returns true in every thread of the CTA that arrived last; in that
@@ -200,15 +206,39 @@ __device__ __forceinline__ double ll_poll(const uint4 *slot, unsigned step) {
 
 template <int E, bool PEER>
 __global__ void __launch_bounds__(kVecThreads) lanczos_post_sharded_kernel(VecParams P) {
-    __shared__ double sh[kVecThreads / 32];
+    __shared__ double sh[2 * (kVecThreads / 32)];
     __shared__ double s_alpha[kMaxPeers];
     __shared__ int s_last;
     pdl_wait();
     pdl_trigger();
-    if (P.ctl->done) return;
-    const int col = P.ctl->col, store_idx = P.ctl->store_idx;
-    const bool final_ = P.ctl->final_ != 0;
+    const bool deferred = P.defer_slot >= 0;
+    const LanczosCtl st = *P.ctl;
+    if (st.done) return;
+    const int col = st.col, store_idx = st.store_idx;
+    const bool final_ = st.final_ != 0;
     const int64_t base = (int64_t)blockIdx.x * (kVecThreads * E) + threadIdx.x;
+    // this rank's share of sum_i t_i (Av)_i and |v|^2: left whole by the row sweep's tail, or (deferred) still in per-tile
+    // pieces, added here by every CTA in the order of the sweep kernels' consumer-side sums
+    double mine_alpha, vsq;
+    if (deferred) {
+        double x = 0.0, y = 0.0;
+        const int ce = (P.rows_count + 1) & ~1;
+        for (int i = threadIdx.x; i < P.rows_count; i += kVecThreads) {
+            x += __ldcg(P.rows_part + i);
+            y += __ldcg(P.rows_part + ce + i);
+        }
+        for (int i = threadIdx.x; i < P.rows_nlong; i += kVecThreads) x += __ldcg(P.rows_longdot + i);
+        x = warp_sum(x);
+        y = warp_sum(y);
+        if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = x; sh[kVecThreads / 32 + (threadIdx.x >> 5)] = y; }
+        __syncthreads();
+        mine_alpha = vsq = 0.0;
+        for (int w = 0; w < kVecThreads / 32; ++w) { mine_alpha += sh[w]; vsq += sh[kVecThreads / 32 + w]; }
+        __syncthreads();
+    } else {
+        mine_alpha = P.alpha_raw[0];
+        vsq = P.alpha_raw2[0];
+    }
     unsigned step = 0;
     const uint4 *mine = nullptr;
     double s1 = 0.0, ymine[E];
@@ -218,7 +248,7 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_post_sharded_kernel(VecPa
         mine = S.mine + (size_t)(step & 1u) * S.world * S.stride;
         const size_t my_slot = ((size_t)(step & 1u) * S.world + S.rank) * S.stride;
         if (blockIdx.x == 0 && threadIdx.x < S.world && threadIdx.x != S.rank)
-            ll_push(S.recv[threadIdx.x] + my_slot + P.d, P.alpha_raw[0], step);
+            ll_push(S.recv[threadIdx.x] + my_slot + P.d, mine_alpha, step);
         if (!final_) {
 #pragma unroll
             for (int e = 0; e < E; ++e) {
@@ -231,17 +261,17 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_post_sharded_kernel(VecPa
             }
         }
         if (threadIdx.x < S.world)
-            s_alpha[threadIdx.x] = threadIdx.x == S.rank ? P.alpha_raw[0] : ll_poll(mine + threadIdx.x * S.stride + P.d, step);
+            s_alpha[threadIdx.x] = threadIdx.x == S.rank ? mine_alpha : ll_poll(mine + threadIdx.x * S.stride + P.d, step);
         __syncthreads();
         for (int k = 0; k < S.world; ++k) s1 += s_alpha[k];
     } else {
-        s1 = P.alpha_raw[0];
+        s1 = mine_alpha;
     }
-    const double alpha = __dadd_rn(quotient(s1, P.n_samples, P.inv_n), __dmul_rn(P.l2, P.alpha_raw2[0]));
+    const double alpha = __dadd_rn(quotient(s1, P.n_samples, P.inv_n), __dmul_rn(P.l2, vsq));
     const double *v = P.V + (size_t)col * P.d;
     const bool subtract = col > 0;
     const double *vpre = subtract ? P.V + (size_t)(col - 1) * P.d : nullptr;
-    const double beta_prev = subtract ? P.ctl->cur_beta : 0.0;
+    const double beta_prev = subtract ? st.cur_beta : 0.0;
     double loc = 0.0;
     if (!final_) {
 #pragma unroll
@@ -264,6 +294,28 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_post_sharded_kernel(VecPa
                 loc = fma(hv, hv, loc);
             }
         }
+    }
+    if (deferred) {
+        // |w'|^2 stays in per-CTA pieces for the next row sweep (it advances the recurrence); nobody waits here.  The
+        // exchange counter moves once every CTA has read it: a bare atomic, off every critical path
+        loc = warp_sum(loc);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = loc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double cta = 0.0;
+            for (int w = 0; w < kVecThreads / 32; ++w) cta += sh[w];
+            P.post_part[blockIdx.x] = cta;
+            if constexpr (PEER) {
+                if (atomicInc(P.peer.ticket, gridDim.x - 1) == gridDim.x - 1) *P.peer.epoch = step;
+            }
+            if (blockIdx.x == 0) {
+                P.alphas[final_ ? store_idx : col] = alpha;
+                P.ctl->cur_alpha = alpha;
+                P.ctl->hvps = st.hvps + 1;
+                if (final_) P.ctl->done = 1;
+            }
+        }
+        return;
     }
     double tot = 0.0;
     if (!grid_sum(loc, P.red_partials, P.red_ticket, sh, &s_last, &tot)) return;
@@ -616,6 +668,7 @@ VecParams base_params(kcrn_problem *h) {
     VecParams P{};
     P.ctl = h->ctl; P.V = h->V; P.wp = h->wp; P.g = h->g; P.d = h->d; P.alphas = h->alphas; P.bet = h->bet;
     P.red_partials = h->red_partials; P.n_samples = (double)h->n_global; P.l2 = h->l2; P.info = h->info;
+    P.defer_slot = -1;
     return P;
 }
 
@@ -681,11 +734,21 @@ int launch_lanczos_post(kcrn_problem *h, const double *hv_or_raw, int raw) {
     return KCRN_OK;
 }
 
-int launch_lanczos_post_sharded(kcrn_problem *h, const double *y_allreduced, int reorth) {
+// slot >= 0: the fused loop with deferred sums (the control block ping-pongs, see launch_rows_lanczos)
+static void post_deferred(kcrn_problem *h, VecParams &P, int slot) {
+    P.defer_slot = slot;
+    if (slot < 0) return;
+    P.ctl = h->ctl + ((slot + 1) & 1);
+    P.rows_part = h->lan_rows_part; P.rows_count = h->csr.grid; P.rows_longdot = h->csr.longdot; P.rows_nlong = h->csr.nlong;
+    P.post_part = h->post_part;
+}
+
+int launch_lanczos_post_sharded(kcrn_problem *h, const double *y_allreduced, int reorth, int slot) {
     VecParams P = base_params(h);
     P.w_in = y_allreduced; P.alpha_raw = h->ypart + h->d; P.alpha_raw2 = h->scal + 17; P.inv_n = 1.0 / P.n_samples;
     P.stage = reorth ? 1 : 0;
     P.red_ticket = h->red_ticket + 2;
+    post_deferred(h, P, slot);
     if (h->vec_elems == 4) KCRN_CUDA(launch_kernel(lanczos_post_sharded_kernel<4, false>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
     else KCRN_CUDA(launch_kernel(lanczos_post_sharded_kernel<1, false>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
     h->counters[0] += 1;
@@ -694,12 +757,13 @@ int launch_lanczos_post_sharded(kcrn_problem *h, const double *y_allreduced, int
 
 // the same with the allreduce done inside the kernel over peer memory; y_partial = this rank's A't, alpha
 // partial behind it at [d]
-int launch_lanczos_post_peer(kcrn_problem *h, const double *y_partial, int reorth) {
+int launch_lanczos_post_peer(kcrn_problem *h, const double *y_partial, int reorth, int slot) {
     VecParams P = base_params(h);
     P.w_in = y_partial; P.alpha_raw = y_partial + h->d; P.alpha_raw2 = h->scal + 17; P.inv_n = 1.0 / P.n_samples;
     P.stage = reorth ? 1 : 0;
     P.red_ticket = h->red_ticket + 2;
     P.peer = peer_set(h);
+    post_deferred(h, P, slot);
     if (h->vec_elems == 4) KCRN_CUDA(launch_kernel(lanczos_post_sharded_kernel<4, true>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
     else KCRN_CUDA(launch_kernel(lanczos_post_sharded_kernel<1, true>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
     h->counters[0] += 1;
@@ -728,7 +792,8 @@ int launch_lanczos_update(kcrn_problem *h, int reorth, int fused) {
 int launch_lanczos_finish(kcrn_problem *h, int m, int defer) {
     static_assert(kVecThreads == kSweepThreads, "the finish kernel repeats the sweep kernels' summation order");
     FinishParams P{};
-    P.ctl_in = defer == 2 ? h->ctl + (m & 1) : h->ctl;
+    P.ctl_in = defer >= 2 ? h->ctl + (m & 1) : h->ctl;     // 2, 3: the state ended in the other half of the ping-pong pair
+    if (defer == 3) defer = 0;                             // 3 (row-sharded deferral): the last alpha is already finished
     P.ctl_main = h->ctl; P.info = h->info; P.bet = h->bet; P.alphas = h->alphas;
     P.defer = defer; P.part = h->lan_rows_part; P.longdot = h->csr.longdot; P.count = h->csr.grid; P.nlong = h->csr.nlong;
     P.n_samples = (double)h->n_global; P.inv_n = 1.0 / P.n_samples; P.l2 = h->l2;

@@ -949,6 +949,11 @@ int tune_plain_sweeps(kcrn_problem *h) {
 // The consumer-side sums stage the producer's pieces in the tile's product buffer: both sets must fit
 bool lanczos_defer_fits(const kcrn_problem *h) {
     auto even = [](int v) { return (v + 1) & ~1; };
+    if (h->sharded()) {                    // only the row sweep stages pieces (those of the epilogue kernel); the alpha pieces
+                                           // are added by the epilogue kernel straight from global memory
+        const bool async_r = h->csr.gidx && h->csr.gather_lanczos >= kGatherAsync;
+        return even(h->vec_grid) <= (async_r ? kSumCapAsync : h->csr.items * kSweepThreads);
+    }
     // staged in the CONSUMER's product buffer: row pieces in the column sweep's, column pieces in the row sweep's
     const bool async_cols = h->csc.gidx && h->csc.gather_lanczos >= kGatherAsync;     // async / staged: pieces go to the sums buffer
     const bool async_rows = h->csr.gidx && h->csr.gather_lanczos >= kGatherAsync;
@@ -969,7 +974,11 @@ int launch_rows_lanczos(kcrn_problem *h, double *alpha_raw, int slot, int defer,
     if (defer == 2) {                      // advance here: beta pieces of the previous column sweep
         P.ctl_in = h->ctl + (slot & 1); P.ctl = h->ctl + ((slot + 1) & 1);
         P.advance_here = slot > 0;
-        P.prev_part = h->lan_cols_part; P.prev_count = h->csc.grid; P.prev_longdot = h->csc.longdot; P.prev_nlong = h->csc.nlong;
+        if (h->sharded()) {                // row-sharded: the epilogue kernel after the exchange left the pieces of |w'|^2
+            P.prev_part = h->post_part; P.prev_count = h->vec_grid; P.prev_longdot = h->post_part; P.prev_nlong = 0;
+        } else {
+            P.prev_part = h->lan_cols_part; P.prev_count = h->csc.grid; P.prev_longdot = h->csc.longdot; P.prev_nlong = h->csc.nlong;
+        }
         if (slot == 0 && init_m > 0) { P.init_here = 1; P.m_init = init_m; }
     } else {
         P.ctl_in = P.ctl = h->ctl;
