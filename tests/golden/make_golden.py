@@ -379,9 +379,30 @@ def config4():
     save("traj_config4", **out)
 
 
+def config4_l2():
+    """SSCN with an l2 term (the value and the block gradient then depend on x itself, not only on A x: the cached-A x
+    override of update_mat_vec_product must not freeze x -- advisor finding of round 1)."""
+    P = make_problem("small", seed=0)
+    out = {"fp": np.array(P.fingerprint()), "l2": np.array(1e-3)}
+    for m in (10,):
+        loss = LogisticRegression(P.scipy_csr().tocsc(), P.b, l1=0, l2=1e-3, store_mat_vec_prod=True)
+        opt = ref_cubic.SSCN(loss=loss, reg_coef=1e-3, subspace_dim=m, tolerance=1e-9, label="s")
+        opt.rng = np.random.default_rng(42)
+        opt.init_run(P.x0)
+        f, M, sit = [], [], []
+        for _ in range(40):
+            opt.step()
+            f.append(opt.value); M.append(opt.reg_coef); sit.append(opt.solver_it)
+        out.update({f"sscn{m}_f": np.array(f), f"sscn{m}_M": np.array(M), f"sscn{m}_solver_it": np.array(sit, dtype=np.int64),
+                    f"sscn{m}_x_final": opt.x.copy()})
+        print("sscn l2", m, "f[-1] = %.6e" % f[-1])
+    save("traj_config4_l2", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["prims", "oracle_methods", "lanczos", "cubic", "traj", "config4", "news20", "fstar"]
+    which = sys.argv[1:] or ["prims", "oracle_methods", "lanczos", "cubic", "traj", "config4", "config4_l2", "news20", "fstar"]
     if "config4" in which: config4()
+    if "config4_l2" in which: config4_l2()
     if "prims" in which: prims()
     if "oracle_methods" in which: oracle_methods()
     if "lanczos" in which: lanczos_cases()

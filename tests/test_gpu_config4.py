@@ -106,6 +106,29 @@ def test_sscn_trajectory_vs_reference(torch, golden, m):
     assert rel_err(opt.x.cpu().numpy(), g[f"sscn{m}_x_final"]) <= 1e-8
 
 
+def test_sscn_trajectory_with_l2_vs_reference(torch, golden):
+    """l2 > 0: value and block gradient depend on x itself; the cached-A x override (update_mat_vec_product, loss.py:279-286)
+    must not freeze the x the engine uses for those terms (kcrn_set_x_only)."""
+    from optimizer.cubic import SSCN
+    from optimizer.loss import LogisticRegression
+    g = golden("traj_config4_l2")
+    P = make_problem("small", seed=0)
+    assert P.fingerprint() == str(g["fp"])
+    loss = LogisticRegression(P.scipy_csr(), P.b, l1=0, l2=float(g["l2"]), store_mat_vec_prod=True)
+    opt = SSCN(loss=loss, reg_coef=1e-3, subspace_dim=10, tolerance=1e-9, label="s", tqdm=False)
+    opt.rng = np.random.default_rng(42)
+    opt.init_run(P.x0)
+    ref, f = g["sscn10_f"], []
+    for _ in range(len(ref)):
+        opt.step()
+        f.append(opt.value)
+    dev = np.abs(np.array(f) - ref) / np.abs(ref)
+    print(f"\nSSCN m=10, l2=1e-3: max dev {dev.max():.2e}")
+    assert dev.max() <= 1e-8
+    assert opt.reg_coef == g["sscn10_M"][-1]
+    assert rel_err(opt.x.cpu().numpy(), g["sscn10_x_final"]) <= 1e-8
+
+
 def test_full_hessian_crn_trajectory_vs_reference(torch, golden):
     from optimizer.cubic import Cubic_LS
     g = golden("traj_config4")

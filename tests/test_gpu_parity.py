@@ -536,6 +536,26 @@ def test_batched_values_of_iterates_vs_oracle(torch, name, l2, k):
     assert eng.values_batch(Xd[:0]).numel() == 0
 
 
+def test_values_of_temporaries_are_never_served_from_a_stale_cache(torch):
+    """store_mat_vec_prod=True memoises A x on the identity of the iterate tensor.  A freed temporary's block comes back
+    from the caching allocator at the same address with version 0: the memo must not mistake the next temporary for it
+    (advisor finding of round 1: the remembered tensor is kept alive while it is the key)."""
+    P = make_problem("small", seed=0)
+    opt = _make_opt(P, 10)
+    loss, L = opt.loss, _oracle(P)
+    rng = np.random.default_rng(3)
+    x, d = _dev(torch, P.x0), _dev(torch, rng.standard_normal(P.d))
+    for a in (0.1, 0.2, 0.3, 0.1):
+        got = loss.value(x + a * d)                         # a temporary every time
+        want = L.value(P.x0 + a * d.cpu().numpy())
+        assert abs(got - want) <= TOL * abs(want), a
+    y = x + 0.5 * d
+    v1 = loss.value(y)
+    y.add_(d, alpha=0.25)                                    # in place: the version counter moves
+    v2 = loss.value(y)
+    assert abs(v2 - L.value(y.cpu().numpy())) <= TOL * abs(v2) and v1 != v2
+
+
 def test_drop_in_driver_flow_with_numpy_iterates(torch):
     """What cubic_newton.py does (:58-68, :94-111, :140): numpy x0, run, compute_loss_of_iterates, f_opt."""
     P = make_problem("small", seed=0)
