@@ -34,6 +34,7 @@ Switches read_switches() {
     w.persist = num("KCRN_PERSIST") != 0;
     w.persist_trace = on("KCRN_PERSIST_TRACE");
     w.persist_flags = num("KCRN_PERSIST_FLAGS");
+    if (getenv("KCRN_DSHARD")) w.dshard = num("KCRN_DSHARD") != 0 ? 1 : 0;
     return w;
 }
 
@@ -133,6 +134,7 @@ int enqueue_lanczos(kcrn_problem *h, int m, int reorth, bool allow_persist = tru
     // epilogue kernel after the exchange adds the alpha pieces of the row sweep, the next row sweep the beta pieces of the
     // epilogue kernel (round 1 finished both with last-CTA tails: two fences + an atomic + a serial sum per HVP).  With
     // NCCL in front of the epilogue the alpha piece must be inside the allreduced buffer: 0.
+    h->cur_m_enqueue = m;
     const bool shard_defer = h->sharded() && !reorth && (h->p2p_ready || h->world == 1);
     const int defer = ((h->sharded() && !shard_defer) || h->sw.no_defer || !lanczos_defer_fits(h)) ? 0 : (reorth ? 1 : 2);
     const bool self_init = g_pieces && defer == 2 && !h->sharded();   // the first row sweep starts the recurrence itself
@@ -468,6 +470,8 @@ int kcrn_create(kcrn_handle *out, int64_t n_rows, int64_t n_cols, int64_t nnz, c
         KCRN_CUDA(cudaMemsetAsync(h->red_ticket, 0, sizeof(unsigned) * 8, s));
         KCRN_CUDA(cudaMemsetAsync(h->scal, 0, sizeof(double) * 32, s));
         KCRN_CUDA(cudaMemsetAsync(h->sub, 0, sizeof(double) * (kMaxM + 8), s));
+        KCRN_CUDA(cudaMemsetAsync(h->coef, 0, sizeof(double) * (kMaxM + 2), s));
+        KCRN_CUDA(cudaMemsetAsync(h->coef2, 0, sizeof(double) * (kMaxM + 2), s));
         KCRN_CUDA(cudaMemsetAsync(h->ctl, 0, 2 * sizeof(LanczosCtl), s));
         KCRN_CUDA(cudaMemsetAsync(h->info, 0, sizeof(int32_t) * 8, s));
         KCRN_CUDA(cudaMallocHost(&h->rec_host, sizeof(double) * 16));

@@ -60,6 +60,7 @@ struct Switches {
     int short_seg = 0, tile_items = 0;            // KCRN_SHORT_SEG, KCRN_TILE_ITEMS: tiling knobs (0: default)
     bool persist = false, persist_trace = false;  // KCRN_PERSIST, KCRN_PERSIST_TRACE: one-kernel recurrence (opt-in)
     int persist_flags = 0;                        // KCRN_PERSIST_FLAGS: its measured experiments
+    int dshard = -1;                              // KCRN_DSHARD=1 / 0: d-sharded re-orthogonalisation on / off (-1: by size)
 };
 Switches read_switches();
 
@@ -275,6 +276,17 @@ struct kcrn_problem {
     // the one-GPU test suite
     bool emulate_sharded = false;
     bool sharded() const { return world > 1 || emulate_sharded; }
+    // d-sharded re-orthogonalisation: for row-sharded handles whose basis is large enough that 1/world of its traffic
+    // outweighs four NCCL collectives per step (KCRN_DSHARD=1 / 0 forces it on / off).  Measured at 8 GPUs
+    // (profiles/r2s_dshard_*.json): a small NCCL allreduce costs ~44 us there, so at d = 1 M, m = 100 the two ways tie
+    // (39.1 vs 36.3 ms of re-orthogonalisation per recurrence) and at the news20 shape the sharded one loses; the
+    // default threshold sits above both
+    int cur_m_enqueue = 0;         // m of the recurrence being enqueued
+    bool dshard_reorth() const {
+        if (!sharded()) return false;
+        if (sw.dshard >= 0) return sw.dshard != 0;
+        return world > 1 && (double)d * (double)cur_m_enqueue > 2.0e8;
+    }
     // persistent recurrence (kcrn_persist.cu); persist_ok: both matrices fit one tile per SM
     kcrn::PersistMat prow, pcol;
     bool persist_ok = false;

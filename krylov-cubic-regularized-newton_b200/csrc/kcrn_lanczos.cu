@@ -57,6 +57,12 @@ struct VecParams {
     int32_t *info;
     // row-sharded fused loop with deferred sums (defer_slot >= 0): the alpha pieces the row sweep left (2 x rows_count, +
     // the shares of its long rows), where this kernel leaves its own pieces of |w'|^2
+    // d-sharded re-orthogonalisation (row-sharded runs): this rank works on the slice [lo, hi) of the
+    // d-vectors only (0, d: everything); sliced != 0: dots and norms are sums over the ranks (finished outside), stage 3
+    // leaves zeros outside the slice so that a sum over the ranks re-assembles w'
+    int64_t lo, hi;
+    int sliced;
+    double *slice_scal;        // [2] this rank's share of |w'|^2 (+ pad), summed over the ranks before advance_kernel
     int defer_slot;
     const double *rows_part, *rows_longdot;
     int rows_count, rows_nlong;
@@ -347,7 +353,7 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int64_t c = base + (int64_t)e * kVecThreads;
-            x[e] = c < P.d ? P.wp[c] : 0.0;
+            x[e] = (c >= P.lo && c < P.hi) ? P.wp[c] : 0.0;
         }
     } else if (P.stage <= 1) {
         const double alpha = P.ctl->cur_alpha;
@@ -355,7 +361,7 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int64_t c = base + (int64_t)e * kVecThreads;
-            x[e] = c < P.d ? __dsub_rn(P.w_in[c], __dmul_rn(alpha, v[c])) : 0.0;
+            x[e] = (c >= P.lo && c < P.hi) ? __dsub_rn(P.w_in[c], __dmul_rn(alpha, v[c])) : 0.0;
         }
     } else {
         // w' -= V[:, :nv] c: the coefficients come from shared memory and the basis entries are fetched eight columns
@@ -364,7 +370,7 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int64_t c = base + (int64_t)e * kVecThreads;
-            x[e] = c < P.d ? P.wp[c] : 0.0;
+            x[e] = (c >= P.lo && c < P.hi) ? P.wp[c] : 0.0;
             s[e] = 0.0;
         }
         for (int i = threadIdx.x; i < nv; i += blockDim.x) scoef[i] = P.coef_in[i];
@@ -376,7 +382,7 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     const int64_t c = base + (int64_t)e * kVecThreads;
-                    vv[u][e] = (i0 + u < nv && c < P.d) ? P.V[(size_t)(i0 + u) * P.d + c] : 0.0;
+                    vv[u][e] = (i0 + u < nv && (c >= P.lo && c < P.hi)) ? P.V[(size_t)(i0 + u) * P.d + c] : 0.0;
                 }
 #pragma unroll
             for (int u = 0; u < 8; ++u)
@@ -392,7 +398,8 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const int64_t c = base + (int64_t)e * kVecThreads;
-        if (c < P.d) P.wp[c] = x[e];
+        if ((c >= P.lo && c < P.hi)) P.wp[c] = x[e];
+        else if (P.sliced && P.stage == 3 && c < P.d) P.wp[c] = 0.0;      // the owner's value arrives with the sum over the ranks
     }
 
     if (P.stage == 0 || P.stage == 3) {
@@ -401,7 +408,10 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P
         for (int e = 0; e < E; ++e) loc = fma(x[e], x[e], loc);
         double tot = 0.0;
         if (!grid_sum(loc, P.red_partials, P.red_ticket, sh, &s_last, &tot)) return;
-        if (threadIdx.x == 0) lanczos_advance(P.ctl, P.bet, sqrt(tot));
+        if (threadIdx.x == 0) {
+            if (P.sliced) { P.slice_scal[0] = tot; P.slice_scal[1] = 0.0; }    // the other ranks' shares are still missing
+            else lanczos_advance(P.ctl, P.bet, sqrt(tot));
+        }
         return;
     }
 
@@ -413,7 +423,7 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const int64_t c = base + (int64_t)e * kVecThreads;
-                vv[u][e] = (i0 + u < nv && c < P.d) ? P.V[(size_t)(i0 + u) * P.d + c] : 0.0;
+                vv[u][e] = (i0 + u < nv && (c >= P.lo && c < P.hi)) ? P.V[(size_t)(i0 + u) * P.d + c] : 0.0;
             }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -446,6 +456,12 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P
         for (int b = 0; b < (int)gridDim.x; ++b) tot += __ldcg(P.red_partials + (size_t)b * nv + i);
         P.coef_out[i] = tot;
     }
+}
+
+// d-sharded re-orthogonalisation: |w'|^2 has been summed over the ranks -- the bookkeeping of cubic.py:98-109
+__global__ void advance_kernel(LanczosCtl *ctl, double *bet, const double *bsq) {
+    pdl_wait();
+    if (threadIdx.x == 0 && !ctl->done) lanczos_advance(ctl, bet, sqrt(bsq[0]));
 }
 
 struct FinishParams {
@@ -669,6 +685,7 @@ VecParams base_params(kcrn_problem *h) {
     P.ctl = h->ctl; P.V = h->V; P.wp = h->wp; P.g = h->g; P.d = h->d; P.alphas = h->alphas; P.bet = h->bet;
     P.red_partials = h->red_partials; P.n_samples = (double)h->n_global; P.l2 = h->l2; P.info = h->info;
     P.defer_slot = -1;
+    P.lo = 0; P.hi = h->d; P.sliced = 0; P.slice_scal = h->scal + 18;
     return P;
 }
 
@@ -775,15 +792,36 @@ int launch_lanczos_post_peer(kcrn_problem *h, const double *y_partial, int reort
 // fused = 1: w' already holds w - alpha v (formed by the column sweep / the sharded post kernel)
 int launch_lanczos_update(kcrn_problem *h, int reorth, int fused) {
     const int first = reorth ? 1 : 0, last = reorth ? 3 : 0;
+    // d-sharded re-orthogonalisation (row-sharded runs with a large basis): every rank orthogonalises its slice of d
+    // against the same slice of V -- 1/world of the basis traffic -- and three small sums over the ranks (the
+    // coefficients twice, |w'|^2) plus one sum of disjoint slices (w') replace the replicated work
+    const bool sliced = reorth && fused && h->dshard_reorth();
+    int64_t lo = 0, hi = h->d;
+    if (sliced) {
+        const int64_t per = (h->d + h->world - 1) / h->world;
+        lo = std::min<int64_t>(h->d, per * h->rank);
+        hi = std::min<int64_t>(h->d, lo + per);
+    }
     for (int stage = first; stage <= last; ++stage) {
         VecParams P = base_params(h);
         P.w_in = h->w; P.stage = stage; P.from_wp = fused;
         P.coef_in = stage == 2 ? h->coef : h->coef2;
         P.coef_out = stage == 1 ? h->coef : h->coef2;
         P.red_ticket = h->red_ticket + 1;
+        P.lo = lo; P.hi = hi; P.sliced = sliced ? 1 : 0;
         if (h->vec_elems == 4) KCRN_CUDA(launch_kernel(lanczos_update_kernel<4>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
         else KCRN_CUDA(launch_kernel(lanczos_update_kernel<1>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
         h->counters[0] += 1;
+        if (sliced) {
+            if (stage < 3) {
+                KCRN_TRY(nccl_allreduce_sum(h, P.coef_out, (h->cur_m_enqueue + 1) & ~1));
+            } else {
+                KCRN_TRY(nccl_allreduce_sum(h, h->scal + 18, 2));
+                KCRN_TRY(nccl_allreduce_sum(h, h->wp, h->d));
+                KCRN_CUDA(launch_kernel(advance_kernel, dim3(1), dim3(32), 0, h->stream, h->pdl, h->ctl, h->bet, (const double *)(h->scal + 18)));
+                h->counters[0] += 1;
+            }
+        }
     }
     return KCRN_OK;
 }

@@ -102,6 +102,28 @@ def main():
         errs["device_loop_equals_host_loop"] = 0.0 if same else 1.0
     except Exception as e:
         print(f"rank {rank}: device loop unavailable ({e})", flush=True)
+    # d-sharded re-orthogonalisation (KCRN_DSHARD=1: every rank orthogonalises its slice of d; coefficients, |w'|^2 and
+    # w' are sums over the ranks) against the replicated one, on a second handle over the same shard
+    os.environ["KCRN_DSHARD"] = "1"
+    loss2 = LogisticRegression(S.scipy_csr(), P_labels(S), l1=0, l2=0, store_mat_vec_prod=True, n_global=P.n)
+    join_communicator(loss2.engine, rank, world)
+    os.environ.pop("KCRN_DSHARD")
+    res = []
+    for eng_k in (eng, loss2.engine):
+        eng_k.set_x(xd)
+        gk = eng_k.gradient()
+        eng_k.lanczos(12, reorth=True, g=gk)
+        Vk, ak, bk, _ = eng_k.lanczos_view()
+        res.append((ak.cpu().numpy().copy(), bk.cpu().numpy().copy(), Vk.cpu().numpy().copy()))
+    G = res[1][2] @ res[1][2].T
+    errs["dshard_reorth_vs_replicated"] = max(rel(res[1][0], res[0][0]), rel(res[1][1][:12], res[0][1][:12]), rel(res[1][2], res[0][2]))
+    errs["dshard_orthogonality"] = float(np.max(np.abs(G - np.eye(12))))
+    mine = torch.as_tensor(res[1][2], device="cuda")
+    ref0 = mine.clone()
+    dist.broadcast(ref0, 0)
+    if not torch.equal(ref0, mine) or errs["dshard_reorth_vs_replicated"] > 1e-9 or errs["dshard_orthogonality"] > 1e-12:
+        errs["peer_fail"] = 1.0
+    loss2.engine.close()
     Xs = torch.stack([loss.to_device(x) for x in opt.trace.xs[:5]])
     vb = eng.values_batch(Xs).cpu().numpy()
     vo = np.array([L.value(x.cpu().numpy()) for x in opt.trace.xs[:5]])

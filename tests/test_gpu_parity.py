@@ -179,13 +179,13 @@ def test_gather_variants_give_the_same_bits(torch, monkeypatch, name):
             assert torch.equal(a, b)
 
 
-def _lanczos_probe(tmp_path, tag, extra_env, name="small"):
+def _lanczos_probe(tmp_path, tag, extra_env, name="small", reorth=0):
     import os, subprocess, sys
     here = os.path.dirname(os.path.abspath(__file__))
     e = {k: v for k, v in os.environ.items() if not k.startswith("KCRN_")}
     e.update(extra_env)
     out = str(tmp_path / f"probe_{tag}.npz")
-    subprocess.run([sys.executable, os.path.join(here, "lanczos_probe.py"), name, "6", "0", out], env=e, check=True,
+    subprocess.run([sys.executable, os.path.join(here, "lanczos_probe.py"), name, "6", str(int(reorth)), out], env=e, check=True,
                    timeout=600)
     with np.load(out) as z:
         return {k: z[k] for k in z.files}
@@ -240,6 +240,21 @@ def test_persistent_recurrence_kernel_matches_the_graph_path(torch, tmp_path, na
     assert rel_err(got["alphas"][:m], ref["alphas"][:m]) <= 1e-9
     assert rel_err(got["bet"][:m], ref["bet"][:m]) <= 1e-7
     assert rel_err(got["V"][:m], ref["V"][:m]) <= 1e-6
+
+
+def test_dsharded_reorthogonalisation_code_path_on_one_gpu(torch, tmp_path):
+    # KCRN_EMULATE_SHARDED + KCRN_DSHARD=1: the re-orthogonalisation kernels run in their sliced form (one rank: the slice is
+    # everything, the sums over the ranks are the identity) with the separate advance kernel; the real exchange is
+    # covered by tests/mgpu_worker.py and the parity key of bench.py on 2 and 8 GPUs
+    ref = _lanczos_probe(tmp_path, "ro", {}, reorth=1)
+    got = _lanczos_probe(tmp_path, "ro_dshard", {"KCRN_EMULATE_SHARDED": "1", "KCRN_DSHARD": "1"}, reorth=1)
+    assert ref["info"][0] == got["info"][0] and ref["info"][3] == got["info"][3]
+    m = int(ref["info"][0])
+    assert rel_err(got["alphas"][:m], ref["alphas"][:m]) <= 1e-9
+    assert rel_err(got["bet"][:m], ref["bet"][:m]) <= 1e-7
+    assert rel_err(got["V"][:m], ref["V"][:m]) <= 1e-6
+    G = got["V"][:m] @ got["V"][:m].T
+    assert np.max(np.abs(G - np.eye(m))) <= 1e-12
 
 
 def test_long_segments_and_empty_rows(torch):
