@@ -26,8 +26,8 @@ Switches read_switches() {
     if (const char *e = getenv("KCRN_GATHER")) {         // "p[,l]": plain / Lanczos passes
         int a = -1, b = -1;
         const int k = sscanf(e, "%d,%d", &a, &b);
-        if (k >= 1 && a >= 0 && a < 3) w.gather_plain = w.gather_lanczos = a;
-        if (k >= 2 && b >= 0 && b < 3) w.gather_lanczos = b;
+        if (k >= 1 && a >= 0 && a < 4) w.gather_plain = w.gather_lanczos = a;
+        if (k >= 2 && b >= 0 && b < 4) w.gather_lanczos = b;
     }
     w.short_seg = num("KCRN_SHORT_SEG");
     w.tile_items = num("KCRN_TILE_ITEMS");
@@ -35,6 +35,7 @@ Switches read_switches() {
     w.persist_trace = on("KCRN_PERSIST_TRACE");
     w.persist_flags = num("KCRN_PERSIST_FLAGS");
     if (getenv("KCRN_DSHARD")) w.dshard = num("KCRN_DSHARD") != 0 ? 1 : 0;
+    if (getenv("KCRN_SPLIT")) w.split_passes = num("KCRN_SPLIT") != 0;
     return w;
 }
 

@@ -88,6 +88,152 @@ __device__ __forceinline__ double sumsq(const double *__restrict__ x, int m) {
     return acc;
 }
 
+// r/2 |s|^2 - M/3 |s|^3 - <g, s>/2 with g = gnorm e1 (cubic.py:74): every operation rounded on its own, as numpy does
+__device__ __forceinline__ double model_decrease(double r, double M, double ns, double gnorm, double s0) {
+    const double n2 = __dmul_rn(ns, ns), n3 = __dmul_rn(n2, ns);
+    const double t0 = __dmul_rn(r / 2.0, n2), t1 = __dmul_rn(M / 3.0, n3), t2 = __dmul_rn(gnorm, s0) / 2.0;
+    return __dsub_rn(__dsub_rn(t0, t1), t2);
+}
+
+// ---- m <= kSmallM: the same arithmetic with the factor and the two solution vectors in REGISTERS.  The general kernel
+// below keeps them in shared memory behind run-time loop bounds, so every step of its dependent chains goes through
+// a store and a load of the same address; here the loops are unrolled over kSmallM with `j < m` guards, the factor
+// never leaves the register file and the chain is arithmetic only (sqrt -> reciprocal -> quotient per row).  Same
+// operations in the same order: bit-identical results (test_cubic_small_path_equals_general_path).
+constexpr int kSmallM = 16;
+
+struct SmallTri {
+    double l[kSmallM], li[kSmallM], e[kSmallM];
+};
+
+__device__ __forceinline__ bool factor_forward_small(const double *__restrict__ a, const double *__restrict__ b, SmallTri &F,
+                                                     double (&y)[kSmallM], int m, double lam, double gnorm) {
+    double prev_e = 0.0, prev_y = 0.0;
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < kSmallM; ++j) {
+        if (j < m) {
+            double piv = a[j] + lam;
+            piv = __dsub_rn(piv, __dmul_rn(prev_e, prev_e));
+            if (!(piv > 0.0)) ok = false;
+            const double lj = sqrt(piv);
+            const double rj = 1.0 / lj;
+            F.l[j] = lj;
+            F.li[j] = rj;
+            double v = j == 0 ? gnorm : 0.0;
+            if (j > 0) v = __dsub_rn(v, __dmul_rn(prev_e, prev_y));
+            prev_y = quotient(v, lj, rj);
+            y[j] = prev_y;
+            if (j + 1 < m) {
+                prev_e = quotient(b[j], lj, rj);
+                F.e[j] = prev_e;
+            }
+        }
+    }
+    return ok;
+}
+
+__device__ __forceinline__ void forward_small(const SmallTri &F, const double (&rhs)[kSmallM], double (&out)[kSmallM], int m) {
+    double prev = 0.0;
+#pragma unroll
+    for (int j = 0; j < kSmallM; ++j) {
+        if (j < m) {
+            double v = rhs[j];
+            if (j > 0) v = __dsub_rn(v, __dmul_rn(F.e[j - 1], prev));
+            prev = quotient(v, F.l[j], F.li[j]);
+            out[j] = prev;
+        }
+    }
+}
+
+__device__ __forceinline__ void backward_small(const SmallTri &F, double (&x)[kSmallM], int m, bool negate) {
+    double prev = 0.0;
+#pragma unroll
+    for (int j = kSmallM - 1; j >= 0; --j) {
+        if (j < m) {
+            double v = x[j];
+            if (j + 1 < m) v = __dsub_rn(v, __dmul_rn(F.e[j], prev));
+            prev = quotient(v, F.l[j], F.li[j]);
+            x[j] = negate ? -prev : prev;
+        }
+    }
+}
+
+__device__ __forceinline__ double dot_small(const double (&x)[kSmallM], const double (&y)[kSmallM], int m) {
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < kSmallM; ++j)
+        if (j < m) acc = __dadd_rn(acc, __dmul_rn(x[j], y[j]));
+    return acc;
+}
+
+__global__ void __launch_bounds__(32) cubic_small_kernel(const double *__restrict__ alphas,
+                                                         const double *__restrict__ betas, int m_arg,
+                                                         const int32_t *__restrict__ info,
+                                                         const double *__restrict__ gnorm_dev, double gnorm_arg,
+                                                         double M, double r0, double eps, int it_max,
+                                                         double *__restrict__ s_out, double *__restrict__ scal_out,
+                                                         const double *__restrict__ params) {
+    __shared__ double sa[kSmallM], sb[kSmallM], sres[kSmallM];
+    // all inputs are requested at once (one round trip), by different lanes
+    double pv = 0.0;
+    if (params && threadIdx.x < 4) pv = params[threadIdx.x];
+    // (the loads are guarded by m_arg, which is a kernel argument, not by the device-side m: one round trip, not two)
+    double la = 0.0, lb = 0.0;
+    if ((int)threadIdx.x < m_arg) la = alphas[threadIdx.x];
+    if ((int)threadIdx.x + 1 < m_arg) lb = betas[threadIdx.x];
+    const int m = info ? info[0] : m_arg;
+    const double gnorm = gnorm_dev ? gnorm_dev[0] : gnorm_arg;
+    if (threadIdx.x < kSmallM) {
+        const int j = threadIdx.x;
+        sa[j] = j < m ? la : 0.0;
+        sb[j] = j + 1 < m ? lb : 0.0;
+    }
+    if (params) {                                  // whole-step graph
+        M = __shfl_sync(0xffffffffu, pv, 0); r0 = __shfl_sync(0xffffffffu, pv, 1);
+        eps = __shfl_sync(0xffffffffu, pv, 2); it_max = (int)__shfl_sync(0xffffffffu, pv, 3);
+    }
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        SmallTri F;
+        double ss[kSmallM], sq[kSmallM];
+        double r = r0, dec = 0.0;
+        int its = 0, status = 0;
+        double p0 = r0, p = r0;
+        bool finished = false;
+        for (int itr = 0; itr < it_max && !finished; ++itr) {
+            if (!factor_forward_small(sa, sb, F, ss, m, p0, gnorm)) { status = KCRN_E_NOTPD; r = p0; its = itr; finished = true; break; }
+            backward_small(F, ss, m, true);
+            const double ns = sqrt(dot_small(ss, ss, m));
+            const double fval = __dsub_rn(__dmul_rn(p0, p0), __dmul_rn(__dmul_rn(M, M), __dmul_rn(ns, ns)));
+            if (fval == 0.0) { r = p0; its = itr; finished = true; break; }
+            forward_small(F, ss, sq, m);
+            backward_small(F, sq, m, false);
+            const double sdot = dot_small(ss, sq, m);
+            const double fder = __dsub_rn(__dmul_rn(2.0, p0), __dmul_rn(__dmul_rn(M, M), __dmul_rn(-2.0, sdot)));
+            if (fder == 0.0) { r = p0; its = itr + 1; finished = true; break; }
+            p = __dsub_rn(p0, fval / fder);
+            if (fabs(p - p0) <= eps) { r = p; its = itr + 1; finished = true; break; }
+            p0 = p;
+        }
+        if (!finished) { r = p; its = it_max; }
+        if (status == 0 && !factor_forward_small(sa, sb, F, ss, m, r, gnorm)) status = KCRN_E_NOTPD;
+        if (status == 0) {
+            backward_small(F, ss, m, true);
+            const double ns = sqrt(dot_small(ss, ss, m));
+            dec = model_decrease(r, M, ns, gnorm, ss[0]);
+        }
+#pragma unroll
+        for (int j = 0; j < kSmallM; ++j) sres[j] = (status == 0 && j < m) ? ss[j] : 0.0;
+        scal_out[0] = r;
+        scal_out[1] = dec;
+        scal_out[2] = (double)its;
+        scal_out[3] = (double)status;
+    }
+    __syncwarp();
+    for (int j = threadIdx.x; j < m_arg; j += 32) s_out[j] = sres[j];
+}
+
 __global__ void __launch_bounds__(32) cubic_kernel(const double *__restrict__ alphas,
                                                    const double *__restrict__ betas, int m_arg,
                                                    const int32_t *__restrict__ info,
@@ -135,7 +281,7 @@ __global__ void __launch_bounds__(32) cubic_kernel(const double *__restrict__ al
             backward(sl, sli, se, ss, m, true);
             const double ns = sqrt(sumsq(ss, m));
             // r/2 |s|^2 - M/3 |s|^3 - <g, s>/2
-            dec = (r / 2.0) * (ns * ns) - (M / 3.0) * (ns * ns * ns) - (gnorm * ss[0]) / 2.0;
+            dec = model_decrease(r, M, ns, gnorm, ss[0]);
         } else {
             for (int j = 0; j < m; ++j) ss[j] = 0.0;
         }
@@ -292,8 +438,12 @@ int launch_cubic(const double *alphas, const double *betas, int m, const int32_t
         set_error("cubic sub-problem: m = %d outside [1, %d]", m, kMaxM);
         return KCRN_E_ARG;
     }
-    cubic_kernel<<<1, 32, 0, st>>>(alphas, betas, m, info, gnorm_dev, gnorm, M, r0, eps, it_max, s_out, scal_out,
-                                   params_dev);
+    if (m <= kSmallM)
+        cubic_small_kernel<<<1, 32, 0, st>>>(alphas, betas, m, info, gnorm_dev, gnorm, M, r0, eps, it_max, s_out, scal_out,
+                                             params_dev);
+    else
+        cubic_kernel<<<1, 32, 0, st>>>(alphas, betas, m, info, gnorm_dev, gnorm, M, r0, eps, it_max, s_out, scal_out,
+                                       params_dev);
     KCRN_LAUNCH_CHECK();
     return KCRN_OK;
 }

@@ -55,7 +55,7 @@
         if (P.trace && threadIdx.x == 0) {                                                                          \
             unsigned long long t_;                                                                                  \
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                                  \
-            P.trace[((size_t)P.trace_slot * 1024 + blockIdx.x) * 12 + (k)] = t_;                                    \
+            P.trace[((size_t)P.trace_slot * 1024 + blockIdx.x + P.tile0) * 12 + (k)] = t_;                                    \
         }                                                                                                           \
     } while (0)
 #else
@@ -75,8 +75,11 @@ namespace kcrn {
 // (Two more were built and measured on a B200 in round 2 and dropped -- profiles/r2a_variants.txt: values staged in
 // shared memory with 16-byte cp.async, 23.8 vs 20.7 us per HVP; separate 16-bit natural positions for gather lengths
 // beyond 2^20, 283 vs 288 us per 4-step recurrence at the news20 shape.)
-enum GatherVariant { kGatherStored = 0, kGatherOrdered = 1, kGatherAsync = 2 };
-constexpr int kGatherVariants = 3;
+//   kGatherBulk     as kGatherAsync, but the tile's words do not travel through registers either: one thread asks for the
+//                   whole block of words with ONE bulk copy (cp.async.bulk + mbarrier, SASS UBLKCP) the moment the CTA
+//                   starts -- the block's position comes from the kernel's parameter bank (SweepParams::pdesc), not from a
+//                   descriptor load, so nothing precedes the request -- and the gathers read them from shared memory
+enum GatherVariant { kGatherStored = 0, kGatherOrdered = 1, kGatherAsync = 2, kGatherBulk = 3 };
 // shared buffer of the per-segment sums; with asynchronous gathers the product buffer is busy receiving them, so
 // the pieces of the deferred sums are staged here instead
 constexpr int kSumCapAsync = kTileSegs + 256;
@@ -242,7 +245,12 @@ int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s, const Switches &s
     // gather-ordered copy for the sweeps (KCRN_NO_GATHER_ORDER=1: A/B switch, sweeps read idx / val as stored)
     if (A->nnz > 0 && A->ntiles > 0 && gather_len <= ((int64_t)1 << (32 - kSlotBits)) && tile_nnz <= kSortCap &&
         !sw.no_gather_order) {
-        KCRN_CUDA(cudaMalloc(&A->gidx, sizeof(uint32_t) * (size_t)A->nnz));
+        KCRN_CUDA(cudaMalloc(&A->gidx, sizeof(uint32_t) * ((size_t)A->nnz + 8)));    // + 8: bulk copies run to a 16-byte boundary
+        KCRN_CUDA(cudaMemsetAsync(A->gidx + A->nnz, 0xff, sizeof(uint32_t) * 8, s));
+        if ((int)tiles.size() <= kParamTiles) {
+            A->pdesc_host.resize(tiles.size());
+            for (size_t i = 0; i < tiles.size(); ++i) A->pdesc_host[i] = make_int2(tiles[i].y, tiles[i].w & 0xffff);
+        }
         KCRN_CUDA(cudaMalloc(&A->gval, sizeof(double) * ((size_t)A->nnz + 2)));      // + 2: 16-byte pairs may straddle the end
         KCRN_CUDA(cudaMemsetAsync(A->gval + A->nnz, 0, sizeof(double) * 2, s));
         gather_order_kernel<<<(unsigned)A->ntiles, kSweepThreads, 0, s>>>(A->tiles, A->idx, A->val, A->gidx, A->gval);
@@ -310,6 +318,20 @@ struct SweepParams {
 #endif
     int init_here, m_init;         // rows-Lanczos, first pass: |g| is still in the pieces the gradient sweep left; the
                                    // recurrence state of an m_init-step run starts here (no separate init kernel)
+    // Split passes (fused single-GPU recurrence): a pass is launched as TWO kernels over the two halves of the tile list.
+    // The second half skips the wait at its start (it launches only after every CTA of the first half has passed its own
+    // wait, so the predecessor pass is complete) and waits at its end instead (its completion then implies the first
+    // half's: dependents stay transitive).  Both halves release their dependents as soon as their gathers are out, so
+    // the next kernel of the stream becomes resident -- and brings its (constant) tile stream in -- while this one is
+    // still gathering and reducing.
+    int tile0;                     // first tile of this launch (blockIdx.x + tile0 = tile)
+    int grid_total;                // CTAs of the whole pass (partial-sum slots, strides); 0: gridDim.x
+    int late_wait;                 // second half: wait for the predecessor at the end, not at the start
+    int early_trigger;             // release the dependents right after the gathers have been issued
+    // {first entry, entries} of the first npdesc tiles, in the kernel's parameter (constant) bank: a CTA knows where its
+    // stream starts without a load (kGatherBulk); matrices of more tiles read the descriptor from global memory
+    int npdesc;
+    int2 pdesc[kParamTiles];
 };
 
 struct SweepState {
@@ -454,11 +476,14 @@ __device__ __forceinline__ void defer_end(bool two, int n0, int n1, const double
 }
 
 template <int MODE, int kItems, int GATHER>
-__global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepParams P) {
+__global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const __grid_constant__ SweepParams P) {
     constexpr int kTileNnz = kItems * kSweepThreads;       // non-zeros per CTA tile, kItems per thread
-    constexpr bool ordered = GATHER != kGatherStored, kAsyncGather = GATHER == kGatherAsync;
-    __shared__ double sprod[kTileNnz];                     // products of the tile
-    __shared__ double ssum[kAsyncGather ? kSumCapAsync : kTileSegs];   // per-segment sums of the tile
+    constexpr bool kBulk = GATHER == kGatherBulk;
+    constexpr bool ordered = GATHER != kGatherStored, kAsyncGather = GATHER == kGatherAsync || kBulk;
+    __shared__ __align__(16) double sprod[kTileNnz];       // products of the tile (16-byte aligned: the deferred sums' pieces arrive by 16-byte cp.async)
+    __shared__ __align__(16) uint32_t swords[kBulk ? kTileNnz + 8 : 4];   // bulk variant: the tile's words
+    __shared__ uint64_t sbar;
+    __shared__ __align__(16) double ssum[kAsyncGather ? kSumCapAsync : kTileSegs];   // per-segment sums of the tile
     double *const spieces = kAsyncGather ? ssum : sprod;   // staging of the deferred sums' pieces (the product buffer is
                                                            // busy receiving the asynchronous gathers)
     __shared__ int sptr[kTileSegs + 8];          // segment pointers of the tile
@@ -470,22 +495,73 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
     // Everything that only depends on the (constant) matrix is requested BEFORE waiting for the previous kernel
     // of the stream: with programmatic dependent launch this CTA may already be resident while that kernel is
     // still finishing, so the descriptor -> (index, value) part of the latency chain overlaps with its tail.
-    const int tile = blockIdx.x;
+    const int tile = (int)blockIdx.x + P.tile0;                        // split passes: this launch covers tiles tile0 ..
+    const unsigned nblk = P.grid_total ? (unsigned)P.grid_total : gridDim.x;   // CTAs of the whole pass
+    auto leave = [&]() { if (P.late_wait) pdl_wait(); };            // second half of a split pass: see SweepParams
     KTRACE(0);                       // kernel entry
     int4 td = make_int4(0, 0, 0, 0);
     int ci[kItems];                  // index, or gather-ordered word (index << kSlotBits | natural position); -1: none
     double av[kItems];
-    if (tile < P.ntiles) {
+    int woff = 0, nke = 0;           // bulk variant: where the tile's first word sits in swords (16-byte aligned source); entries
+    if constexpr (kBulk) {
+        if (tile < P.ntiles) {
+            int k0e;
+            if (tile < P.npdesc) {
+                const int2 pd = P.pdesc[tile];
+                k0e = pd.x; nke = pd.y;
+                td = __ldg(P.tiles + tile);          // the rest of the descriptor is not needed before the stream is on its way
+            } else {
+                td = __ldg(P.tiles + tile);
+                k0e = td.y; nke = td.w & 0xffff;
+            }
+            woff = k0e & 3;
+            if (tid == 0 && nke > 0) {
+                mbar_init(&sbar, 1);
+                fence_mbar_init();
+                const unsigned bytes = (((unsigned)(woff + nke) * 4u) + 15u) & ~15u;
+                mbar_expect_tx(&sbar, bytes);
+                bulk_g2s(swords, P.gidx + (k0e - woff), bytes, &sbar);
+            }
+            const double *vp = P.val + k0e;
+#pragma unroll
+            for (int r = 0; r < kItems; ++r) {
+                const int i = r * kSweepThreads + tid;
+                av[r] = i < nke ? ld_stream(vp + i) : 0.0;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < kItems; ++r) av[r] = 0.0;
+        }
+        __syncthreads();             // the barrier object is initialised before anybody waits on it
+    }
+    if (!kBulk && tile < P.ntiles) {      // (kBulk is a compile-time constant: the branch disappears)
         td = __ldg(P.tiles + tile);
         const int32_t *ip = (ordered ? reinterpret_cast<const int32_t *>(P.gidx) : P.idx) + td.y;
         const double *vp = (ordered && !kAsyncGather ? P.gval : P.val) + td.y;
         const int nk0 = td.w & 0xffff;
+        // all index words first, then the values: the gathers only need the words (a third of the stream's bytes), so
+        // they can start while the values are still on their way (-DKCRN_INTERLEAVED_STREAM: the old order, for A/B)
+#ifdef KCRN_INTERLEAVED_STREAM
 #pragma unroll
         for (int r = 0; r < kItems; ++r) {
             const int i = r * kSweepThreads + tid;
             ci[r] = i < nk0 ? ld_stream(ip + i) : -1;
             av[r] = i < nk0 ? ld_stream(vp + i) : 0.0;
         }
+#else
+#pragma unroll
+        for (int r = 0; r < kItems; ++r) {
+            const int i = r * kSweepThreads + tid;
+            ci[r] = i < nk0 ? ld_stream(ip + i) : -1;
+        }
+#pragma unroll
+        for (int r = 0; r < kItems; ++r) {
+            const int i = r * kSweepThreads + tid;
+            av[r] = i < nk0 ? ld_stream(vp + i) : 0.0;
+        }
+#endif
+    }
+    if (tile < P.ntiles) {
         if (td.z > 0 && (td.w >> 16) != kSingleTag) {
 #pragma unroll
             for (int r = 0; r < kSegRounds + 1; ++r) {
@@ -495,7 +571,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         }
     }
     KTRACE(1);                       // matrix-only loads requested
-    pdl_wait();      // the previous kernel's results (control block, vectors) are complete and visible from here on
+    if (!P.late_wait) pdl_wait();      // the previous kernel's results (control block, vectors) are complete and visible from here on
     KTRACE(2);                       // predecessor complete
 
     SweepState S;
@@ -505,23 +581,46 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
     double xv[kItems];                   // gathered values of the tile
     bool gathered = false;
     // the gathers of the tile from `src`: into registers, or (asynchronous) straight into the natural slots of sprod
+    bool words_here = false;
     auto gather_from = [&](const double *src) {
+        if constexpr (kBulk) {
+            if (tile < P.ntiles) {
+                if (!words_here && nke > 0) { mbar_wait(&sbar, 0); words_here = true; }
 #pragma unroll
-        for (int r = 0; r < kItems; ++r) {
-            if constexpr (kAsyncGather) {
-                const int i = r * kSweepThreads + tid;
-                if (ci[r] != -1)
-                    cp_async_8(sprod + KCRN_SLOT(ordered ? (ci[r] & ((1 << kSlotBits) - 1)) : i, i), src + gather_index(ci[r], ordered));
-            } else {
-                xv[r] = ci[r] != -1 ? __ldg(src + gather_index(ci[r], ordered)) : 0.0;
+                for (int r = 0; r < kItems; ++r) {
+                    const int i = r * kSweepThreads + tid;
+                    if (i < nke) {
+                        const unsigned w = swords[woff + i];
+                        cp_async_8(sprod + KCRN_SLOT(w & ((1u << kSlotBits) - 1u), i), src + (w >> kSlotBits));
+                    }
+                }
             }
+            cp_async_commit();
+        } else {
+#pragma unroll
+            for (int r = 0; r < kItems; ++r) {
+                if constexpr (kAsyncGather) {
+                    const int i = r * kSweepThreads + tid;
+                    if (ci[r] != -1)
+                        cp_async_8(sprod + KCRN_SLOT(ordered ? (ci[r] & ((1 << kSlotBits) - 1)) : i, i), src + gather_index(ci[r], ordered));
+                } else {
+                    xv[r] = ci[r] != -1 ? __ldg(src + gather_index(ci[r], ordered)) : 0.0;
+                }
+            }
+            if constexpr (kAsyncGather) cp_async_commit();
         }
-        if constexpr (kAsyncGather) cp_async_commit();
+    };
+    // before a CTA leaves early nothing may still be on its way into its shared memory
+    auto drain = [&]() {
+        cp_async_wait_all();
+        if constexpr (kBulk) {
+            if (tile < P.ntiles && !words_here && nke > 0) { mbar_wait(&sbar, 0); words_here = true; }
+        }
     };
     bool alpha_pending = false;
     LanczosCtl st_cols;
     if constexpr (MODE == kRowsLanczos) {
-        const bool scribe = blockIdx.x == 0 && tid == 0;      // the one thread that persists what all compute
+        const bool scribe = tile == 0 && tid == 0;            // the one thread that persists what all compute
         // Requests that do not depend on the control block go first: the pieces of the sum this kernel has to finish
         // (beta = |w'| of the column sweep before us, or |g| of the gradient sweep).  (Starting the gathers here as
         // well, speculatively from the vector the host knows, was measured: no gain, profiles/r2g_ab.txt.)
@@ -540,15 +639,22 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
             st.col = 0; st.redo = 0; st.final_ = (P.m_init == 1); st.done = 0; st.m_eff = P.m_init; st.nvalid = 1;
             st.store_idx = P.m_init - 1; st.m = P.m_init; st.broke = 0; st.hvps = 0; st.last_beta = 0.0;
             st.cur_beta = gn; st.cur_alpha = 0.0;
-            if (blockIdx.x == 0) {
+            if (tile == 0) {
                 for (int i = tid; i < P.m_init; i += kSweepThreads) { P.alphas[i] = 0.0; P.bet[i + 1] = 0.0; }
                 if (tid == 0) P.bet[0] = gn;
             }
         } else {
             st = *P.ctl_in;
+            // bulk variant: the words are (almost) here, the control block is on its way -- the gathers go out now, from
+            // w' (the source unless the recurrence breaks down, which the `redo` branch below repairs), instead of behind
+            // the round trip of the control block
+            if constexpr (kBulk) {
+                if (P.advance_here && !gathered) { gather_from(P.wp); gathered = true; }
+            }
             if (st.done) {
-                cp_async_wait_all();                           // nothing may still be on its way into this CTA's shared memory
+                drain();                                       // nothing may still be on its way into this CTA's shared memory
                 if (scribe && P.ctl != P.ctl_in) *P.ctl = st;      // keep the pair in step
+                leave();
                 return;
             }
             if (P.advance_here) {
@@ -586,19 +692,25 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
             alpha_pending = true;
         }
         st_cols = *P.ctl_in;
-        if (st_cols.done) { cp_async_wait_all(); return; }
+        if constexpr (kBulk) {                   // the source of the column pass (t) does not depend on the control block
+            gather_from(P.src);
+            gathered = true;
+        }
+        if (st_cols.done) { drain(); leave(); return; }
         col = st_cols.col;
         if (P.defer) {
             if (st_cols.final_) {                              // cubic.py:109: the last alpha needs no further vector
                 double s1, s2;
                 defer_end<false>(true, P.prev_count, P.prev_nlong, spieces, sred, s1, s2);      // waits for everything in flight
-                if (blockIdx.x == 0 && tid == 0) {
+                drain();
+                if (tile == 0 && tid == 0) {
                     const double alpha = __dadd_rn(quotient(s1, P.n_samples, P.inv_n), __dmul_rn(P.l2, s2));
                     P.alphas[st_cols.store_idx] = alpha;
                     P.ctl->cur_alpha = alpha;
                     P.ctl->hvps = st_cols.hvps + 1;
                     P.ctl->done = 1;
                 }
+                leave();
                 return;
             }
         } else {
@@ -620,7 +732,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         // basis column `col` (the sweep itself divides on the fly); |v|^2 for the l2 part of alpha
         if (!redo || P.l2 != 0.0) {
             double *vout = P.V + (size_t)col * P.d;
-            for (int64_t c = (int64_t)blockIdx.x * blockDim.x + tid; c < P.d; c += (int64_t)gridDim.x * blockDim.x) {
+            for (int64_t c = (int64_t)tile * blockDim.x + tid; c < P.d; c += (int64_t)nblk * blockDim.x) {
                 const double vc = quotient(__ldg(S.src + c), S.beta, S.rinv);
                 if (!redo) vout[c] = vc;
                 vsq = fma(vc, vc, vsq);
@@ -651,12 +763,13 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         }
         KTRACE(4);                   // basis column stored, operands requested
         if (!gathered) gather_from(S.src);
+        if (P.early_trigger) pdl_trigger();      // split passes: the next kernel may come in and fetch its stream now
         if constexpr (MODE == kColsLanczos) {
             if (alpha_pending) {                 // the gathers above are in flight while the pieces are added
                 double s1, s2;
                 defer_end<kAsyncGather>(true, P.prev_count, P.prev_nlong, spieces, sred, s1, s2);
                 S.alpha = __dadd_rn(quotient(s1, P.n_samples, P.inv_n), __dmul_rn(P.l2, s2));
-                if (blockIdx.x == 0 && tid == 0) {
+                if (tile == 0 && tid == 0) {
                     P.alphas[col] = S.alpha;
                     P.ctl->cur_alpha = S.alpha;
                     P.ctl->hvps = st_cols.hvps + 1;
@@ -753,14 +866,14 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         if (P.red_partials) {
             __syncthreads();
             const double mine = cta_sum_to_thread0(acc, sred);
-            if (tid == 0) P.red_partials[blockIdx.x] = mine;
+            if (tid == 0) P.red_partials[tile] = mine;
         }
     }
 
     if constexpr (MODE == kRowsForward) {
         __syncthreads();
         const double mine = cta_sum_to_thread0(acc, sred);
-        if (tid == 0) P.red_partials[blockIdx.x] = mine;
+        if (tid == 0) P.red_partials[tile] = mine;
     }
 
     if constexpr (MODE == kRowsLanczos) {
@@ -770,21 +883,21 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         double mine, mine2;
         cta_sum2_to_thread0(acc, vsq, sred, mine, mine2);
         if (tid == 0) {
-            P.red_partials[blockIdx.x] = mine;
-            P.red_partials[((gridDim.x + 1) & ~1u) + blockIdx.x] = mine2;      // even stride: 16-byte copies later
+            P.red_partials[tile] = mine;
+            P.red_partials[((nblk + 1) & ~1u) + tile] = mine2;            // even stride: 16-byte copies later
         }
-        if (P.defer) { KTRACE(9); return; }
+        if (P.defer) { KTRACE(9); leave(); return; }
         if (tid == 0) {
             __threadfence();
-            s_last = atomicInc(P.red_ticket, gridDim.x - 1) == gridDim.x - 1;
+            s_last = atomicInc(P.red_ticket, nblk - 1) == nblk - 1;
         }
         __syncthreads();
         if (s_last) {
             __threadfence();
             double tot = 0.0, tot2 = 0.0;
-            for (int i = tid; i < (int)gridDim.x; i += kSweepThreads) {
+            for (int i = tid; i < (int)nblk; i += kSweepThreads) {
                 tot += __ldcg(P.red_partials + i);
-                tot2 += __ldcg(P.red_partials + ((gridDim.x + 1) & ~1u) + i);
+                tot2 += __ldcg(P.red_partials + ((nblk + 1) & ~1u) + i);
             }
             for (int i = tid; i < P.nlong; i += kSweepThreads) tot += __ldcg(P.longdot + i);
             __syncthreads();
@@ -808,20 +921,20 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
     if constexpr (MODE == kColsLanczos) {
         // beta^2 = |w'|^2: threads -> tile (fixed order) -> tiles in tile order, by the next row sweep (deferred) or
         // by the last CTA here
-        if (!P.update_ctl) return;                 // re-orthogonalisation follows: it recomputes the norm
+        if (!P.update_ctl) { leave(); return; }    // re-orthogonalisation follows: it recomputes the norm
         __syncthreads();
         const double mine = cta_sum_to_thread0(acc, sred);
-        if (tid == 0) P.red_partials[blockIdx.x] = mine;
-        if (P.defer) { KTRACE(9); return; }
+        if (tid == 0) P.red_partials[tile] = mine;
+        if (P.defer) { KTRACE(9); leave(); return; }
         if (tid == 0) {
             __threadfence();
-            s_last = atomicInc(P.red_ticket, gridDim.x - 1) == gridDim.x - 1;
+            s_last = atomicInc(P.red_ticket, nblk - 1) == nblk - 1;
         }
         __syncthreads();
         if (s_last) {
             __threadfence();
             double tot = 0.0;
-            for (int i = tid; i < (int)gridDim.x; i += kSweepThreads) tot += __ldcg(P.red_partials + i);
+            for (int i = tid; i < (int)nblk; i += kSweepThreads) tot += __ldcg(P.red_partials + i);
             for (int i = tid; i < P.nlong; i += kSweepThreads) tot += __ldcg(P.longdot + i);
             __syncthreads();
             const double bsq = cta_sum_to_thread0(tot, sred);
@@ -829,33 +942,53 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         }
     }
     KTRACE(9);                       // tail sums written
+    leave();
 }
 
 void fill_matrix(SweepParams &P, const SegMat &A) {
     P.ptr = A.ptr; P.idx = A.idx; P.val = A.val; P.gidx = A.gidx; P.gval = A.gval; P.tiles = A.tiles; P.ntiles = A.ntiles;
     P.longtab = A.longtab; P.segid = A.segid; P.partial = A.partial; P.longdot = A.longdot; P.ticket = A.ticket;
     P.nlong = A.nlong;
+    P.npdesc = (int)A.pdesc_host.size();
+    if (P.npdesc) memcpy(P.pdesc, A.pdesc_host.data(), sizeof(int2) * A.pdesc_host.size());
 }
 
 template <int MODE, int GATHER>
-int launch_variant(kcrn_problem *h, const SegMat &A, const SweepParams &P) {
-    if (A.items == 11) KCRN_CUDA(launch_kernel(sweep_kernel<MODE, 11, GATHER>, dim3(A.grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
-    else if (A.items == 12) KCRN_CUDA(launch_kernel(sweep_kernel<MODE, 12, GATHER>, dim3(A.grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
-    else KCRN_CUDA(launch_kernel(sweep_kernel<MODE, 8, GATHER>, dim3(A.grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
+int launch_variant(kcrn_problem *h, const SegMat &A, const SweepParams &P, int grid) {
+    if (A.items == 11) KCRN_CUDA(launch_kernel(sweep_kernel<MODE, 11, GATHER>, dim3(grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
+    // (12 per thread + the word buffer of the bulk variant exceed the 48 KB of static shared memory: those tiles gather asynchronously)
+    else if (A.items == 12) KCRN_CUDA(launch_kernel(sweep_kernel<MODE, 12, GATHER == kGatherBulk ? kGatherAsync : GATHER>, dim3(grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
+    else KCRN_CUDA(launch_kernel(sweep_kernel<MODE, 8, GATHER>, dim3(grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
     return KCRN_OK;
 }
 
 // The gather variant is a property of (matrix, class of pass): the Lanczos passes carry more state than the others
 template <int MODE>
-int launch(kcrn_problem *h, const SegMat &A, SweepParams &P, double *longdot = nullptr) {
+int launch(kcrn_problem *h, const SegMat &A, SweepParams &P, double *longdot = nullptr, bool split = false) {
     fill_matrix(P, A);
     if (longdot) P.longdot = longdot;      // the forward sweep keeps its long-segment shares apart from the Lanczos passes'
     const int variant = !A.gidx ? kGatherStored : (MODE == kRowsLanczos || MODE == kColsLanczos ? A.gather_lanczos : A.gather_plain);
-    if (variant == kGatherAsync) KCRN_TRY((launch_variant<MODE, kGatherAsync>(h, A, P)));
-    else if (variant == kGatherOrdered) KCRN_TRY((launch_variant<MODE, kGatherOrdered>(h, A, P)));
-    else KCRN_TRY((launch_variant<MODE, kGatherStored>(h, A, P)));
-    h->counters[0] += 1;
-    return KCRN_OK;
+    auto go = [&](int grid) -> int {
+        if (variant == kGatherBulk) KCRN_TRY((launch_variant<MODE, kGatherBulk>(h, A, P, grid)));
+        else if (variant == kGatherAsync) KCRN_TRY((launch_variant<MODE, kGatherAsync>(h, A, P, grid)));
+        else if (variant == kGatherOrdered) KCRN_TRY((launch_variant<MODE, kGatherOrdered>(h, A, P, grid)));
+        else KCRN_TRY((launch_variant<MODE, kGatherStored>(h, A, P, grid)));
+        h->counters[0] += 1;
+        return KCRN_OK;
+    };
+    // A pass of at most one wave of tiles, inside a captured graph with programmatic edges: two half launches, the second
+    // out of phase with the first (SweepParams::tile0 ...), so that the NEXT pass's first half finds free slots -- and
+    // loads its tile stream -- while this pass's second half is still at work
+    const int half = (A.grid + 1) / 2;
+    if (split && h->pdl && A.grid >= 64 && half <= 2 * kNumSm) {
+        P.grid_total = A.grid;
+        P.early_trigger = 1;
+        P.tile0 = 0; P.late_wait = 0;
+        KCRN_TRY(go(half));
+        P.tile0 = half; P.late_wait = 1;
+        return go(A.grid - half);
+    }
+    return go(A.grid);
 }
 
 // everything that loss.py derives from a cached A x, for kcrn_set_Ax (SSCN's incremental update)
@@ -888,7 +1021,7 @@ int launch_rows_weighted(kcrn_problem *h, const double *v) {
     return launch<kRowsWeighted>(h, h->csr, P);
 }
 
-int gather_candidates_last() { return kGatherAsync; }
+int gather_candidates_last() { return kGatherBulk; }
 
 // Which gather variant serves the passes outside the Lanczos recurrence: measured per matrix on the weighted row
 // pass / the scaled column pass, a few back-to-back launches each (the operands are zeroed scratch; all variants
@@ -988,7 +1121,7 @@ int launch_rows_lanczos(kcrn_problem *h, double *alpha_raw, int slot, int defer,
     P.trace = h->sweep_trace; P.trace_slot = 2 * slot;
 #endif
     h->counters[3] += 1;
-    return launch<kRowsLanczos>(h, h->csr, P);
+    return launch<kRowsLanczos>(h, h->csr, P, nullptr, defer == 2 && !h->sharded() && h->sw.split_passes);
 }
 
 int launch_cols_raw(kcrn_problem *h, const double *src, double *out) {
@@ -1022,7 +1155,7 @@ int launch_cols_lanczos(kcrn_problem *h, int update_ctl, int slot, int defer) {
     P.trace = h->sweep_trace; P.trace_slot = 2 * slot + 1;
 #endif
     h->counters[4] += 1;
-    return launch<kColsLanczos>(h, h->csc, P);
+    return launch<kColsLanczos>(h, h->csc, P, nullptr, defer == 2 && update_ctl && !h->sharded() && h->sw.split_passes);
 }
 
 int launch_derive_from_Ax(kcrn_problem *h) {

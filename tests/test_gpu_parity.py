@@ -156,7 +156,7 @@ def test_gather_variants_give_the_same_bits(torch, monkeypatch, name):
     x, v = _dev(torch, 0.3 * rng.standard_normal(P.d)), _dev(torch, rng.standard_normal(P.d))
     out, seen = [], []
     for env in (("KCRN_NO_GATHER_ORDER", "1"), ("KCRN_GATHER", "0"), ("KCRN_GATHER", "1"), ("KCRN_GATHER", "2"),
-                ("KCRN_GATHER", "2,1"), None):
+                ("KCRN_GATHER", "2,1"), None, ("KCRN_GATHER", "3"), ("KCRN_GATHER", "1,3")):
         monkeypatch.delenv("KCRN_NO_GATHER_ORDER", raising=False)
         monkeypatch.delenv("KCRN_GATHER", raising=False)
         if env:
@@ -172,7 +172,8 @@ def test_gather_variants_give_the_same_bits(torch, monkeypatch, name):
         eng.close()
     assert seen[0] == (0, 0, 0, 0) and seen[1] == (0, 0, 0, 0) and seen[2] == (1, 1, 1, 1) and seen[3] == (2, 2, 2, 2)
     assert seen[4] == (2, 1, 2, 1)
-    assert all(0 <= c <= 2 for c in seen[5])                 # measured
+    assert all(0 <= c <= 3 for c in seen[5])                 # measured
+    assert seen[6] == (3, 3, 3, 3) and seen[7] == (1, 3, 1, 3)      # words by bulk copy (cp.async.bulk + mbarrier)
     for other in out[1:]:
         assert out[0][0] == other[0]
         for a, b in zip(out[0][1:], other[1:]):
@@ -197,6 +198,7 @@ def lanczos_probe_default(tmp_path_factory):
 
 
 @pytest.mark.parametrize("env", [{"KCRN_NO_DEFER": "1", "KCRN_GATHER": "2"}, {"KCRN_NO_DEFER": "1", "KCRN_GATHER": "1"},
+                                 {"KCRN_NO_DEFER": "1", "KCRN_GATHER": "3"}, {"KCRN_NO_PDL": "1", "KCRN_GATHER": "3"},
                                  {"KCRN_NO_PDL": "1"}])
 def test_fused_lanczos_under_process_wide_switches(torch, tmp_path, lanczos_probe_default, env):
     # grid-wide sums finished by a last-CTA tail instead of by the consumer kernel (the mode row-sharded runs use)
@@ -204,11 +206,27 @@ def test_fused_lanczos_under_process_wide_switches(torch, tmp_path, lanczos_prob
     # their order, so the recurrence is expected to keep its bits; asserted to 1e-10 (the point here is that these
     # launch modes are exercised at all on one GPU).  The switches are read once per process -> child processes.
     ref, got = lanczos_probe_default, _lanczos_probe(tmp_path, "switched", env)
-    if "KCRN_GATHER" in env:
+    if "KCRN_GATHER" in env and "KCRN_NO_DEFER" in env:
         assert set(got["variants"].tolist()) == {int(env["KCRN_GATHER"])}
     assert ref["info"][0] == got["info"][0] and ref["info"][3] == got["info"][3]      # m_eff, operator applications
     for k in ("value", "grad", "hvp", "V", "alphas", "bet"):
         assert np.allclose(ref[k], got[k], rtol=1e-10, atol=1e-12), k
+
+
+@pytest.mark.parametrize("name,gather", [("rcv1", None), ("w8a", None), ("rcv1", "3"), ("rcv1", "0")])
+def test_split_passes_keep_the_bits(torch, tmp_path, name, gather):
+    # KCRN_SPLIT: every Lanczos pass of the fused recurrence is launched as two half kernels, the second out of phase
+    # with the first (it waits for its predecessor at its end, not at its start), so that the next pass's tile stream
+    # comes in while this pass is still reducing.  Same tiles, same sums in the same order: nothing may change.
+    env = {} if gather is None else {"KCRN_GATHER": gather}
+    ref = _lanczos_probe(tmp_path, "whole", dict(env, KCRN_SPLIT="0"), name=name)
+    got = _lanczos_probe(tmp_path, "split", dict(env, KCRN_SPLIT="1"), name=name)
+    for k in ("info", "V", "alphas", "bet", "grad", "hvp"):
+        assert np.array_equal(ref[k], got[k]), k
+    ref2 = _lanczos_probe(tmp_path, "whole_r", dict(env, KCRN_SPLIT="0"), name=name, reorth=1)
+    got2 = _lanczos_probe(tmp_path, "split_r", dict(env, KCRN_SPLIT="1"), name=name, reorth=1)
+    for k in ("info", "V", "alphas", "bet"):
+        assert np.array_equal(ref2[k], got2[k]), k
 
 
 def test_sharded_code_path_on_one_gpu(torch, tmp_path, lanczos_probe_default):
@@ -372,6 +390,35 @@ def test_cubic_subproblem_vs_reference_golden(torch, golden):
         assert abs(dec - dec_ref) <= 1e-9 * abs(dec_ref) + 1e-300
         worst = max(worst, rel_err(s.cpu().numpy(), g[f"c{i}_s"]))
     assert worst <= 1e-8   # tridiagonal Cholesky vs LAPACK dposv on T + r I with cond up to ~1e9
+
+
+def test_cubic_small_path_equals_general_path(torch, golden):
+    """m <= 16 runs with the factor in registers (cubic_small_kernel), larger m in shared memory (cubic_kernel).  Padding
+    T with an identity tail block and a zero gradient tail is exactly equivalent to the small problem, and
+    pushes it through the general kernel: both paths must give the same bits."""
+    from kcrn_b200.engine import cubic_tridiag
+    g = golden("cubic")
+    rng = np.random.default_rng(5)
+    cases = [(g[f"c{i}_alphas"], g[f"c{i}_betas"], *g[f"c{i}_scal"][:3]) for i in range(int(g["count"]))]
+    for m in (1, 2, 3, 10, 16):                       # plus fresh SPD tridiagonals at the sizes the step loop uses
+        be = rng.uniform(1e-3, 0.5, size=m - 1)
+        al = rng.uniform(1.0, 2.0, size=m) + 1.0
+        cases.append((al, be, rng.uniform(0.1, 3.0), 10.0 ** rng.uniform(-6, 0), 0.1))
+    checked = 0
+    for al, be, g0, M, r0 in cases:
+        m = al.size
+        if m > 16:
+            continue
+        pad = 24 - m
+        al2 = np.concatenate([al, np.ones(pad)])
+        be2 = np.concatenate([be, np.zeros(pad)])
+        s, r, dec, its, status = cubic_tridiag(al, be, g0, M, r0=r0, eps=1e-8, it_max=100)
+        s2, r2, dec2, its2, status2 = cubic_tridiag(al2, be2, g0, M, r0=r0, eps=1e-8, it_max=100)
+        assert (status, its) == (status2, its2)
+        assert r == r2 and dec == dec2
+        assert torch.equal(s, s2[:m]) and float(s2[m:].abs().max()) == 0.0
+        checked += 1
+    assert checked >= 5
 
 
 def test_cubic_solver_root_surface(torch, golden):
