@@ -26,8 +26,8 @@ Switches read_switches() {
     if (const char *e = getenv("KCRN_GATHER")) {         // "p[,l]": plain / Lanczos passes
         int a = -1, b = -1;
         const int k = sscanf(e, "%d,%d", &a, &b);
-        if (k >= 1 && a >= 0 && a < 4) w.gather_plain = w.gather_lanczos = a;
-        if (k >= 2 && b >= 0 && b < 4) w.gather_lanczos = b;
+        if (k >= 1 && a >= 0 && a < 3) w.gather_plain = w.gather_lanczos = a;
+        if (k >= 2 && b >= 0 && b < 3) w.gather_lanczos = b;
     }
     w.short_seg = num("KCRN_SHORT_SEG");
     w.tile_items = num("KCRN_TILE_ITEMS");
@@ -35,7 +35,6 @@ Switches read_switches() {
     w.persist_trace = on("KCRN_PERSIST_TRACE");
     w.persist_flags = num("KCRN_PERSIST_FLAGS");
     if (getenv("KCRN_DSHARD")) w.dshard = num("KCRN_DSHARD") != 0 ? 1 : 0;
-    if (getenv("KCRN_SPLIT")) w.split_passes = num("KCRN_SPLIT") != 0;
     return w;
 }
 
@@ -501,7 +500,7 @@ int kcrn_create(kcrn_handle *out, int64_t n_rows, int64_t n_cols, int64_t nnz, c
 #ifdef KCRN_SWEEP_TRACE
 // where the time of the LAST captured recurrence went: per pass (slot), the marks of thread 0 of every CTA
 static void print_sweep_trace(kcrn_problem *h) {
-    const int slots = 20;
+    const int slots = 22;      // 0 .. 19: Lanczos passes of the last recurrence; 20, 21: the last plain row / column pass
     std::vector<unsigned long long> T((size_t)slots * 1024 * 12);
     if (cudaMemcpy(T.data(), h->sweep_trace, sizeof(unsigned long long) * T.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return;
     const char *name[9] = {"entry -> loads requested", "wait for predecessor", "control block (+ deferred sum)", "basis column, operands",
@@ -510,7 +509,7 @@ static void print_sweep_trace(kcrn_problem *h) {
     for (int sl = 0; sl < slots; ++sl) {
         const int grid = sl % 2 == 0 ? h->csr.grid : h->csc.grid;
         unsigned long long t0min = ~0ull, t9max = 0, t2min = ~0ull;
-        double sum[9] = {0}, mx[9] = {0};
+        double sum[9] = {0}, mx[9] = {0}, extra[2] = {0};
         int cnt = 0;
         for (int c = 0; c < grid && c < 1024; ++c) {
             const unsigned long long *t = T.data() + ((size_t)sl * 1024 + c) * 12;
@@ -521,12 +520,17 @@ static void print_sweep_trace(kcrn_problem *h) {
                 const double d = t[k + 1] >= t[k] && t[k + 1] != 0 && t[k] != 0 ? (double)(t[k + 1] - t[k]) : 0.0;
                 sum[k] += d; mx[k] = std::max(mx[k], d);
             }
+            for (int k = 10; k < 12; ++k)          // inside "control block": since the predecessor's completion
+                if (t[k] >= t[2] && t[2] != 0) extra[k - 10] += (double)(t[k] - t[2]);
         }
         if (!cnt) continue;
         fprintf(stderr, "kcrn: sweep trace slot %2d (%s, %d CTAs): first entry -> last end %6.0f ns; gap after previous pass %6.0f ns; first entry -> first released %5.0f ns\n",
                 sl, sl % 2 == 0 ? "rows" : "cols", cnt, (double)(t9max - t0min), prev_end ? (double)t0min - (double)prev_end : 0.0, (double)(t2min - t0min));
-        if (sl == 6 || sl == 7)
+        if (sl == 6 || sl == 7 || sl >= 20)
+        {
             for (int k = 0; k < 9; ++k) fprintf(stderr, "kcrn:     %-32s mean %6.0f  max %6.0f ns\n", name[k], sum[k] / cnt, mx[k]);
+            if (sl < 20) fprintf(stderr, "kcrn:     since predecessor complete: control block read %6.0f ns, index words here + gathers out %6.0f ns\n", extra[0] / cnt, extra[1] / cnt);
+        }
         prev_end = t9max;
     }
 }

@@ -61,7 +61,6 @@ struct Switches {
     bool persist = false, persist_trace = false;  // KCRN_PERSIST, KCRN_PERSIST_TRACE: one-kernel recurrence (opt-in)
     int persist_flags = 0;                        // KCRN_PERSIST_FLAGS: its measured experiments
     int dshard = -1;                              // KCRN_DSHARD=1 / 0: d-sharded re-orthogonalisation on / off (-1: by size)
-    bool split_passes = false;                    // KCRN_SPLIT=1: Lanczos passes of the fused recurrence as two half launches out of phase
 };
 Switches read_switches();
 
@@ -76,7 +75,6 @@ constexpr int kSweepThreads = kSweepWarps * 32;
 constexpr int kVecThreads = 256;   // CTA size of the d-length vector kernels
 constexpr int kMaxM = 512;         // largest Lanczos subspace the single-CTA solver accepts
 constexpr int kNumSm = 148;        // B200
-constexpr int kParamTiles = 4 * kNumSm;   // tiles whose {first entry, entries} travel in the sweep kernels' parameter bank (one wave)
 constexpr int kMaxPeers = 16;      // ranks of one NVLink domain that can share exchange buffers
 
 // One sparse matrix stored by segments: rows (CSR) or columns (CSC).
@@ -114,7 +112,6 @@ struct SegMat {
     int32_t *segid = nullptr;    // [nseg] original column of the s-th stored segment (null: natural order)
     int32_t *pos = nullptr;      // [nseg] where column c is stored
     std::vector<int32_t> cptr_host;   // canonical column pointer (natural order), for kcrn_csc_view
-    std::vector<int2> pdesc_host;     // {first entry, entries} per tile when the tile list fits kParamTiles (kGatherBulk)
 };
 
 // ----------------------------------------------------------------------------- persistent recurrence (kcrn_persist.cu)

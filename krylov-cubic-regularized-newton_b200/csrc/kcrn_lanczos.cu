@@ -335,6 +335,10 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_post_sharded_kernel(VecPa
     }
 }
 
+// (Round 2 also measured stage 2 with the basis entries it fetches for w' -= V c kept in shared memory for the coefficients
+// V' w' that follow -- "staged through shared memory", bit-identical: 24.3 ms (72 KB per CTA) / 28.3 ms (184 KB) against
+// 19.8 ms per 50-step recurrence at the news20 shape, profiles/r2y_c3_reorth_staged.txt.  The second use already comes from
+// L2; the shared memory only costs resident CTAs.  Removed.)
 template <int E>
 __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P) {
     pdl_wait();

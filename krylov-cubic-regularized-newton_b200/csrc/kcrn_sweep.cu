@@ -55,7 +55,7 @@
         if (P.trace && threadIdx.x == 0) {                                                                          \
             unsigned long long t_;                                                                                  \
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                                  \
-            P.trace[((size_t)P.trace_slot * 1024 + blockIdx.x + P.tile0) * 12 + (k)] = t_;                                    \
+            P.trace[((size_t)P.trace_slot * 1024 + blockIdx.x) * 12 + (k)] = t_;                                    \
         }                                                                                                           \
     } while (0)
 #else
@@ -75,11 +75,7 @@ namespace kcrn {
 // (Two more were built and measured on a B200 in round 2 and dropped -- profiles/r2a_variants.txt: values staged in
 // shared memory with 16-byte cp.async, 23.8 vs 20.7 us per HVP; separate 16-bit natural positions for gather lengths
 // beyond 2^20, 283 vs 288 us per 4-step recurrence at the news20 shape.)
-//   kGatherBulk     as kGatherAsync, but the tile's words do not travel through registers either: one thread asks for the
-//                   whole block of words with ONE bulk copy (cp.async.bulk + mbarrier, SASS UBLKCP) the moment the CTA
-//                   starts -- the block's position comes from the kernel's parameter bank (SweepParams::pdesc), not from a
-//                   descriptor load, so nothing precedes the request -- and the gathers read them from shared memory
-enum GatherVariant { kGatherStored = 0, kGatherOrdered = 1, kGatherAsync = 2, kGatherBulk = 3 };
+enum GatherVariant { kGatherStored = 0, kGatherOrdered = 1, kGatherAsync = 2 };
 // shared buffer of the per-segment sums; with asynchronous gathers the product buffer is busy receiving them, so
 // the pieces of the deferred sums are staged here instead
 constexpr int kSumCapAsync = kTileSegs + 256;
@@ -191,6 +187,8 @@ void plan_tiles(const std::vector<int32_t> &ptr, int64_t nseg, int64_t nnz, std:
     const bool env_short = sw.short_seg > 0;                // tuning knob: longest segment that shares a tile
     const bool env_items = sw.tile_items > 0;               // tuning knob: force 8, 11 or 12 non-zeros per thread
     npartial = 0;
+    // (three CTAs of 14 items per SM at 80 registers were measured as well: the row pass gains 0.7 us, the column copy no
+    // longer fits one wave, 21.1 vs 20.3 us per HVP -- profiles/r2x_variants_three_ctas.txt)
     const int cand[3] = {8, 11, 12};
     const int slots = kNumSm * 4 - 32;                      // resident CTAs, minus a margin for the neighbours under PDL
     int short_seg = kShortSeg;
@@ -245,12 +243,7 @@ int build_tiles(SegMat *A, int64_t gather_len, cudaStream_t s, const Switches &s
     // gather-ordered copy for the sweeps (KCRN_NO_GATHER_ORDER=1: A/B switch, sweeps read idx / val as stored)
     if (A->nnz > 0 && A->ntiles > 0 && gather_len <= ((int64_t)1 << (32 - kSlotBits)) && tile_nnz <= kSortCap &&
         !sw.no_gather_order) {
-        KCRN_CUDA(cudaMalloc(&A->gidx, sizeof(uint32_t) * ((size_t)A->nnz + 8)));    // + 8: bulk copies run to a 16-byte boundary
-        KCRN_CUDA(cudaMemsetAsync(A->gidx + A->nnz, 0xff, sizeof(uint32_t) * 8, s));
-        if ((int)tiles.size() <= kParamTiles) {
-            A->pdesc_host.resize(tiles.size());
-            for (size_t i = 0; i < tiles.size(); ++i) A->pdesc_host[i] = make_int2(tiles[i].y, tiles[i].w & 0xffff);
-        }
+        KCRN_CUDA(cudaMalloc(&A->gidx, sizeof(uint32_t) * (size_t)A->nnz));
         KCRN_CUDA(cudaMalloc(&A->gval, sizeof(double) * ((size_t)A->nnz + 2)));      // + 2: 16-byte pairs may straddle the end
         KCRN_CUDA(cudaMemsetAsync(A->gval + A->nnz, 0, sizeof(double) * 2, s));
         gather_order_kernel<<<(unsigned)A->ntiles, kSweepThreads, 0, s>>>(A->tiles, A->idx, A->val, A->gidx, A->gval);
@@ -318,20 +311,6 @@ struct SweepParams {
 #endif
     int init_here, m_init;         // rows-Lanczos, first pass: |g| is still in the pieces the gradient sweep left; the
                                    // recurrence state of an m_init-step run starts here (no separate init kernel)
-    // Split passes (fused single-GPU recurrence): a pass is launched as TWO kernels over the two halves of the tile list.
-    // The second half skips the wait at its start (it launches only after every CTA of the first half has passed its own
-    // wait, so the predecessor pass is complete) and waits at its end instead (its completion then implies the first
-    // half's: dependents stay transitive).  Both halves release their dependents as soon as their gathers are out, so
-    // the next kernel of the stream becomes resident -- and brings its (constant) tile stream in -- while this one is
-    // still gathering and reducing.
-    int tile0;                     // first tile of this launch (blockIdx.x + tile0 = tile)
-    int grid_total;                // CTAs of the whole pass (partial-sum slots, strides); 0: gridDim.x
-    int late_wait;                 // second half: wait for the predecessor at the end, not at the start
-    int early_trigger;             // release the dependents right after the gathers have been issued
-    // {first entry, entries} of the first npdesc tiles, in the kernel's parameter (constant) bank: a CTA knows where its
-    // stream starts without a load (kGatherBulk); matrices of more tiles read the descriptor from global memory
-    int npdesc;
-    int2 pdesc[kParamTiles];
 };
 
 struct SweepState {
@@ -476,13 +455,10 @@ __device__ __forceinline__ void defer_end(bool two, int n0, int n1, const double
 }
 
 template <int MODE, int kItems, int GATHER>
-__global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const __grid_constant__ SweepParams P) {
+__global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepParams P) {
     constexpr int kTileNnz = kItems * kSweepThreads;       // non-zeros per CTA tile, kItems per thread
-    constexpr bool kBulk = GATHER == kGatherBulk;
-    constexpr bool ordered = GATHER != kGatherStored, kAsyncGather = GATHER == kGatherAsync || kBulk;
+    constexpr bool ordered = GATHER != kGatherStored, kAsyncGather = GATHER == kGatherAsync;
     __shared__ __align__(16) double sprod[kTileNnz];       // products of the tile (16-byte aligned: the deferred sums' pieces arrive by 16-byte cp.async)
-    __shared__ __align__(16) uint32_t swords[kBulk ? kTileNnz + 8 : 4];   // bulk variant: the tile's words
-    __shared__ uint64_t sbar;
     __shared__ __align__(16) double ssum[kAsyncGather ? kSumCapAsync : kTileSegs];   // per-segment sums of the tile
     double *const spieces = kAsyncGather ? ssum : sprod;   // staging of the deferred sums' pieces (the product buffer is
                                                            // busy receiving the asynchronous gathers)
@@ -495,50 +471,19 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const __grid_co
     // Everything that only depends on the (constant) matrix is requested BEFORE waiting for the previous kernel
     // of the stream: with programmatic dependent launch this CTA may already be resident while that kernel is
     // still finishing, so the descriptor -> (index, value) part of the latency chain overlaps with its tail.
-    const int tile = (int)blockIdx.x + P.tile0;                        // split passes: this launch covers tiles tile0 ..
-    const unsigned nblk = P.grid_total ? (unsigned)P.grid_total : gridDim.x;   // CTAs of the whole pass
-    auto leave = [&]() { if (P.late_wait) pdl_wait(); };            // second half of a split pass: see SweepParams
+    const int tile = blockIdx.x;
+    const unsigned nblk = gridDim.x;
     KTRACE(0);                       // kernel entry
     int4 td = make_int4(0, 0, 0, 0);
     int ci[kItems];                  // index, or gather-ordered word (index << kSlotBits | natural position); -1: none
     double av[kItems];
-    int woff = 0, nke = 0;           // bulk variant: where the tile's first word sits in swords (16-byte aligned source); entries
-    if constexpr (kBulk) {
-        if (tile < P.ntiles) {
-            int k0e;
-            if (tile < P.npdesc) {
-                const int2 pd = P.pdesc[tile];
-                k0e = pd.x; nke = pd.y;
-                td = __ldg(P.tiles + tile);          // the rest of the descriptor is not needed before the stream is on its way
-            } else {
-                td = __ldg(P.tiles + tile);
-                k0e = td.y; nke = td.w & 0xffff;
-            }
-            woff = k0e & 3;
-            if (tid == 0 && nke > 0) {
-                mbar_init(&sbar, 1);
-                fence_mbar_init();
-                const unsigned bytes = (((unsigned)(woff + nke) * 4u) + 15u) & ~15u;
-                mbar_expect_tx(&sbar, bytes);
-                bulk_g2s(swords, P.gidx + (k0e - woff), bytes, &sbar);
-            }
-            const double *vp = P.val + k0e;
-#pragma unroll
-            for (int r = 0; r < kItems; ++r) {
-                const int i = r * kSweepThreads + tid;
-                av[r] = i < nke ? ld_stream(vp + i) : 0.0;
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < kItems; ++r) av[r] = 0.0;
-        }
-        __syncthreads();             // the barrier object is initialised before anybody waits on it
-    }
-    if (!kBulk && tile < P.ntiles) {      // (kBulk is a compile-time constant: the branch disappears)
+    if (tile < P.ntiles) {
+        // (The tile's first entry and length were also tried in the kernel's parameter bank, so that the stream is
+        // requested without waiting for this descriptor load: no gain, profiles/r2v_variants_param_desc.txt.)
         td = __ldg(P.tiles + tile);
-        const int32_t *ip = (ordered ? reinterpret_cast<const int32_t *>(P.gidx) : P.idx) + td.y;
-        const double *vp = (ordered && !kAsyncGather ? P.gval : P.val) + td.y;
-        const int nk0 = td.w & 0xffff;
+        const int k0s = td.y, nk0 = td.w & 0xffff;
+        const int32_t *ip = (ordered ? reinterpret_cast<const int32_t *>(P.gidx) : P.idx) + k0s;
+        const double *vp = (ordered && !kAsyncGather ? P.gval : P.val) + k0s;
         // all index words first, then the values: the gathers only need the words (a third of the stream's bytes), so
         // they can start while the values are still on their way (-DKCRN_INTERLEAVED_STREAM: the old order, for A/B)
 #ifdef KCRN_INTERLEAVED_STREAM
@@ -571,7 +516,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const __grid_co
         }
     }
     KTRACE(1);                       // matrix-only loads requested
-    if (!P.late_wait) pdl_wait();      // the previous kernel's results (control block, vectors) are complete and visible from here on
+    pdl_wait();      // the previous kernel's results (control block, vectors) are complete and visible from here on
     KTRACE(2);                       // predecessor complete
 
     SweepState S;
@@ -581,42 +526,21 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const __grid_co
     double xv[kItems];                   // gathered values of the tile
     bool gathered = false;
     // the gathers of the tile from `src`: into registers, or (asynchronous) straight into the natural slots of sprod
-    bool words_here = false;
     auto gather_from = [&](const double *src) {
-        if constexpr (kBulk) {
-            if (tile < P.ntiles) {
-                if (!words_here && nke > 0) { mbar_wait(&sbar, 0); words_here = true; }
 #pragma unroll
-                for (int r = 0; r < kItems; ++r) {
-                    const int i = r * kSweepThreads + tid;
-                    if (i < nke) {
-                        const unsigned w = swords[woff + i];
-                        cp_async_8(sprod + KCRN_SLOT(w & ((1u << kSlotBits) - 1u), i), src + (w >> kSlotBits));
-                    }
-                }
+        for (int r = 0; r < kItems; ++r) {
+            if constexpr (kAsyncGather) {
+                const int i = r * kSweepThreads + tid;
+                if (ci[r] != -1)
+                    cp_async_8(sprod + KCRN_SLOT(ordered ? (ci[r] & ((1 << kSlotBits) - 1)) : i, i), src + gather_index(ci[r], ordered));
+            } else {
+                xv[r] = ci[r] != -1 ? __ldg(src + gather_index(ci[r], ordered)) : 0.0;
             }
-            cp_async_commit();
-        } else {
-#pragma unroll
-            for (int r = 0; r < kItems; ++r) {
-                if constexpr (kAsyncGather) {
-                    const int i = r * kSweepThreads + tid;
-                    if (ci[r] != -1)
-                        cp_async_8(sprod + KCRN_SLOT(ordered ? (ci[r] & ((1 << kSlotBits) - 1)) : i, i), src + gather_index(ci[r], ordered));
-                } else {
-                    xv[r] = ci[r] != -1 ? __ldg(src + gather_index(ci[r], ordered)) : 0.0;
-                }
-            }
-            if constexpr (kAsyncGather) cp_async_commit();
         }
+        if constexpr (kAsyncGather) cp_async_commit();
     };
     // before a CTA leaves early nothing may still be on its way into its shared memory
-    auto drain = [&]() {
-        cp_async_wait_all();
-        if constexpr (kBulk) {
-            if (tile < P.ntiles && !words_here && nke > 0) { mbar_wait(&sbar, 0); words_here = true; }
-        }
-    };
+    auto drain = [&]() { cp_async_wait_all(); };
     bool alpha_pending = false;
     LanczosCtl st_cols;
     if constexpr (MODE == kRowsLanczos) {
@@ -645,22 +569,17 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const __grid_co
             }
         } else {
             st = *P.ctl_in;
-            // bulk variant: the words are (almost) here, the control block is on its way -- the gathers go out now, from
-            // w' (the source unless the recurrence breaks down, which the `redo` branch below repairs), instead of behind
-            // the round trip of the control block
-            if constexpr (kBulk) {
-                if (P.advance_here && !gathered) { gather_from(P.wp); gathered = true; }
-            }
             if (st.done) {
                 drain();                                       // nothing may still be on its way into this CTA's shared memory
                 if (scribe && P.ctl != P.ctl_in) *P.ctl = st;      // keep the pair in step
-                leave();
                 return;
             }
             if (P.advance_here) {
                 // beta = |w'| of the column sweep before us is still in pieces.  While they travel, gather from w'
                 // -- the source unless the recurrence breaks down right now, which the sum will tell
+                KTRACE(10);                                    // control block has arrived
                 if (!gathered) { gather_from(P.wp); gathered = true; }
+                KTRACE(11);                                    // index words have arrived, gathers are out
                 double bsq, unused;
                 defer_end<kAsyncGather>(false, P.prev_count, P.prev_nlong, spieces, sred, bsq, unused);
                 lanczos_advance(&st, scribe ? P.bet : nullptr, sqrt(bsq));     // cubic.py:98-109, in registers
@@ -692,11 +611,8 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const __grid_co
             alpha_pending = true;
         }
         st_cols = *P.ctl_in;
-        if constexpr (kBulk) {                   // the source of the column pass (t) does not depend on the control block
-            gather_from(P.src);
-            gathered = true;
-        }
-        if (st_cols.done) { drain(); leave(); return; }
+        if (st_cols.done) { drain(); return; }
+        KTRACE(10);                                            // control block has arrived
         col = st_cols.col;
         if (P.defer) {
             if (st_cols.final_) {                              // cubic.py:109: the last alpha needs no further vector
@@ -710,7 +626,6 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const __grid_co
                     P.ctl->hvps = st_cols.hvps + 1;
                     P.ctl->done = 1;
                 }
-                leave();
                 return;
             }
         } else {
@@ -763,7 +678,6 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const __grid_co
         }
         KTRACE(4);                   // basis column stored, operands requested
         if (!gathered) gather_from(S.src);
-        if (P.early_trigger) pdl_trigger();      // split passes: the next kernel may come in and fetch its stream now
         if constexpr (MODE == kColsLanczos) {
             if (alpha_pending) {                 // the gathers above are in flight while the pieces are added
                 double s1, s2;
@@ -886,7 +800,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const __grid_co
             P.red_partials[tile] = mine;
             P.red_partials[((nblk + 1) & ~1u) + tile] = mine2;            // even stride: 16-byte copies later
         }
-        if (P.defer) { KTRACE(9); leave(); return; }
+        if (P.defer) { KTRACE(9); return; }
         if (tid == 0) {
             __threadfence();
             s_last = atomicInc(P.red_ticket, nblk - 1) == nblk - 1;
@@ -921,11 +835,11 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const __grid_co
     if constexpr (MODE == kColsLanczos) {
         // beta^2 = |w'|^2: threads -> tile (fixed order) -> tiles in tile order, by the next row sweep (deferred) or
         // by the last CTA here
-        if (!P.update_ctl) { leave(); return; }    // re-orthogonalisation follows: it recomputes the norm
+        if (!P.update_ctl) { return; }    // re-orthogonalisation follows: it recomputes the norm
         __syncthreads();
         const double mine = cta_sum_to_thread0(acc, sred);
         if (tid == 0) P.red_partials[tile] = mine;
-        if (P.defer) { KTRACE(9); leave(); return; }
+        if (P.defer) { KTRACE(9); return; }
         if (tid == 0) {
             __threadfence();
             s_last = atomicInc(P.red_ticket, nblk - 1) == nblk - 1;
@@ -942,52 +856,35 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const __grid_co
         }
     }
     KTRACE(9);                       // tail sums written
-    leave();
 }
 
 void fill_matrix(SweepParams &P, const SegMat &A) {
     P.ptr = A.ptr; P.idx = A.idx; P.val = A.val; P.gidx = A.gidx; P.gval = A.gval; P.tiles = A.tiles; P.ntiles = A.ntiles;
     P.longtab = A.longtab; P.segid = A.segid; P.partial = A.partial; P.longdot = A.longdot; P.ticket = A.ticket;
     P.nlong = A.nlong;
-    P.npdesc = (int)A.pdesc_host.size();
-    if (P.npdesc) memcpy(P.pdesc, A.pdesc_host.data(), sizeof(int2) * A.pdesc_host.size());
 }
 
 template <int MODE, int GATHER>
 int launch_variant(kcrn_problem *h, const SegMat &A, const SweepParams &P, int grid) {
     if (A.items == 11) KCRN_CUDA(launch_kernel(sweep_kernel<MODE, 11, GATHER>, dim3(grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
-    // (12 per thread + the word buffer of the bulk variant exceed the 48 KB of static shared memory: those tiles gather asynchronously)
-    else if (A.items == 12) KCRN_CUDA(launch_kernel(sweep_kernel<MODE, 12, GATHER == kGatherBulk ? kGatherAsync : GATHER>, dim3(grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
+    else if (A.items == 12) KCRN_CUDA(launch_kernel(sweep_kernel<MODE, 12, GATHER>, dim3(grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
     else KCRN_CUDA(launch_kernel(sweep_kernel<MODE, 8, GATHER>, dim3(grid), dim3(kSweepThreads), 0, h->stream, h->pdl, P));
     return KCRN_OK;
 }
 
 // The gather variant is a property of (matrix, class of pass): the Lanczos passes carry more state than the others
 template <int MODE>
-int launch(kcrn_problem *h, const SegMat &A, SweepParams &P, double *longdot = nullptr, bool split = false) {
+int launch(kcrn_problem *h, const SegMat &A, SweepParams &P, double *longdot = nullptr) {
     fill_matrix(P, A);
     if (longdot) P.longdot = longdot;      // the forward sweep keeps its long-segment shares apart from the Lanczos passes'
     const int variant = !A.gidx ? kGatherStored : (MODE == kRowsLanczos || MODE == kColsLanczos ? A.gather_lanczos : A.gather_plain);
     auto go = [&](int grid) -> int {
-        if (variant == kGatherBulk) KCRN_TRY((launch_variant<MODE, kGatherBulk>(h, A, P, grid)));
-        else if (variant == kGatherAsync) KCRN_TRY((launch_variant<MODE, kGatherAsync>(h, A, P, grid)));
+        if (variant == kGatherAsync) KCRN_TRY((launch_variant<MODE, kGatherAsync>(h, A, P, grid)));
         else if (variant == kGatherOrdered) KCRN_TRY((launch_variant<MODE, kGatherOrdered>(h, A, P, grid)));
         else KCRN_TRY((launch_variant<MODE, kGatherStored>(h, A, P, grid)));
         h->counters[0] += 1;
         return KCRN_OK;
     };
-    // A pass of at most one wave of tiles, inside a captured graph with programmatic edges: two half launches, the second
-    // out of phase with the first (SweepParams::tile0 ...), so that the NEXT pass's first half finds free slots -- and
-    // loads its tile stream -- while this pass's second half is still at work
-    const int half = (A.grid + 1) / 2;
-    if (split && h->pdl && A.grid >= 64 && half <= 2 * kNumSm) {
-        P.grid_total = A.grid;
-        P.early_trigger = 1;
-        P.tile0 = 0; P.late_wait = 0;
-        KCRN_TRY(go(half));
-        P.tile0 = half; P.late_wait = 1;
-        return go(A.grid - half);
-    }
     return go(A.grid);
 }
 
@@ -1017,11 +914,14 @@ int launch_forward(kcrn_problem *h, const double *x) {
 int launch_rows_weighted(kcrn_problem *h, const double *v) {
     SweepParams P{};
     P.src = v; P.D = h->D; P.out = h->t;
+#ifdef KCRN_SWEEP_TRACE
+    P.trace = h->sweep_trace; P.trace_slot = 20;      // the plain passes next to the Lanczos ones
+#endif
     h->counters[3] += 1;
     return launch<kRowsWeighted>(h, h->csr, P);
 }
 
-int gather_candidates_last() { return kGatherBulk; }
+int gather_candidates_last() { return kGatherAsync; }
 
 // Which gather variant serves the passes outside the Lanczos recurrence: measured per matrix on the weighted row
 // pass / the scaled column pass, a few back-to-back launches each (the operands are zeroed scratch; all variants
@@ -1121,7 +1021,7 @@ int launch_rows_lanczos(kcrn_problem *h, double *alpha_raw, int slot, int defer,
     P.trace = h->sweep_trace; P.trace_slot = 2 * slot;
 #endif
     h->counters[3] += 1;
-    return launch<kRowsLanczos>(h, h->csr, P, nullptr, defer == 2 && !h->sharded() && h->sw.split_passes);
+    return launch<kRowsLanczos>(h, h->csr, P);
 }
 
 int launch_cols_raw(kcrn_problem *h, const double *src, double *out) {
@@ -1136,6 +1036,9 @@ int launch_cols_scaled(kcrn_problem *h, const double *src, const double *u, doub
     P.src = src; P.out = out; P.u = u; P.n_samples = (double)h->n_global; P.inv_n = 1.0 / P.n_samples; P.l2 = h->l2;
     P.add_l2 = u != nullptr;
     P.red_partials = sq_part;              // pieces of |out|^2 per tile (+ csc.longdot), for the recurrence that follows
+#ifdef KCRN_SWEEP_TRACE
+    P.trace = h->sweep_trace; P.trace_slot = 21;
+#endif
     h->counters[4] += 1;
     return launch<kColsScaled>(h, h->csc, P);
 }
@@ -1155,7 +1058,7 @@ int launch_cols_lanczos(kcrn_problem *h, int update_ctl, int slot, int defer) {
     P.trace = h->sweep_trace; P.trace_slot = 2 * slot + 1;
 #endif
     h->counters[4] += 1;
-    return launch<kColsLanczos>(h, h->csc, P, nullptr, defer == 2 && update_ctl && !h->sharded() && h->sw.split_passes);
+    return launch<kColsLanczos>(h, h->csc, P);
 }
 
 int launch_derive_from_Ax(kcrn_problem *h) {
