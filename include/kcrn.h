@@ -202,7 +202,8 @@ int kcrn_counters(kcrn_handle h, int64_t *counters8_host, int reset);
 /* timing probe used by bench.py's roofline leg: about `reps` back-to-back launches of one sweep kernel (which = 0:
  * CSR pass of the HVP, 1: CSC pass of the HVP), launched the way the product launches it -- nodes of a captured
  * graph joined by programmatic edges, 20 per graph -- between two CUDA events on the handle's stream; returns the
- * mean duration per launch in microseconds. */
+ * mean duration per launch in microseconds.  which = 2: the two passes alternating (= plain HVPs, 10 per graph; still the
+ * mean per launch). */
 int kcrn_time_sweep(kcrn_handle h, int which, int reps, double *mean_us_host);
 /* Host-only (no device needed): the tile list the sweeps would use for a matrix with this pointer array (rows of the
  * CSR copy / columns of the CSC copy) -- no reference counterpart; lets the CPU test suite check the tiling

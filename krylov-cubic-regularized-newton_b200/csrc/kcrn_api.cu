@@ -532,6 +532,42 @@ static void print_sweep_trace(kcrn_problem *h) {
             if (sl < 20) fprintf(stderr, "kcrn:     since predecessor complete: control block read %6.0f ns, index words here + gathers out %6.0f ns\n", extra[0] / cnt, extra[1] / cnt);
         }
         prev_end = t9max;
+        if (sl == 6 || sl == 7 || sl >= 20) {
+            // who is late: entry and end times of the CTAs relative to the first entry, and the slowest tiles
+            const SegMat &A = sl % 2 == 0 ? h->csr : h->csc;
+            std::vector<int4> tiles((size_t)A.ntiles);
+            if (cudaMemcpy(tiles.data(), A.tiles, sizeof(int4) * tiles.size(), cudaMemcpyDeviceToHost) != cudaSuccess) continue;
+            std::vector<std::pair<double, int>> ends, starts;
+            for (int c = 0; c < grid && c < 1024; ++c) {
+                const unsigned long long *t = T.data() + ((size_t)sl * 1024 + c) * 12;
+                if (t[0] == 0 || t[9] == 0) continue;
+                ends.push_back({(double)(t[9] - t0min), c});
+                starts.push_back({(double)(t[0] - t0min), c});
+            }
+            std::sort(ends.begin(), ends.end()); std::sort(starts.begin(), starts.end());
+            auto pct = [](const std::vector<std::pair<double, int>> &v, double q) { return v[(size_t)(q * (v.size() - 1))].first; };
+            fprintf(stderr, "kcrn:     CTA entry  p10 %5.0f p50 %5.0f p90 %5.0f p99 %5.0f max %5.0f ns after the first\n", pct(starts, .1), pct(starts, .5), pct(starts, .9), pct(starts, .99), pct(starts, 1));
+            fprintf(stderr, "kcrn:     CTA end    p10 %5.0f p50 %5.0f p90 %5.0f p99 %5.0f max %5.0f ns after the first entry\n", pct(ends, .1), pct(ends, .5), pct(ends, .9), pct(ends, .99), pct(ends, 1));
+            for (size_t k = ends.size() >= 8 ? ends.size() - 8 : 0; k < ends.size(); ++k) {
+                const int c = ends[k].second;
+                const unsigned long long *t = T.data() + ((size_t)sl * 1024 + c) * 12;
+                const int4 td = c < A.ntiles ? tiles[c] : make_int4(0, 0, 0, 0);
+                fprintf(stderr, "kcrn:       late tile %4d (segments %5d, entries %5d, tag %2d) entry %5.0f end %5.0f | phases", c, td.z, td.w & 0xffff, td.w >> 16,
+                        (double)(t[0] - t0min), ends[k].first);
+                for (int q = 0; q < 9; ++q) fprintf(stderr, " %5.0f", t[q + 1] >= t[q] && t[q] ? (double)(t[q + 1] - t[q]) : 0.0);
+                fprintf(stderr, "\n");
+            }
+            // the same for a typical tile (median end)
+            {
+                const int c = ends[ends.size() / 2].second;
+                const unsigned long long *t = T.data() + ((size_t)sl * 1024 + c) * 12;
+                const int4 td = c < A.ntiles ? tiles[c] : make_int4(0, 0, 0, 0);
+                fprintf(stderr, "kcrn:       median tile %4d (segments %5d, entries %5d, tag %2d) entry %5.0f end %5.0f | phases", c, td.z, td.w & 0xffff, td.w >> 16,
+                        (double)(t[0] - t0min), ends[ends.size() / 2].first);
+                for (int q = 0; q < 9; ++q) fprintf(stderr, " %5.0f", t[q + 1] >= t[q] && t[q] ? (double)(t[q + 1] - t[q]) : 0.0);
+                fprintf(stderr, "\n");
+            }
+        }
     }
 }
 #endif
@@ -1078,7 +1114,8 @@ int kcrn_time_sweep(kcrn_handle h, int which, int reps, double *mean_us_host) {
     cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed);
     int rc = KCRN_OK;
     for (int i = 0; i < kBurst && e == cudaSuccess && rc == KCRN_OK; ++i)
-        rc = which == 0 ? launch_rows_weighted(h, h->x_cur) : launch_cols_scaled(h, h->t, nullptr, h->o_stage);
+        rc = which == 0 || (which == 2 && i % 2 == 0) ? launch_rows_weighted(h, h->x_cur)      // which == 2: alternating, = plain HVPs
+                                                      : launch_cols_scaled(h, h->t, nullptr, h->o_stage);
     cudaError_t e2 = cudaStreamEndCapture(cap, &graph);
     h->stream = user;
     h->pdl = false;
@@ -1106,7 +1143,8 @@ int kcrn_time_sweep(kcrn_handle h, int which, int reps, double *mean_us_host) {
     cudaEventDestroy(e1);
     cudaGraphExecDestroy(exec);
     h->counters[0] += (int64_t)(bursts + 1) * kBurst;
-    h->counters[which == 0 ? 3 : 4] += (int64_t)(bursts + 1) * kBurst;
+    if (which == 2) { h->counters[3] += (int64_t)(bursts + 1) * kBurst / 2; h->counters[4] += (int64_t)(bursts + 1) * kBurst / 2; }
+    else h->counters[which == 0 ? 3 : 4] += (int64_t)(bursts + 1) * kBurst;
     h->counters[1] += bursts + 1;
     *mean_us_host = (double)ms * 1000.0 / ((double)bursts * kBurst);
     return KCRN_OK;

@@ -455,9 +455,29 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    // The CTAs' shares are added in CTA order (fixed order = fixed bits).  The additions are a dependent chain, the loads
+    // are not: 32 of them are in flight per thread.  (One load per addition made this tail the largest part of a
+    // re-orthogonalisation step: ~1 300 CTAs x an L2 round trip each at d = 1.36 M.)
     for (int i = threadIdx.x; i < nv; i += blockDim.x) {
         double tot = 0.0;
-        for (int b = 0; b < (int)gridDim.x; ++b) tot += __ldcg(P.red_partials + (size_t)b * nv + i);
+        const double *p = P.red_partials + i;
+        const int G = (int)gridDim.x;
+        int b = 0;
+        for (; b + 32 <= G; b += 32) {
+            double v[32];
+#pragma unroll
+            for (int u = 0; u < 32; ++u) v[u] = __ldcg(p + (size_t)(b + u) * nv);
+#pragma unroll
+            for (int u = 0; u < 32; ++u) tot += v[u];
+        }
+        for (; b + 4 <= G; b += 4) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldcg(p + (size_t)(b + u) * nv);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) tot += v[u];
+        }
+        for (; b < G; ++b) tot += __ldcg(p + (size_t)b * nv);
         P.coef_out[i] = tot;
     }
 }

@@ -12,6 +12,11 @@ for name in sys.argv[1:] or ["rcv1"]:
     eng.set_x(torch.as_tensor(P.x0, device="cuda"))
     eng.gradient(keep_internal=True)
     us = [min(eng.time_sweep(w, 200) for _ in range(3)) for w in (0, 1)]
+    try:
+        alt = min(eng.time_sweep(2, 200) for _ in range(3))
+        print(f"   plain passes alternating (rows, cols, rows, ...): {alt:6.2f} us per pass, {2 * alt:6.2f} per plain HVP; each pass repeated on its own: {us[0] + us[1]:6.2f}")
+    except Exception as e:
+        print("   alternating passes: not in this build", str(e)[:60])
     for _ in range(5):
         eng.lanczos(10, False)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
