@@ -62,18 +62,6 @@
 #define KTRACE(k)
 #endif
 
-// 1: the Lanczos passes request the tile's values right behind its gathers; 2: only at the fixed place in front of the
-// multiply; 0: at kernel entry with the index words (A/B builds: profiles/microbench/build_variants.sh)
-// timing probes only (wrong results; profiles/microbench/build_variants.sh -DKCRN_KO=bits): what each Lanczos-specific part
-// of the two recurrence passes costs -- 1: no deferred sums (beta / alpha taken as 1 / 0.5), 2: no basis column store,
-// 4: no division of the gathered values by beta, 8: control block not read (fixed state)
-#ifndef KCRN_KO
-#define KCRN_KO 0
-#endif
-#ifndef KCRN_LATE_VALUES
-#define KCRN_LATE_VALUES 1
-#endif
-
 namespace kcrn {
 
 // How the gathered values of a tile travel (template parameter GATHER of the sweep kernel; all three give the same
@@ -470,13 +458,6 @@ template <int MODE, int kItems, int GATHER>
 __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepParams P) {
     constexpr int kTileNnz = kItems * kSweepThreads;       // non-zeros per CTA tile, kItems per thread
     constexpr bool ordered = GATHER != kGatherStored, kAsyncGather = GATHER == kGatherAsync;
-    // The Lanczos passes ask for the tile's VALUES only once its gathers are out.  Requested at kernel entry like the
-    // index words, the 2 * kItems registers they land in are spilled right away (these passes carry the control block,
-    // a deferred sum and the recurrence state through the same 64 registers), and a spill store of a register that a load
-    // is still filling waits for that load: the whole stream had to arrive before the control block was even read
-    // (SASS of round 2's sweep_kernel<2, 11, 1>: LDG.64 R16 ... STL.64 [R1+0x10], R16 in front of everything else).
-    // The index words -- a third of the stream -- are all the gathers need; the values travel while the gathers fly.
-    constexpr bool kLateValues = KCRN_LATE_VALUES && (MODE == kRowsLanczos || MODE == kColsLanczos);
     __shared__ __align__(16) double sprod[kTileNnz];       // products of the tile (16-byte aligned: the deferred sums' pieces arrive by 16-byte cp.async)
     __shared__ __align__(16) double ssum[kAsyncGather ? kSumCapAsync : kTileSegs];   // per-segment sums of the tile
     double *const spieces = kAsyncGather ? ssum : sprod;   // staging of the deferred sums' pieces (the product buffer is
@@ -518,12 +499,10 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
             const int i = r * kSweepThreads + tid;
             ci[r] = i < nk0 ? ld_stream(ip + i) : -1;
         }
-        if constexpr (!kLateValues) {
 #pragma unroll
-            for (int r = 0; r < kItems; ++r) {
-                const int i = r * kSweepThreads + tid;
-                av[r] = i < nk0 ? ld_stream(vp + i) : 0.0;
-            }
+        for (int r = 0; r < kItems; ++r) {
+            const int i = r * kSweepThreads + tid;
+            av[r] = i < nk0 ? ld_stream(vp + i) : 0.0;
         }
 #endif
     }
@@ -560,22 +539,6 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         }
         if constexpr (kAsyncGather) cp_async_commit();
     };
-    // the tile's values, right behind its gathers (kLateValues)
-    bool have_values = !kLateValues;
-    auto load_values = [&]() {
-        if constexpr (kLateValues) {
-            if (!have_values && tile < P.ntiles) {
-                const int k0s = td.y, nk0 = td.w & 0xffff;
-                const double *vp = (ordered && !kAsyncGather ? P.gval : P.val) + k0s;
-#pragma unroll
-                for (int r = 0; r < kItems; ++r) {
-                    const int i = r * kSweepThreads + tid;
-                    av[r] = i < nk0 ? ld_stream(vp + i) : 0.0;
-                }
-            }
-            have_values = true;
-        }
-    };
     // before a CTA leaves early nothing may still be on its way into its shared memory
     auto drain = [&]() { cp_async_wait_all(); };
     bool alpha_pending = false;
@@ -585,7 +548,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         // Requests that do not depend on the control block go first: the pieces of the sum this kernel has to finish
         // (beta = |w'| of the column sweep before us, or |g| of the gradient sweep).  (Starting the gathers here as
         // well, speculatively from the vector the host knows, was measured: no gain, profiles/r2g_ab.txt.)
-        const bool pieces = (P.advance_here || P.init_here) && !(KCRN_KO & 1);
+        const bool pieces = P.advance_here || P.init_here;
         if (pieces) {
             defer_begin(P.prev_part, false, P.prev_count, P.prev_longdot, P.prev_nlong, spieces);
             if constexpr (kAsyncGather) cp_async_commit();
@@ -594,9 +557,8 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         if (P.init_here) {
             // a fresh recurrence (what lanczos_init_kernel does): bet[0] = |g|, everything else reset
             if (!gathered) { gather_from(P.g); gathered = true; }
-            if (KCRN_LATE_VALUES == 1) load_values();
-            double gsq = 1.0, unused;
-            if (!(KCRN_KO & 1)) defer_end<kAsyncGather>(false, P.prev_count, P.prev_nlong, spieces, sred, gsq, unused);
+            double gsq, unused;
+            defer_end<kAsyncGather>(false, P.prev_count, P.prev_nlong, spieces, sred, gsq, unused);
             const double gn = sqrt(gsq);
             st.col = 0; st.redo = 0; st.final_ = (P.m_init == 1); st.done = 0; st.m_eff = P.m_init; st.nvalid = 1;
             st.store_idx = P.m_init - 1; st.m = P.m_init; st.broke = 0; st.hvps = 0; st.last_beta = 0.0;
@@ -606,10 +568,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
                 if (tid == 0) P.bet[0] = gn;
             }
         } else {
-            if (KCRN_KO & 8) {
-                st.col = 1; st.redo = 0; st.final_ = 0; st.done = 0; st.m_eff = 10; st.nvalid = 2; st.store_idx = 9; st.m = 10; st.broke = 0;
-                st.hvps = 0; st.last_beta = 1.0; st.cur_beta = 1.0; st.cur_alpha = 0.5;
-            } else st = *P.ctl_in;
+            st = *P.ctl_in;
             if (st.done) {
                 drain();                                       // nothing may still be on its way into this CTA's shared memory
                 if (scribe && P.ctl != P.ctl_in) *P.ctl = st;      // keep the pair in step
@@ -620,11 +579,10 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
                 // -- the source unless the recurrence breaks down right now, which the sum will tell
                 KTRACE(10);                                    // control block has arrived
                 if (!gathered) { gather_from(P.wp); gathered = true; }
-                if (KCRN_LATE_VALUES == 1) load_values();
                 KTRACE(11);                                    // index words have arrived, gathers are out
-                double bsq = 1.0, unused;
-                if (!(KCRN_KO & 1)) defer_end<kAsyncGather>(false, P.prev_count, P.prev_nlong, spieces, sred, bsq, unused);
-                if (!(KCRN_KO & 8)) lanczos_advance(&st, scribe ? P.bet : nullptr, sqrt(bsq));     // cubic.py:98-109, in registers
+                double bsq, unused;
+                defer_end<kAsyncGather>(false, P.prev_count, P.prev_nlong, spieces, sred, bsq, unused);
+                lanczos_advance(&st, scribe ? P.bet : nullptr, sqrt(bsq));     // cubic.py:98-109, in registers
             }
             if (st.redo && gathered) {                         // breakdown: the operator is re-applied to V[col]
                 gathered = false;
@@ -647,22 +605,19 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
     if constexpr (MODE == kColsLanczos) {
         // first what does not depend on the control block: the pieces of alpha = v'Hv the row sweep before us left (needed
         // by the epilogue only)
-        if (P.defer && !(KCRN_KO & 1)) {
+        if (P.defer) {
             defer_begin(P.prev_part, true, P.prev_count, P.prev_longdot, P.prev_nlong, spieces);
             if constexpr (kAsyncGather) cp_async_commit();
             alpha_pending = true;
         }
-        if (KCRN_KO & 8) {
-            st_cols.col = 1; st_cols.redo = 0; st_cols.final_ = 0; st_cols.done = 0; st_cols.m_eff = 10; st_cols.nvalid = 2; st_cols.store_idx = 9;
-            st_cols.m = 10; st_cols.broke = 0; st_cols.hvps = 0; st_cols.last_beta = 1.0; st_cols.cur_beta = 1.0; st_cols.cur_alpha = 0.5;
-        } else st_cols = *P.ctl_in;
+        st_cols = *P.ctl_in;
         if (st_cols.done) { drain(); return; }
         KTRACE(10);                                            // control block has arrived
         col = st_cols.col;
         if (P.defer) {
             if (st_cols.final_) {                              // cubic.py:109: the last alpha needs no further vector
-                double s1 = 1.0, s2 = 1.0;
-                if (!(KCRN_KO & 1)) defer_end<false>(true, P.prev_count, P.prev_nlong, spieces, sred, s1, s2);      // waits for everything in flight
+                double s1, s2;
+                defer_end<false>(true, P.prev_count, P.prev_nlong, spieces, sred, s1, s2);      // waits for everything in flight
                 drain();
                 if (tile == 0 && tid == 0) {
                     const double alpha = __dadd_rn(quotient(s1, P.n_samples, P.inv_n), __dmul_rn(P.l2, s2));
@@ -690,7 +645,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
     if constexpr (MODE == kRowsLanczos) {
         // side job, issued before the tile so that its loads overlap the gathers: store the normalised vector as
         // basis column `col` (the sweep itself divides on the fly); |v|^2 for the l2 part of alpha
-        if ((!redo || P.l2 != 0.0) && !(KCRN_KO & 2)) {
+        if (!redo || P.l2 != 0.0) {
             double *vout = P.V + (size_t)col * P.d;
             for (int64_t c = (int64_t)tile * blockDim.x + tid; c < P.d; c += (int64_t)nblk * blockDim.x) {
                 const double vc = quotient(__ldg(S.src + c), S.beta, S.rinv);
@@ -723,7 +678,6 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
         }
         KTRACE(4);                   // basis column stored, operands requested
         if (!gathered) gather_from(S.src);
-        load_values();
         if constexpr (MODE == kColsLanczos) {
             if (alpha_pending) {                 // the gathers above are in flight while the pieces are added
                 double s1, s2;
@@ -750,7 +704,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_kernel(const SweepPara
 #pragma unroll
         for (int r = 0; r < kItems; ++r) {
             double x = xv[r];
-            if constexpr (MODE == kRowsLanczos && !(KCRN_KO & 4)) x = quotient(x, S.beta, S.rinv);      // beta = 1 when re-applying
+            if constexpr (MODE == kRowsLanczos) x = quotient(x, S.beta, S.rinv);      // beta = 1 when re-applying
             p[r] = av[r] * x;
         }
         if (!stream) {
