@@ -35,6 +35,8 @@ Switches read_switches() {
     w.persist_trace = on("KCRN_PERSIST_TRACE");
     w.persist_flags = num("KCRN_PERSIST_FLAGS");
     if (getenv("KCRN_DSHARD")) w.dshard = num("KCRN_DSHARD") != 0 ? 1 : 0;
+    w.no_reorth_reg = on("KCRN_NO_REORTH_REG");
+    w.force_reorth_reg = on("KCRN_REORTH_REG");
     return w;
 }
 
@@ -157,7 +159,7 @@ int enqueue_lanczos(kcrn_problem *h, int m, int reorth, bool allow_persist = tru
         } else if (slot + 1 < m) {
             KCRN_TRY(launch_cols_lanczos(h, reorth ? 0 : 1, slot, defer));
         }
-        if (reorth && slot + 1 < m) KCRN_TRY(launch_lanczos_update(h, 1, 1));
+        if (reorth && slot + 1 < m) KCRN_TRY(launch_lanczos_update(h, 1, 1, slot + 1));
     }
     // row-sharded deferral: the last epilogue kernel has finished the last alpha; only the state moves to ctl[0]
     return launch_lanczos_finish(h, m, defer == 2 && h->sharded() ? 3 : defer);

@@ -61,6 +61,8 @@ struct Switches {
     bool persist = false, persist_trace = false;  // KCRN_PERSIST, KCRN_PERSIST_TRACE: one-kernel recurrence (opt-in)
     int persist_flags = 0;                        // KCRN_PERSIST_FLAGS: its measured experiments
     int dshard = -1;                              // KCRN_DSHARD=1 / 0: d-sharded re-orthogonalisation on / off (-1: by size)
+    bool no_reorth_reg = false;                   // KCRN_NO_REORTH_REG: re-orthogonalisation stages 1, 2 by the general kernel (A/B)
+    bool force_reorth_reg = false;                // KCRN_REORTH_REG: ... by the register kernel whatever d is (tests)
 };
 Switches read_switches();
 
@@ -332,7 +334,7 @@ int gather_candidates_last();                            // last variant the tun
 int lanczos_alloc(kcrn_problem *h, int m);
 int launch_lanczos_init(kcrn_problem *h, int m);      // ctl, alphas, bet reset; bet[0] = |g|
 int launch_lanczos_post(kcrn_problem *h, const double *hv_or_raw, int raw);  // epilogue after allreduce / generic feed
-int launch_lanczos_update(kcrn_problem *h, int reorth, int fused);
+int launch_lanczos_update(kcrn_problem *h, int reorth, int fused, int max_cols = 0);
 int launch_lanczos_post_sharded(kcrn_problem *h, const double *y_allreduced, int reorth, int slot = -1);   // slot >= 0: deferred sums
 int values_batch(kcrn_problem *h, const double *X, int k, double *out);
 int launch_run_init(kcrn_problem *h);

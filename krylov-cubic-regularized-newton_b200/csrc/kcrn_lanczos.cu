@@ -335,6 +335,44 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_post_sharded_kernel(VecPa
     }
 }
 
+// The per-warp shares of the nv dots of a CTA -> the CTA's shares, stored column by column ([column][CTA]) for
+// dots_reduce_kernel.  (Until the last session of round 2 the CTA that arrived last added all shares itself: at
+// d = 1.36 M that is 1 324 CTAs x nv values walked by nv threads of ONE CTA -- ~28 us per launch whatever nv is, a quarter
+// of the re-orthogonalisation at the news20 shape, profiles/r3d_c3_reorth_launches.csv.  One more small kernel with a CTA
+// per column costs ~2 us behind a programmatic edge.)  Called by all threads of the CTA after a barrier behind the last
+// write to sdots.
+template <int kWarps>
+__device__ __forceinline__ void finish_dots(const VecParams &P, int nv, const double (*sdots)[kMaxM]) {
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        double cta = 0.0;
+        for (int wv = 0; wv < kWarps; ++wv) cta += sdots[wv][i];
+        P.red_partials[(size_t)i * gridDim.x + blockIdx.x] = cta;
+    }
+}
+
+// coef_out[i] = sum over the G CTAs' shares of column i = blockIdx.x, in a fixed order (thread-strided, warp butterfly,
+// warps in order)
+__global__ void __launch_bounds__(kVecThreads) dots_reduce_kernel(VecParams P, int G) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ double sh[kVecThreads / 32];
+    if (P.ctl->done) return;
+    const int nv = P.ctl->col + 1, i = blockIdx.x;
+    if (i >= nv) return;
+    const double *p = P.red_partials + (size_t)i * G;
+    double t = 0.0;
+    for (int b = threadIdx.x; b < G; b += kVecThreads) t += __ldcg(p + b);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    t = warp_sum(t);
+    if (lane == 0) sh[warp] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < kVecThreads / 32; ++w) tot += sh[w];
+        P.coef_out[i] = tot;
+    }
+}
+
 // (Round 2 also measured stage 2 with the basis entries it fetches for w' -= V c kept in shared memory for the coefficients
 // V' w' that follow -- "staged through shared memory", bit-identical: 24.3 ms (72 KB per CTA) / 28.3 ms (184 KB) against
 // 19.8 ms per 50-step recurrence at the news20 shape, profiles/r2y_c3_reorth_staged.txt.  The second use already comes from
@@ -441,45 +479,107 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-        double cta = 0.0;
-        for (int wv = 0; wv < kVecThreads / 32; ++wv) cta += sdots[wv][i];
-        P.red_partials[(size_t)blockIdx.x * nv + i] = cta;
-        __threadfence();
+    finish_dots<kVecThreads / 32>(P, nv, sdots);
+}
+
+// Stages 1 and 2 with the basis entries of an element in REGISTERS (K6 where it is bandwidth-bound).  The general kernel
+// above walks the columns eight at a time, so stage 2 -- w' -= V c, then c2 = V' w' -- has to fetch every basis entry
+// twice: at d = 1.36 M the second fetch comes from HBM again (ncu launch list, profiles/r3c_c3_reorth_launches.csv: 207 us
+// for stage 2 against 96 us for stage 3 at 50 columns).  Here a thread owns ONE element at a time and keeps its (up to CAP)
+// basis entries in registers: all CAP loads are in flight at once, the update uses them, the dots use them again.  The
+// host knows an upper bound of the column count from the position of the step in the captured recurrence and picks CAP.
+// The 32 lanes' products of a column are added by recursive halving -- lane pairs exchange half of their columns per
+// step, (CAP - CAP / 32) value exchanges instead of 5 CAP -- in a fixed tree, and the per-warp sums accumulate over the
+// CTA's chunks in shared memory; per-CTA shares and the grid-wide sums as above.  w' gets the same bits as from the
+// general kernel (same order of the fused multiply-adds); the coefficients differ in the association of their sums.
+constexpr int kRegThreads = 128;
+
+// one halving step: the lane keeps the lower (bit clear) or upper (bit set) half of its N values, adds the partner's
+template <int N>
+__device__ __forceinline__ void halve(double (&p)[N], int lane, int bit) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k) {
+        const double keep = up ? p[k + N / 2] : p[k];
+        const double send = up ? p[k] : p[k + N / 2];
+        p[k] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+}
+
+template <int CAP, int E>
+__global__ void __launch_bounds__(kRegThreads, CAP >= 64 ? 3 : 4) lanczos_reorth_reg_kernel(VecParams P) {
+    static_assert(CAP == 16 || CAP == 32 || CAP == 64, "column capacity");
+    pdl_wait();
+    pdl_trigger();
+    __shared__ double sdots[kRegThreads / 32][kMaxM];       // only [.][0 .. CAP) is used (the tail's signature)
+    __shared__ double scoef[CAP];
+    if (P.ctl->done) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = P.ctl->col;
+    const int nv = col + 1;                                  // <= CAP: the host's bound
+    const bool update = P.stage == 2;
+    for (int i = threadIdx.x; i < CAP; i += kRegThreads) {
+        scoef[i] = (update && i < nv) ? P.coef_in[i] : 0.0;
+#pragma unroll
+        for (int wv = 0; wv < kRegThreads / 32; ++wv) sdots[wv][i] = 0.0;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = atomicInc(P.red_ticket, gridDim.x - 1) == gridDim.x - 1;
+    // where this lane's values end up after the halving steps
+    int mycol = 0;
+    {
+        int n = CAP;
+#pragma unroll
+        for (int bit = 16; bit >= 1; bit >>= 1)
+            if (n > 1) { n >>= 1; if (lane & bit) mycol += n; }
+    }
+    constexpr int kLeft = CAP >= 32 ? CAP / 32 : 1;          // values per lane after the five steps
+    const double alpha = P.ctl->cur_alpha;
+    const double *vcur = P.V + (size_t)col * P.d;
+    constexpr int kChunks = kVecThreads * E / kRegThreads;   // the CTA covers what a CTA of the general kernel covers
+    for (int q = 0; q < kChunks; ++q) {
+        const int64_t c = (int64_t)blockIdx.x * (kVecThreads * E) + (int64_t)q * kRegThreads + threadIdx.x;
+        const bool in = c >= P.lo && c < P.hi;
+        double vv[CAP];
+#pragma unroll
+        for (int i = 0; i < CAP; ++i) vv[i] = (in && i < nv) ? __ldg(P.V + (size_t)i * P.d + c) : 0.0;
+        double x = 0.0;
+        if (in) {
+            if (update || P.from_wp) x = P.wp[c];
+            else x = __dsub_rn(P.w_in[c], __dmul_rn(alpha, vcur[c]));
+        }
+        if (update) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int i = 0; i < CAP; ++i) sacc = fma(scoef[i], vv[i], sacc);     // zero coefficients beyond nv: exact no-ops
+            x -= sacc;
+        }
+        if (in && (update || !P.from_wp)) P.wp[c] = x;
+#pragma unroll
+        for (int i = 0; i < CAP; ++i) vv[i] *= x;
+        // sums over the 32 lanes, column by column
+        if constexpr (CAP >= 64) halve<CAP>(vv, lane, 16);
+        else halve<CAP>(vv, lane, 16);
+        {
+            double(&h1)[CAP / 2] = reinterpret_cast<double(&)[CAP / 2]>(vv);
+            halve<CAP / 2>(h1, lane, 8);
+            double(&h2)[CAP / 4] = reinterpret_cast<double(&)[CAP / 4]>(vv);
+            halve<CAP / 4>(h2, lane, 4);
+            double(&h3)[CAP / 8] = reinterpret_cast<double(&)[CAP / 8]>(vv);
+            halve<CAP / 8>(h3, lane, 2);
+            if constexpr (CAP >= 32) {
+                double(&h4)[CAP / 16] = reinterpret_cast<double(&)[CAP / 16]>(vv);
+                halve<CAP / 16>(h4, lane, 1);
+            } else {
+                vv[0] += __shfl_xor_sync(0xffffffffu, vv[0], 1);
+            }
+        }
+        if (CAP >= 32 || (lane & 1) == 0) {
+#pragma unroll
+            for (int k = 0; k < kLeft; ++k) sdots[warp][mycol + k] += vv[k];
+        }
     }
     __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    // The CTAs' shares are added in CTA order (fixed order = fixed bits).  The additions are a dependent chain, the loads
-    // are not: 32 of them are in flight per thread.  (One load per addition made this tail the largest part of a
-    // re-orthogonalisation step: ~1 300 CTAs x an L2 round trip each at d = 1.36 M.)
-    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-        double tot = 0.0;
-        const double *p = P.red_partials + i;
-        const int G = (int)gridDim.x;
-        int b = 0;
-        for (; b + 32 <= G; b += 32) {
-            double v[32];
-#pragma unroll
-            for (int u = 0; u < 32; ++u) v[u] = __ldcg(p + (size_t)(b + u) * nv);
-#pragma unroll
-            for (int u = 0; u < 32; ++u) tot += v[u];
-        }
-        for (; b + 4 <= G; b += 4) {
-            double v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = __ldcg(p + (size_t)(b + u) * nv);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) tot += v[u];
-        }
-        for (; b < G; ++b) tot += __ldcg(p + (size_t)b * nv);
-        P.coef_out[i] = tot;
-    }
+    finish_dots<kRegThreads / 32>(P, nv, sdots);
 }
 
 // d-sharded re-orthogonalisation: |w'|^2 has been summed over the ranks -- the bookkeeping of cubic.py:98-109
@@ -814,7 +914,8 @@ int launch_lanczos_post_peer(kcrn_problem *h, const double *y_partial, int reort
 
 // reorth = 0: stage 0 (w' = w - alpha v, beta) -- the step-wise API; reorth = 1: the three Gram-Schmidt stages;
 // fused = 1: w' already holds w - alpha v (formed by the column sweep / the sharded post kernel)
-int launch_lanczos_update(kcrn_problem *h, int reorth, int fused) {
+// max_cols: what the host knows about the number of basis columns at this step (0: nothing)
+int launch_lanczos_update(kcrn_problem *h, int reorth, int fused, int max_cols) {
     const int first = reorth ? 1 : 0, last = reorth ? 3 : 0;
     // d-sharded re-orthogonalisation (row-sharded runs with a large basis): every rank orthogonalises its slice of d
     // against the same slice of V -- 1/world of the basis traffic -- and three small sums over the ranks (the
@@ -833,9 +934,28 @@ int launch_lanczos_update(kcrn_problem *h, int reorth, int fused) {
         P.coef_out = stage == 1 ? h->coef : h->coef2;
         P.red_ticket = h->red_ticket + 1;
         P.lo = lo; P.hi = hi; P.sliced = sliced ? 1 : 0;
-        if (h->vec_elems == 4) KCRN_CUDA(launch_kernel(lanczos_update_kernel<4>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
-        else KCRN_CUDA(launch_kernel(lanczos_update_kernel<1>, dim3(h->vec_grid), dim3(kVecThreads), 0, h->stream, h->pdl, P));
+        // stages 1 and 2 of a step with few enough columns: basis entries in registers, every entry fetched once
+        // (large d only: at d = 47 k the general kernel is the faster one, 109 vs 116 us per 10-step recurrence --
+        // profiles/r3e_reorth_time.txt; KCRN_REORTH_REG=1 forces the register kernel for the tests)
+        const bool reg = (stage == 1 || stage == 2) && max_cols > 0 && max_cols <= 64 && !h->sw.no_reorth_reg &&
+                         (h->vec_elems == 4 || h->sw.force_reorth_reg);
+        auto go = [&](auto kern, int threads) { return launch_kernel(kern, dim3(h->vec_grid), dim3(threads), 0, h->stream, h->pdl, P); };
+        if (reg && h->vec_elems == 4) {
+            if (max_cols <= 16) KCRN_CUDA(go(lanczos_reorth_reg_kernel<16, 4>, kRegThreads));
+            else if (max_cols <= 32) KCRN_CUDA(go(lanczos_reorth_reg_kernel<32, 4>, kRegThreads));
+            else KCRN_CUDA(go(lanczos_reorth_reg_kernel<64, 4>, kRegThreads));
+        } else if (reg) {
+            if (max_cols <= 16) KCRN_CUDA(go(lanczos_reorth_reg_kernel<16, 1>, kRegThreads));
+            else if (max_cols <= 32) KCRN_CUDA(go(lanczos_reorth_reg_kernel<32, 1>, kRegThreads));
+            else KCRN_CUDA(go(lanczos_reorth_reg_kernel<64, 1>, kRegThreads));
+        } else if (h->vec_elems == 4) KCRN_CUDA(go(lanczos_update_kernel<4>, kVecThreads));
+        else KCRN_CUDA(go(lanczos_update_kernel<1>, kVecThreads));
         h->counters[0] += 1;
+        if (stage == 1 || stage == 2) {        // the CTAs' shares of the coefficients -> coef_out, one CTA per column
+            const int cols = max_cols > 0 ? max_cols : std::max(1, std::max(h->cur_m_enqueue, h->cur_m));
+            KCRN_CUDA(launch_kernel(dots_reduce_kernel, dim3(cols), dim3(kVecThreads), 0, h->stream, h->pdl, P, (int)h->vec_grid));
+            h->counters[0] += 1;
+        }
         if (sliced) {
             if (stage < 3) {
                 KCRN_TRY(nccl_allreduce_sum(h, P.coef_out, (h->cur_m_enqueue + 1) & ~1));

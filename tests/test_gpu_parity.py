@@ -179,13 +179,13 @@ def test_gather_variants_give_the_same_bits(torch, monkeypatch, name):
             assert torch.equal(a, b)
 
 
-def _lanczos_probe(tmp_path, tag, extra_env, name="small", reorth=0):
+def _lanczos_probe(tmp_path, tag, extra_env, name="small", reorth=0, m=6):
     import os, subprocess, sys
     here = os.path.dirname(os.path.abspath(__file__))
     e = {k: v for k, v in os.environ.items() if not k.startswith("KCRN_")}
     e.update(extra_env)
     out = str(tmp_path / f"probe_{tag}.npz")
-    subprocess.run([sys.executable, os.path.join(here, "lanczos_probe.py"), name, "6", str(int(reorth)), out], env=e, check=True,
+    subprocess.run([sys.executable, os.path.join(here, "lanczos_probe.py"), name, str(int(m)), str(int(reorth)), out], env=e, check=True,
                    timeout=600)
     with np.load(out) as z:
         return {k: z[k] for k in z.files}
@@ -209,6 +209,23 @@ def test_fused_lanczos_under_process_wide_switches(torch, tmp_path, lanczos_prob
     assert ref["info"][0] == got["info"][0] and ref["info"][3] == got["info"][3]      # m_eff, operator applications
     for k in ("value", "grad", "hvp", "V", "alphas", "bet"):
         assert np.allclose(ref[k], got[k], rtol=1e-10, atol=1e-12), k
+
+
+@pytest.mark.parametrize("name,m", [("small", 6), ("rcv1", 40)])
+def test_reorth_register_kernel_vs_general_kernel(torch, tmp_path, name, m):
+    # K6 stages 1 and 2 keep the basis entries of an element in registers (every entry fetched once) where the host knows
+    # that the columns fit; KCRN_NO_REORTH_REG=1 sends the same recurrence through the general kernel (eight columns at a
+    # time, entries fetched twice in stage 2).  w' is updated with the same fused multiply-adds in the same order; the
+    # coefficients are summed in a different association, so the re-orthogonalised recurrence agrees to rounding level
+    a = _lanczos_probe(tmp_path, "reg", {"KCRN_REORTH_REG": "1"}, name=name, reorth=1, m=m)   # m = 40: capacities 16, 32 and 64 in one run
+                                                                                               # (by default only large d takes this kernel)
+    b = _lanczos_probe(tmp_path, "general", {"KCRN_NO_REORTH_REG": "1"}, name=name, reorth=1, m=m)
+    assert a["info"][0] == b["info"][0] and a["info"][3] == b["info"][3]
+    m = int(a["info"][0])
+    assert rel_err(a["alphas"][:m], b["alphas"][:m]) <= 1e-11 and rel_err(a["bet"][:m], b["bet"][:m]) <= 1e-11
+    assert np.allclose(a["V"], b["V"], rtol=0, atol=1e-10)
+    G = a["V"][:m] @ a["V"][:m].T
+    assert np.abs(G - np.eye(m)).max() <= 1e-13            # what the re-orthogonalisation is for
 
 
 def test_sharded_code_path_on_one_gpu(torch, tmp_path, lanczos_probe_default):
