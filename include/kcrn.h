@@ -205,6 +205,11 @@ int kcrn_counters(kcrn_handle h, int64_t *counters8_host, int reset);
  * mean duration per launch in microseconds.  which = 2: the two passes alternating (= plain HVPs, 10 per graph; still the
  * mean per launch). */
 int kcrn_time_sweep(kcrn_handle h, int which, int reps, double *mean_us_host);
+/* Benchmark utility (no reference counterpart): evict everything from L2 -- a buffer of `bytes` (choose > 126 MB) is
+ * written on the handle's stream, a second one of the same size is read (the first one's dirty lines leave L2 as well),
+ * both are freed; returns when that is done.  A write-only flush, or a flush buffer that stays allocated, slows an
+ * L2-resident working set down for good (profiles/r3g_flush_probe.txt, r3h_flush_probe2.txt). */
+int kcrn_flush_l2(kcrn_handle h, size_t bytes);
 /* Host-only (no device needed): the tile list the sweeps would use for a matrix with this pointer array (rows of the
  * CSR copy / columns of the CSC copy) -- no reference counterpart; lets the CPU test suite check the tiling
  * invariants.  tiles4[i] = {first segment, first entry, z, entries | tag << 16}: z > 0 whole segments (tag 15: one

@@ -488,9 +488,9 @@ __global__ void __launch_bounds__(kVecThreads) lanczos_update_kernel(VecParams P
 // for stage 2 against 96 us for stage 3 at 50 columns).  Here a thread owns ONE element at a time and keeps its (up to CAP)
 // basis entries in registers: all CAP loads are in flight at once, the update uses them, the dots use them again.  The
 // host knows an upper bound of the column count from the position of the step in the captured recurrence and picks CAP.
-// The 32 lanes' products of a column are added by recursive halving -- lane pairs exchange half of their columns per
-// step, (CAP - CAP / 32) value exchanges instead of 5 CAP -- in a fixed tree, and the per-warp sums accumulate over the
-// CTA's chunks in shared memory; per-CTA shares and the grid-wide sums as above.  w' gets the same bits as from the
+// The 32 lanes' products of a column are added by recursive halving, eight columns at a time -- lane pairs exchange half
+// of their columns per step: 7 + 2 value exchanges per eight columns instead of 40 -- in a fixed tree, and the per-warp
+// sums accumulate over the CTA's chunks in shared memory; per-CTA shares and the grid-wide sums as above.  w' gets the same bits as from the
 // general kernel (same order of the fused multiply-adds); the coefficients differ in the association of their sums.
 constexpr int kRegThreads = 128;
 
@@ -507,8 +507,8 @@ __device__ __forceinline__ void halve(double (&p)[N], int lane, int bit) {
 }
 
 template <int CAP, int E>
-__global__ void __launch_bounds__(kRegThreads, CAP >= 64 ? 3 : 4) lanczos_reorth_reg_kernel(VecParams P) {
-    static_assert(CAP == 16 || CAP == 32 || CAP == 64, "column capacity");
+__global__ void __launch_bounds__(kRegThreads, CAP > 32 ? 3 : 4) lanczos_reorth_reg_kernel(VecParams P) {
+    static_assert(CAP % 8 == 0 && CAP >= 8 && CAP <= 64, "column capacity");
     pdl_wait();
     pdl_trigger();
     __shared__ double sdots[kRegThreads / 32][kMaxM];       // only [.][0 .. CAP) is used (the tail's signature)
@@ -524,15 +524,9 @@ __global__ void __launch_bounds__(kRegThreads, CAP >= 64 ? 3 : 4) lanczos_reorth
         for (int wv = 0; wv < kRegThreads / 32; ++wv) sdots[wv][i] = 0.0;
     }
     __syncthreads();
-    // where this lane's values end up after the halving steps
-    int mycol = 0;
-    {
-        int n = CAP;
-#pragma unroll
-        for (int bit = 16; bit >= 1; bit >>= 1)
-            if (n > 1) { n >>= 1; if (lane & bit) mycol += n; }
-    }
-    constexpr int kLeft = CAP >= 32 ? CAP / 32 : 1;          // values per lane after the five steps
+    // columns are reduced in groups of eight: three halving steps leave lane l with column 4 b4 + 2 b3 + b2 of the group
+    // (b = bits of l), two butterflies finish it; the lanes with b1 = b0 = 0 keep the sums
+    const int gcol = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
     const double alpha = P.ctl->cur_alpha;
     const double *vcur = P.V + (size_t)col * P.d;
     constexpr int kChunks = kVecThreads * E / kRegThreads;   // the CTA covers what a CTA of the general kernel covers
@@ -557,25 +551,18 @@ __global__ void __launch_bounds__(kRegThreads, CAP >= 64 ? 3 : 4) lanczos_reorth
 #pragma unroll
         for (int i = 0; i < CAP; ++i) vv[i] *= x;
         // sums over the 32 lanes, column by column
-        if constexpr (CAP >= 64) halve<CAP>(vv, lane, 16);
-        else halve<CAP>(vv, lane, 16);
-        {
-            double(&h1)[CAP / 2] = reinterpret_cast<double(&)[CAP / 2]>(vv);
-            halve<CAP / 2>(h1, lane, 8);
-            double(&h2)[CAP / 4] = reinterpret_cast<double(&)[CAP / 4]>(vv);
-            halve<CAP / 4>(h2, lane, 4);
-            double(&h3)[CAP / 8] = reinterpret_cast<double(&)[CAP / 8]>(vv);
-            halve<CAP / 8>(h3, lane, 2);
-            if constexpr (CAP >= 32) {
-                double(&h4)[CAP / 16] = reinterpret_cast<double(&)[CAP / 16]>(vv);
-                halve<CAP / 16>(h4, lane, 1);
-            } else {
-                vv[0] += __shfl_xor_sync(0xffffffffu, vv[0], 1);
-            }
-        }
-        if (CAP >= 32 || (lane & 1) == 0) {
 #pragma unroll
-            for (int k = 0; k < kLeft; ++k) sdots[warp][mycol + k] += vv[k];
+        for (int g = 0; g < CAP / 8; ++g) {
+            double(&p8)[8] = *reinterpret_cast<double(*)[8]>(&vv[8 * g]);
+            halve<8>(p8, lane, 16);
+            double(&p4)[4] = *reinterpret_cast<double(*)[4]>(&vv[8 * g]);
+            halve<4>(p4, lane, 8);
+            double(&p2)[2] = *reinterpret_cast<double(*)[2]>(&vv[8 * g]);
+            halve<2>(p2, lane, 4);
+            double t = vv[8 * g];
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+            if ((lane & 3) == 0) sdots[warp][8 * g + gcol] += t;
         }
     }
     __syncthreads();
@@ -940,14 +927,18 @@ int launch_lanczos_update(kcrn_problem *h, int reorth, int fused, int max_cols) 
         const bool reg = (stage == 1 || stage == 2) && max_cols > 0 && max_cols <= 64 && !h->sw.no_reorth_reg &&
                          (h->vec_elems == 4 || h->sw.force_reorth_reg);
         auto go = [&](auto kern, int threads) { return launch_kernel(kern, dim3(h->vec_grid), dim3(threads), 0, h->stream, h->pdl, P); };
-        if (reg && h->vec_elems == 4) {
-            if (max_cols <= 16) KCRN_CUDA(go(lanczos_reorth_reg_kernel<16, 4>, kRegThreads));
-            else if (max_cols <= 32) KCRN_CUDA(go(lanczos_reorth_reg_kernel<32, 4>, kRegThreads));
-            else KCRN_CUDA(go(lanczos_reorth_reg_kernel<64, 4>, kRegThreads));
-        } else if (reg) {
-            if (max_cols <= 16) KCRN_CUDA(go(lanczos_reorth_reg_kernel<16, 1>, kRegThreads));
-            else if (max_cols <= 32) KCRN_CUDA(go(lanczos_reorth_reg_kernel<32, 1>, kRegThreads));
-            else KCRN_CUDA(go(lanczos_reorth_reg_kernel<64, 1>, kRegThreads));
+        if (reg) {
+            const int cap = (max_cols + 7) / 8;            // capacity in groups of eight columns
+            cudaError_t e = cudaErrorInvalidValue;
+#define KCRN_REG_CASE(G)                                                                                              \
+    case G: e = h->vec_elems == 4 ? go(lanczos_reorth_reg_kernel<8 * G, 4>, kRegThreads) : go(lanczos_reorth_reg_kernel<8 * G, 1>, kRegThreads); break;
+            switch (cap) {
+                KCRN_REG_CASE(1) KCRN_REG_CASE(2) KCRN_REG_CASE(3) KCRN_REG_CASE(4)
+                KCRN_REG_CASE(5) KCRN_REG_CASE(6) KCRN_REG_CASE(7) KCRN_REG_CASE(8)
+                default: break;
+            }
+#undef KCRN_REG_CASE
+            KCRN_CUDA(e);
         } else if (h->vec_elems == 4) KCRN_CUDA(go(lanczos_update_kernel<4>, kVecThreads));
         else KCRN_CUDA(go(lanczos_update_kernel<1>, kVecThreads));
         h->counters[0] += 1;

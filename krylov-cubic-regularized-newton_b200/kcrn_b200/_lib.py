@@ -65,6 +65,7 @@ SIGNATURES = {
     "kcrn_update_Ax": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "kcrn_counters": (c_int, [c_void_p, POINTER(c_int64), c_int]),
     "kcrn_time_sweep": (c_int, [c_void_p, c_int, c_int, POINTER(c_double)]),
+    "kcrn_flush_l2": (c_int, [c_void_p, ctypes.c_size_t]),
     "kcrn_gather_variants": (c_int, [c_void_p, POINTER(c_int)]),
     "kcrn_plan_persist": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, POINTER(c_int64), c_void_p, c_int64,
                                   POINTER(c_int64), POINTER(c_int)]),

@@ -356,6 +356,11 @@ class Engine:
         check(self.lib.kcrn_time_sweep(self.h, int(which), int(reps), byref(us)))
         return us.value
 
+    def flush_l2(self, nbytes: int = 256 << 20) -> None:
+        """Benchmark utility: everything out of L2 (allocate, write, free ``nbytes`` > L2; returns when done)."""
+        self._use_stream()
+        check(self.lib.kcrn_flush_l2(self.h, ctypes.c_size_t(int(nbytes))))
+
     def gather_variants(self) -> dict:
         """Gather variant of the sweep kernel measured fastest per matrix and class of pass (0 stored order,
         1 gather-ordered tiles, 2 gather-ordered tiles + LDGSTS gathers); same bits whichever runs."""
