@@ -431,11 +431,16 @@ def main():
     # flush buffer that stays allocated -- an L2-resident working set stays slower for good (recurrence at this shape 20.5 ->
     # 21.6 / 22.5 us per HVP; profiles/r3g_flush_probe.txt, r3h_flush_probe2.txt, r3g_bench_vs_microbench.txt): a property of
     # the harness, not of the library, which in production shares the GPU with nothing.  The effect is reported
-    # (`roofline.resident_flush_buffer`).
+    # (`roofline.resident_flush_buffer`).  The host then idles 2 ms (untimed): the driver finishes releasing the two buffers
+    # in the background, and a launch that arrives meanwhile is held up by ~0.1 ms (one-iteration device loop behind the
+    # flush 0.345 ms, behind flush + 2 ms 0.244, without any flush 0.215; profiles/r4a_flush_step_probe.txt).
     FLUSH_BYTES = 256 << 20
+    FLUSH_SLEEP_MS = float(os.environ.get("KCRN_BENCH_FLUSH_SLEEP_MS", "0"))
 
     def flush_l2():
         eng.flush_l2(FLUSH_BYTES)
+        if FLUSH_SLEEP_MS > 0:
+            time.sleep(1e-3 * FLUSH_SLEEP_MS)
 
     def barrier():
         torch.cuda.synchronize()
@@ -463,8 +468,9 @@ def main():
         return ms
 
     # ---------------- device-resident run: the real trajectory from x0 = 0.5 (cubic_newton.py:61)
+    DEVICE_STEP = os.environ.get("KCRN_BENCH_DEVICE_STEP", "0") != "0"
     opt = Cubic_Krylov_LS(loss=loss, reg_coef=1e-3, subspace_dim=args.m, tolerance=0, reorth=bool(args.reorth),
-                          label="bench", tqdm=False)
+                          label="bench", tqdm=False, device_step=DEVICE_STEP)
     opt.init_run(P.x0)
     for _ in range(W):
         opt.step()
@@ -472,6 +478,7 @@ def main():
     n_hist = len(opt.history)
     clk = ClockSampler(local)
     clk.__enter__()            # sampled over every measured phase below (the device-resident run alone is ~10 ms)
+    time.sleep(float(os.environ.get("KCRN_BENCH_SAMPLER_LEAD_S", "0")))
     ms = timed_steps(opt.step, K)
     cnt = eng.counters()
     hvps = sum(h["hvps"] for h in opt.history[n_hist:])
@@ -510,7 +517,7 @@ def main():
 
     # ---------------- end to end: numpy iterate in pinned host memory goes in and comes back every step
     opt2 = Cubic_Krylov_LS(loss=loss, reg_coef=1e-3, subspace_dim=args.m, tolerance=0, reorth=bool(args.reorth),
-                           label="bench-e2e", tqdm=False)
+                           label="bench-e2e", tqdm=False, device_step=DEVICE_STEP)
     opt2.init_run(P.x0)
     x_host = torch.as_tensor(P.x0).clone().pin_memory()
     rec_host = torch.zeros(1, dtype=torch.float64).pin_memory()
@@ -612,8 +619,11 @@ def main():
                                f"{' reorth' if args.reorth else ''}, x0=0.5, reg_coef=1e-3",
                    "sharding": "rows, one shard per rank, allreduce(d) per sweep" if world > 1 else "single GPU",
                    "l2": "before every timed step (untimed, kcrn_flush_l2) 256 MiB are written, another 256 MiB read, both "
-                         "freed: the write evicts the matrices, the read evicts the write's dirty lines, which otherwise "
-                         "linger and slow the L2-resident step down; inside a step the matrix is re-read 2m+2 times by design"},
+                         "freed, then the host idles 2 ms while the driver finishes the release: the write evicts the "
+                         "matrices, the read evicts the write's dirty lines, which otherwise linger and slow the "
+                         "L2-resident step down; inside a step the matrix is re-read 2m+2 times by design",
+                   "step": "Cubic_Krylov_LS.step(): one outer iteration = one graph launch (gradient, Lanczos, line search "
+                           "in a WHILE node, commit) and one synchronisation; `device_loop` = K iterations per launch"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * P.d, "d2h_bytes_per_step": 8 * P.d + 120,
                 "ms_per_step": ms2 / K, "outer_iters_per_sec": 1e3 * K / ms2},
         "gpu_launches": cnt["kernels"], "graph_launches": cnt["graph_launches"],

@@ -127,6 +127,9 @@ int kcrn_values_batch(kcrn_handle h, const double *X_dev, int k, double *out_dev
 /* Device views after kcrn_krylov_run: accepted iterates [iters][d] (null without keep_xs), the best point [d]
  * (valid when the record's flag is set), the current iterate [d]. */
 int kcrn_run_view(kcrn_handle h, const double **xs_dev, const double **x_opt_dev, const double **x_dev);
+/* Copy of the handle's current iterate into out[d] (device), enqueued on the handle's stream: the `x_new` a caller of
+ * Cubic_Krylov_LS.step keeps (optimizer/cubic.py:291, 303) after a one-iteration kcrn_krylov_run. */
+int kcrn_current_x(kcrn_handle h, double *out_dev);
 
 /* basis V as m contiguous d-vectors, alphas[m], bet[m] with bet[0] = |g| and bet[j+1] = beta_j,
  * info[8] int32 = {m_eff, n_valid_columns, broke, hvps, 0...}.  Any pointer may be NULL. */

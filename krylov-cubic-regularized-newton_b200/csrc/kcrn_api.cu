@@ -602,6 +602,7 @@ int kcrn_destroy(kcrn_handle h) {
     cudaFree(h->red_ticket);
     cudaFreeHost(h->rec_host);
     cudaFreeHost(h->run_host);
+    if (h->ev_trial) cudaEventDestroy(h->ev_trial);
     cudaFree(h->batch_xt); cudaFree(h->batch_scal); cudaFree(h->batch_partial); cudaFree(h->batch_ticket);
     cudaFree(h->run_ctl); cudaFree(h->run_recs); cudaFree(h->run_xs); cudaFree(h->run_x_opt);
     delete h;
@@ -815,12 +816,16 @@ int kcrn_krylov_trial(kcrn_handle h, int first, int m, int reorth, double M, dou
     KCRN_TRY(lanczos_alloc(h, m));
     if (first) KCRN_TRY(tune_lanczos_sweeps(h, m, false));
     cudaStream_t s = h->stream;
-    double *pp = h->rec_host + 12;          // pinned; every trial ends with a stream synchronise, so it is free
+    // The four parameters go in and the 12-double record comes out through copy nodes of the graph itself (pinned
+    // memory, fixed addresses): one cudaGraphLaunch is all the host enqueues in front of the work.  The host waits for an
+    // event behind the graph; the copy of the trial point to the caller's vector runs behind that event, off the host's
+    // critical path (stream order covers every later reader).  Every trial ends with that wait, so `pp` is free here.
+    double *pp = h->rec_host + 12;
     pp[0] = M; pp[1] = r0; pp[2] = eps; pp[3] = (double)it_max;
-    KCRN_CUDA(cudaMemcpyAsync(h->step_params, pp, sizeof(double) * 4, cudaMemcpyHostToDevice, s));
     h->cur_m = m;
     h->cur_reorth = reorth;
     KCRN_TRY(run_graph(h, first ? 1 : 2, m, reorth, [&]() -> int {
+        KCRN_CUDA(cudaMemcpyAsync(h->step_params, h->rec_host + 12, sizeof(double) * 4, cudaMemcpyHostToDevice, h->stream));
         if (first) {
             KCRN_CUDA(cudaMemcpyAsync(h->x_base, h->x_cur, sizeof(double) * h->d, cudaMemcpyDeviceToDevice, h->stream));
             KCRN_TRY(cols_product(h, h->resid, h->l2 != 0.0 ? h->x_cur : nullptr, h->g, true));      // gradient
@@ -832,13 +837,21 @@ int kcrn_krylov_trial(kcrn_handle h, int first, int m, int reorth, double M, dou
         KCRN_TRY(launch_axpy_basis(h->x_base, h->V, h->sub, m, h->info, h->d, h->x_cur, h->stream, h->red_partials,
                                    h->red_ticket + 5, h->scal + 3));
         KCRN_TRY(launch_forward(h, h->x_cur));
-        return enqueue_value(h, h->scal + 0, 1);
+        KCRN_TRY(enqueue_value(h, h->scal + 0, 1));
+        KCRN_CUDA(cudaMemcpyAsync(h->rec_host, h->scal + 4, sizeof(double) * 12, cudaMemcpyDeviceToHost, h->stream));
+        return KCRN_OK;
     }));
     if (first) h->counters[2] += m;
     h->have_base = true;
+    if (!h->ev_trial) KCRN_CUDA(cudaEventCreateWithFlags(&h->ev_trial, cudaEventDisableTiming));
+    KCRN_CUDA(cudaEventRecord(h->ev_trial, s));
     if (x_out_dev)
         KCRN_CUDA(cudaMemcpyAsync(x_out_dev, h->x_cur, sizeof(double) * h->d, cudaMemcpyDeviceToDevice, s));
-    return read_step_record(h, rec12_host);
+    KCRN_CUDA(cudaEventSynchronize(h->ev_trial));
+    h->counters[6] += (int64_t)sizeof(double) * 4;
+    h->counters[7] += (int64_t)sizeof(double) * 12;
+    memcpy(rec12_host, h->rec_host, sizeof(double) * 12);
+    return KCRN_OK;
 }
 
 int kcrn_krylov_run(kcrn_handle h, int max_iters, int m, int reorth, double value0, double reg_coef, double beta,
@@ -872,7 +885,7 @@ int kcrn_krylov_run(kcrn_handle h, int max_iters, int m, int reorth, double valu
             cudaFreeHost(h->run_host);
             h->run_recs = nullptr; h->run_host = nullptr; h->run_cap = 0;
             KCRN_CUDA(cudaMalloc(&h->run_recs, sizeof(double) * 16 * (size_t)max_iters));
-            KCRN_CUDA(cudaMallocHost(&h->run_host, sizeof(double) * 16 * (size_t)(max_iters + 1)));
+            KCRN_CUDA(cudaMallocHost(&h->run_host, sizeof(double) * 16 * (size_t)(max_iters + 2)));   // + 256 B: RunCtl
             h->run_cap = max_iters;
         }
         if (!keep_xs || want_xs > h->run_xs_cap) { cudaFree(h->run_xs); h->run_xs = nullptr; h->run_xs_cap = 0; }
@@ -902,21 +915,30 @@ int kcrn_krylov_run(kcrn_handle h, int max_iters, int m, int reorth, double valu
     h->cur_reorth = reorth;
     KCRN_CUDA(cudaGraphLaunch(exec, s));
     h->counters[1] += 1;
-    // iteration count and status first (they size the record copy)
-    KCRN_CUDA(cudaMemcpyAsync(pp, h->run_ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, s));
+    // the control block lands behind the records (the last 256 bytes of the pinned buffer)
+    static_assert(sizeof(RunCtl) <= 256, "RunCtl must fit the tail of run_host");
+    double *ctl_host = h->run_host + 16 * (size_t)h->run_cap;
+    KCRN_CUDA(cudaMemcpyAsync(ctl_host, h->run_ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, s));
+    // short runs (a single step of Cubic_Krylov_LS.step, small chunks): all max_iters record slots travel with the
+    // control block -- one synchronisation per launch; long runs read the iteration count first, it sizes the copy
+    const bool one_trip = max_iters <= 64;
+    if (one_trip)
+        KCRN_CUDA(cudaMemcpyAsync(h->run_host, h->run_recs, sizeof(double) * 16 * (size_t)max_iters, cudaMemcpyDeviceToHost, s));
     KCRN_CUDA(cudaStreamSynchronize(s));
     RunCtl done;
-    memcpy(&done, pp, sizeof(RunCtl));
+    memcpy(&done, ctl_host, sizeof(RunCtl));
     const int iters = done.iter;
     if (iters > 0) {
-        KCRN_CUDA(cudaMemcpyAsync(h->run_host, h->run_recs, sizeof(double) * 16 * (size_t)iters, cudaMemcpyDeviceToHost, s));
-        KCRN_CUDA(cudaStreamSynchronize(s));
+        if (!one_trip) {
+            KCRN_CUDA(cudaMemcpyAsync(h->run_host, h->run_recs, sizeof(double) * 16 * (size_t)iters, cudaMemcpyDeviceToHost, s));
+            KCRN_CUDA(cudaStreamSynchronize(s));
+        }
         memcpy(recs16_host, h->run_host, sizeof(double) * 16 * (size_t)iters);
     }
     *iters_done_host = iters;
     if (status_host) *status_host = done.status;
     h->counters[6] += (int64_t)sizeof(double) * 14;
-    h->counters[7] += (int64_t)sizeof(RunCtl) + (int64_t)sizeof(double) * 16 * iters;
+    h->counters[7] += (int64_t)sizeof(RunCtl) + (int64_t)sizeof(double) * 16 * (one_trip ? max_iters : iters);
     int64_t trials = 0;
     for (int k = 0; k < iters; ++k) trials += 1 + (int64_t)recs16_host[16 * k + 13];
     if (done.status != 0) trials += 1 + done.tries;      // the iteration that failed
@@ -939,6 +961,13 @@ int kcrn_run_view(kcrn_handle h, const double **xs_dev, const double **x_opt_dev
     if (xs_dev) *xs_dev = h->run_xs;
     if (x_opt_dev) *x_opt_dev = h->run_x_opt;
     if (x_dev) *x_dev = h->x_cur;
+    return KCRN_OK;
+}
+
+int kcrn_current_x(kcrn_handle h, double *out_dev) {
+    if (!h || !out_dev) { set_error("kcrn_current_x: null argument"); return KCRN_E_ARG; }
+    KCRN_TRY(need_x(h, "kcrn_current_x"));
+    KCRN_CUDA(cudaMemcpyAsync(out_dev, h->x_cur, sizeof(double) * h->d, cudaMemcpyDeviceToDevice, h->stream));
     return KCRN_OK;
 }
 

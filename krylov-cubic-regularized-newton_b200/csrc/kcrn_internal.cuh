@@ -252,7 +252,8 @@ struct kcrn_problem {
     // sub-problem result {s[kMaxM], r, model_decrease, iterations, status}
     double *sub = nullptr;
     double *scal = nullptr;     // [16] device scalars: value, |x|^2, ...
-    double *rec_host = nullptr; // pinned [16]
+    double *rec_host = nullptr; // pinned [16]: step record [12] + trial parameters [4]
+    cudaEvent_t ev_trial = nullptr;   // behind the graph of a trial: what kcrn_krylov_trial waits for
     // reductions
     double *red_partials = nullptr;
     unsigned *red_ticket = nullptr;   // [8]

@@ -42,6 +42,7 @@ SIGNATURES = {
     "kcrn_krylov_run": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_double, c_double, c_double, c_double, c_int,
                                 c_double, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p]),
     "kcrn_run_view": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kcrn_current_x": (c_int, [c_void_p, c_void_p]),
     "kcrn_values_batch": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "kcrn_svmlight_count": (c_int, [c_char_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "kcrn_svmlight_parse": (c_int, [c_char_p, c_int64, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -76,6 +76,8 @@ class Engine:
         if keep[3].shape[0] != self.n:
             raise ValueError("labels must have one entry per row")
         self._stream = torch.cuda.current_stream().cuda_stream
+        self._raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         h = c_void_p()
         check(self.lib.kcrn_create(byref(h), self.n, self.d, self.nnz, ptrs[0], ptrs[1], ptrs[2], ptrs[3],
                                    float(l2), int(n_global if n_global is not None else self.n), on_device,
@@ -87,6 +89,9 @@ class Engine:
         self._rec = (c_double * 12)()
         self._cnt = (c_int64 * 8)()
         self.world = 1
+        self.p2p = False          # peer exchange attached and on (row-sharded device loop needs it)
+        self._rec16 = (c_double * 16)()
+        self._iters, self._status = ctypes.c_int(0), ctypes.c_int(0)
         _live.add(self)
 
     # ------------------------------------------------------------------ plumbing
@@ -102,7 +107,8 @@ class Engine:
             pass
 
     def _use_stream(self):
-        s = self.torch.cuda.current_stream().cuda_stream
+        # the raw handle of torch's current stream (torch.cuda.current_stream() builds a Stream object: ~5 us per call)
+        s = self._raw_stream(self._dev_index) if self._raw_stream else self.torch.cuda.current_stream().cuda_stream
         if s != self._stream:
             check(self.lib.kcrn_set_stream(self.h, s))
             self._stream = s
@@ -136,9 +142,11 @@ class Engine:
     def p2p_attach(self, all_handles: bytes):
         buf = ctypes.create_string_buffer(bytes(all_handles), len(all_handles))
         check(self.lib.kcrn_p2p_attach(self.h, buf))
+        self.p2p = True
 
     def p2p_enable(self, on: bool):
         check(self.lib.kcrn_p2p_enable(self.h, int(bool(on))))
+        self.p2p = bool(on)
 
     def nccl_unique_id(self) -> bytes:
         buf = ctypes.create_string_buffer(128)
@@ -278,6 +286,25 @@ class Engine:
         self._m = int(m)
         self._views = None
         return recs[:iters.value], status.value
+
+    def krylov_step(self, m: int, reorth: bool, value0: float, reg_coef: float, beta: float, r0: float, eps: float,
+                    solver_it_max: int, max_tries: int, f_opt: float):
+        """ONE outer iteration with its line search on the device (kcrn_krylov_run with max_iters = 1: one graph
+        launch, one synchronisation) and the new iterate copied into a fresh vector (kcrn_current_x, not waited
+        for).  Returns (16-double record or None when the sub-problem failed, status, x_new)."""
+        self._use_stream()
+        check(self.lib.kcrn_krylov_run(self.h, 1, int(m), int(bool(reorth)), float(value0), float(reg_coef), float(beta),
+                                       float(r0), float(eps), int(solver_it_max), 0.0, int(max_tries), 0, float(f_opt),
+                                       byref(self._iters), byref(self._status), self._rec16))
+        self._m = int(m)
+        self._views = None
+        x_new = self.new_vector()
+        check(self.lib.kcrn_current_x(self.h, x_new.data_ptr()))
+        return (list(self._rec16) if self._iters.value == 1 else None), self._status.value, x_new
+
+    def best_point(self):
+        """Clone of the best point the device loop has tracked (kcrn_run_view)."""
+        return self.run_view(0)[1].clone()
 
     def run_view(self, iters: int):
         """(accepted iterates [iters, d] or None, best point [d], current iterate [d]) -- device views."""

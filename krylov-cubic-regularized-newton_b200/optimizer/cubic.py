@@ -118,15 +118,24 @@ class Cubic_Krylov_LS(Optimizer):
         solver_eps (float): accuracy of the Newton solve of the cubic sub-problem
         beta (float): backtracking factor for M
         reorth (bool): full re-orthogonalisation inside Lanczos (extension; default False = reference)
+        device_step (bool, default False): step() runs one outer iteration INCLUDING its line search on the device
+            (kcrn_krylov_run with one iteration: one graph launch and one synchronisation per step, however many
+            trials it takes) instead of one graph launch and one host round trip per trial (kcrn_krylov_trial).  Same
+            kernels in the same order, bit-identical results (test_device_step_equals_trial_step).  Measured on a
+            B200 at the rcv1 shape it is SLOWER per step (0.36 vs 0.32 ms: a graph with WHILE nodes costs ~40 us more
+            to launch than the two plain graphs cost in host round trips, profiles/r4c_bench_harness_ab.txt), so it is
+            off by default; it pays when the host is slow or far away.  Row-sharded engines without the peer exchange
+            always take the per-trial path.
         device_loop (bool): run() keeps the whole step loop on the device (kcrn_krylov_run: line search, commit and
             stopping rule in CUDA-graph WHILE nodes) in chunks of ``device_chunk`` iterations; same arithmetic, same
             trace, no per-iteration host round trip.  trace.ts then comes from the device clock.
     """
 
     def __init__(self, reg_coef=None, subspace_dim=100, solver_eps=1e-8, beta=0.5, reorth=False, device_loop=False,
-                 device_chunk=64, *args, **kwargs):
+                 device_chunk=64, device_step=False, *args, **kwargs):
         super().__init__(*args, **kwargs)
         self.device_loop = device_loop
+        self.device_step = device_step
         self.device_chunk = device_chunk
         self.solver_it = 0
         self.subspace_dim = subspace_dim
@@ -145,6 +154,8 @@ class Cubic_Krylov_LS(Optimizer):
             self.value = loss.value(self.x)
         else:
             loss._forward(self.x)                       # no-op when the caches already belong to x
+        if self.device_step and (eng.world == 1 or eng.p2p):
+            return self._step_on_device(loss, eng)
         M = self.reg_coef * self.beta                   # try a smaller M first                  cubic.py:286
         tries = 0
         first = True
@@ -164,7 +175,7 @@ class Cubic_Krylov_LS(Optimizer):
             if status == KCRN_E_NOTPD:
                 raise np.linalg.LinAlgError("T + r I is not positive definite in the cubic sub-problem")
             loss.adopt_iterate(x_new)
-            loss._note_value(value_new, x_new)
+            loss._note_value(value_new, x_new, owned=True)    # x_new is never written again
             if not (value_new > self.value - decrease and tries < 20):   # cubic.py:297
                 break
             M = M / self.beta
@@ -174,6 +185,32 @@ class Cubic_Krylov_LS(Optimizer):
         self._dx = dx
         self.history.append(dict(f=value_new, M=M, solver_it=self.solver_it, m_eff=m_eff, backtracks=tries, r=r,
                                  hvps=hvps, gnorm=gnorm, dx=dx))
+
+    def _step_on_device(self, loss, eng):
+        """cubic.py:265-309 as one graph launch: gradient, Lanczos, then the trials of the line search (sub-problem,
+        x + V s, value, the test of :297, M / beta) in a CUDA-graph WHILE node, the commit of (x, value, M, r0) and the
+        best-point tracking of Oracle.value (loss.py:70-72) -- the host reads one record."""
+        rec, status, x_new = eng.krylov_step(self.subspace_dim, self.reorth, self.value, self.reg_coef, self.beta,
+                                             self.r0, self.solver_eps, 100, 20, loss.f_opt)
+        if rec is None:
+            loss.forget_iterate()
+            if status == KCRN_E_NOTPD:
+                raise np.linalg.LinAlgError("T + r I is not positive definite in the cubic sub-problem")
+            raise RuntimeError(f"kcrn_krylov_run stopped with status {status}")
+        tries = int(rec[13])
+        loss.calls["gradient"] += 1
+        loss.calls["hess_vec_prod"] += self.subspace_dim
+        loss.calls["value"] += 1 + tries
+        loss.calls["forward"] += 1 + tries
+        loss.adopt_iterate(x_new)
+        if rec[11] < loss.f_opt:                        # a trial point (accepted or not) beat the best value so far
+            loss.f_opt = rec[11]
+            loss._defer_x_opt(eng.best_point)           # it sits in the engine; copied when somebody reads x_opt
+        self.x, self.reg_coef, self.value, self.r0 = x_new, rec[12], rec[0], rec[2]
+        self.solver_it += int(rec[3])
+        self._dx = rec[8]
+        self.history.append(dict(f=rec[0], M=rec[12], solver_it=self.solver_it, m_eff=int(rec[5]), backtracks=tries,
+                                 r=rec[2], hvps=int(rec[7]), gnorm=rec[6], dx=rec[8]))
 
     def run(self, x0, t_max=np.inf, it_max=np.inf, ls_it_max=None):
         if not self.device_loop:

@@ -82,9 +82,29 @@ class Oracle:
     def set_seed(self, seed):
         self.seed, self.rng = seed, np.random.default_rng(seed)
 
-    def _note_value(self, value, x):
+    # x_opt (loss.py:70-72) is a plain attribute for every writer; a fused device step that tracked the best point in
+    # the engine's own buffer leaves a callable instead, and the copy is made when somebody reads x_opt
+    @property
+    def x_opt(self):
+        if self._x_opt_source is not None:
+            self._x_opt, self._x_opt_source = self._x_opt_source(), None
+        return self._x_opt
+
+    @x_opt.setter
+    def x_opt(self, x):
+        self._x_opt, self._x_opt_source = x, None
+
+    def _defer_x_opt(self, source):
+        self._x_opt, self._x_opt_source = None, source
+
+    def _note_value(self, value, x, owned=False):
+        """loss.py:70-72.  owned: x is a tensor the caller created for this value and will never write again (the trial
+        point of an optimizer step): the copy is then made when somebody reads x_opt, not on the step's critical path."""
         if value < self.f_opt:
-            self.x_opt = x.clone() if _is_tensor(x) else copy.deepcopy(x)
+            if owned and _is_tensor(x):
+                self._defer_x_opt(x.clone)
+            else:
+                self.x_opt = x.clone() if _is_tensor(x) else copy.deepcopy(x)
             self.f_opt = value
 
     def value(self, x):

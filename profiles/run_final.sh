@@ -25,9 +25,11 @@ CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --sweep-reps 5 --no-
 timeout 150 $CMD > $O/${TAG}_plain.log 2>&1 &&
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 1600 --csv --log-file $O/${TAG}_ncu_launches.csv $CMD > $O/${TAG}_ncu1.log 2>&1
 echo "ncu launch list exit $?"
+if [ -z "$SKIP_SWEEP_NCU" ]; then
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:sweep_kernel -s 400 -c 6 -o $O/${TAG}_ncu_full_sweeps $CMD > $O/${TAG}_ncu2.log 2>&1
 echo "ncu full (sweeps) exit $?"
+fi
 timeout 120 python profiles/microbench/c3_reorth.py child > $O/${TAG}_c3_reorth.txt 2>&1 &&
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:lanczos_reorth_reg -s 140 -c 2 -o $O/${TAG}_ncu_full_reorth python profiles/microbench/c3_reorth.py child > $O/${TAG}_ncu3.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:lanczos_reorth_reg -s 150 -c 3 -o $O/${TAG}_ncu_full_reorth python profiles/microbench/c3_reorth.py child > $O/${TAG}_ncu3.log 2>&1
 echo "ncu full (reorth) exit $?"; tail -1 $O/${TAG}_c3_reorth.txt
 ls -la $O | grep ${TAG}

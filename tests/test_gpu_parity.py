@@ -549,7 +549,7 @@ def test_device_resident_loop_equals_host_loop(torch, name, m, reorth, tol, iter
     loop over kcrn_krylov_trial: the same kernels in the same order, so every number is bit-identical -- values,
     accepted M, backtracks, Newton iterations, iterates kept in the trace, the best point and where the run stops."""
     P = make_problem(name, seed=0)
-    host = _make_opt(P, m, reorth)
+    host = _make_opt(P, m, reorth)                        # one kcrn_krylov_trial per trial, line search in Python
     host.tolerance = tol
     host.run(P.x0, it_max=iters)
     dev = _make_opt(P, m, reorth)
@@ -572,6 +572,38 @@ def test_device_resident_loop_equals_host_loop(torch, name, m, reorth, tol, iter
     assert dev.loss.calls == host.loss.calls
     # the caches belong to the last iterate: the next gradient needs no forward sweep and equals the host loop's
     assert torch.equal(dev.loss.gradient(dev.x), host.loss.gradient(host.x))
+
+
+@pytest.mark.parametrize("name,m,reorth,iters", [("small", 10, False, 30), ("rcv1", 10, False, 25), ("w8a", 10, True, 12)])
+def test_device_step_equals_trial_step(torch, name, m, reorth, iters):
+    """Cubic_Krylov_LS.step with the line search on the device (device_step=True: kcrn_krylov_run, one iteration per launch)
+    against the per-trial path (kcrn_krylov_trial, line search in Python): every number of every step bit-identical,
+    the iterate a fresh tensor per step, the best point handed over on demand, the call counters equal."""
+    P = make_problem(name, seed=0)
+    a, b = _make_opt(P, m, reorth, device_step=True), _make_opt(P, m, reorth, device_step=False)
+    a.init_run(P.x0)
+    b.init_run(P.x0)
+    seen = []
+    for k in range(iters):
+        a.step()
+        b.step()
+        assert a.history[-1] == b.history[-1], (k, a.history[-1], b.history[-1])
+        assert torch.equal(a.x, b.x) and a.step_length() == b.step_length()
+        assert (a.value, a.reg_coef, a.r0, a.solver_it) == (b.value, b.reg_coef, b.r0, b.solver_it)
+        assert a.loss.f_opt == b.loss.f_opt
+        if k in (0, 3, iters - 1):
+            assert torch.equal(a.loss.x_opt, b.loss.x_opt)      # read now and then: the deferred copy, then the cached one
+            assert a.loss.x_opt is a.loss.x_opt
+        seen.append(a.x)
+    assert len({t.data_ptr() for t in seen}) == iters            # no iterate is overwritten by a later step
+    assert sum(h["backtracks"] for h in a.history) > 0 or name != "rcv1"
+    assert a.loss.calls == b.loss.calls
+    assert torch.equal(a.loss.gradient(a.x), b.loss.gradient(b.x))
+    # a value found on the host path replaces the deferred best point
+    y = 0.5 * a.x
+    fy = a.loss.value(y)
+    if fy < b.loss.f_opt:
+        assert torch.equal(a.loss.x_opt, y)
 
 
 @pytest.mark.parametrize("name,l2,k", [("tiny", 1e-3, 3), ("w8a", 0.0, 8), ("rcv1", 1e-4, 11), ("news20", 0.0, 2)])
