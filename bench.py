@@ -431,9 +431,10 @@ def main():
     # flush buffer that stays allocated -- an L2-resident working set stays slower for good (recurrence at this shape 20.5 ->
     # 21.6 / 22.5 us per HVP; profiles/r3g_flush_probe.txt, r3h_flush_probe2.txt, r3g_bench_vs_microbench.txt): a property of
     # the harness, not of the library, which in production shares the GPU with nothing.  The effect is reported
-    # (`roofline.resident_flush_buffer`).  The host then idles 2 ms (untimed): the driver finishes releasing the two buffers
-    # in the background, and a launch that arrives meanwhile is held up by ~0.1 ms (one-iteration device loop behind the
-    # flush 0.345 ms, behind flush + 2 ms 0.244, without any flush 0.215; profiles/r4a_flush_step_probe.txt).
+    # (`roofline.resident_flush_buffer`).  No idle time is added behind the flush: a host sleep of 2 ms (KCRN_BENCH_FLUSH_SLEEP_MS)
+    # makes the step behind it slower, not faster (0.327 -> 0.342 ms; with the line search on the device 0.36 -> 0.39:
+    # a graph launched into an idle GPU starts later), and the lead time of the nvidia-smi sampler does not matter
+    # (profiles/r4c_bench_harness_ab.txt; r4a / r4b_flush_step_probe.txt for the step behind each flush procedure).
     FLUSH_BYTES = 256 << 20
     FLUSH_SLEEP_MS = float(os.environ.get("KCRN_BENCH_FLUSH_SLEEP_MS", "0"))
 
@@ -454,6 +455,9 @@ def main():
         barrier()
         for _ in range(count):
             flush_l2()
+            if world > 1:
+                barrier()          # the flush takes 1-2 ms and a different time on every rank: without this the ranks enter
+                                   # the step that far apart and the timed region of the early one is the other's flush
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             step_fn()
@@ -619,11 +623,10 @@ def main():
                                f"{' reorth' if args.reorth else ''}, x0=0.5, reg_coef=1e-3",
                    "sharding": "rows, one shard per rank, allreduce(d) per sweep" if world > 1 else "single GPU",
                    "l2": "before every timed step (untimed, kcrn_flush_l2) 256 MiB are written, another 256 MiB read, both "
-                         "freed, then the host idles 2 ms while the driver finishes the release: the write evicts the "
-                         "matrices, the read evicts the write's dirty lines, which otherwise linger and slow the "
-                         "L2-resident step down; inside a step the matrix is re-read 2m+2 times by design",
-                   "step": "Cubic_Krylov_LS.step(): one outer iteration = one graph launch (gradient, Lanczos, line search "
-                           "in a WHILE node, commit) and one synchronisation; `device_loop` = K iterations per launch"},
+                         "freed: the write evicts the matrices, the read evicts the write's dirty lines, which otherwise "
+                         "linger and slow the L2-resident step down; inside a step the matrix is re-read 2m+2 times by design",
+                   "step": "Cubic_Krylov_LS.step(): one graph launch + one 96-byte record per trial of the line search "
+                           "(kcrn_krylov_trial); `device_loop` = K iterations in one launch (kcrn_krylov_run)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * P.d, "d2h_bytes_per_step": 8 * P.d + 120,
                 "ms_per_step": ms2 / K, "outer_iters_per_sec": 1e3 * K / ms2},
         "gpu_launches": cnt["kernels"], "graph_launches": cnt["graph_launches"],
