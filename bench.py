@@ -619,7 +619,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "outer_iters_per_sec": 1e3 * K / ms, "hvps_per_step": hvps / K,
-        "config": {"workload": f"{args.workload}-shape n={P.n} d={P.d} nnz={P.nnz} per rank, Krylov CRN m={args.m}"
+        "config": {"workload": f"{args.workload}-shape n={P.n} d={P.d} nnz={P.nnz}{' per rank' if world > 1 else ''}, Krylov CRN m={args.m}"
                                f"{' reorth' if args.reorth else ''}, x0=0.5, reg_coef=1e-3",
                    "sharding": "rows, one shard per rank, allreduce(d) per sweep" if world > 1 else "single GPU",
                    "l2": "before every timed step (untimed, kcrn_flush_l2) 256 MiB are written, another 256 MiB read, both "
