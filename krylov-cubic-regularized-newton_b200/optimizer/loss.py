@@ -102,7 +102,14 @@ class Oracle:
         point of an optimizer step): the copy is then made when somebody reads x_opt, not on the step's critical path."""
         if value < self.f_opt:
             if owned and _is_tensor(x):
-                self._defer_x_opt(x.clone)
+                version = x._version
+
+                def copy_now():
+                    if x._version != version:       # same guard as the A x memo: in-place writes bump the version
+                        raise RuntimeError("x_opt: the best iterate was modified in place before x_opt was read; "
+                                           "read loss.x_opt first or rebind the optimizer's x instead of writing into it")
+                    return x.clone()
+                self._defer_x_opt(copy_now)
             else:
                 self.x_opt = x.clone() if _is_tensor(x) else copy.deepcopy(x)
             self.f_opt = value

@@ -328,3 +328,35 @@ def test_persist_plan_hypothesis():
         _check_persist_plan(lengths, grid=grid)
 
     run()
+
+
+def test_best_point_bookkeeping_of_the_oracle():
+    """Oracle.value's best-point tracking (loss.py:70-72): x_opt is a copy taken when the value was noted.  For a trial
+    point the optimizer owns the copy is deferred to the first read of x_opt -- same content, a distinct tensor, made once;
+    an in-place write to the noted tensor before that read fails loudly instead of handing out the wrong point; every
+    other writer (plain assignment, numpy iterates, a better value found later) replaces a deferred copy."""
+    import torch
+    from optimizer.loss import Oracle
+    o = Oracle()
+    assert o.x_opt is None and o.f_opt == np.inf
+    x = torch.arange(4, dtype=torch.float64)
+    o._note_value(1.0, x, owned=True)
+    got = o.x_opt
+    assert o.f_opt == 1.0 and torch.equal(got, x) and got is not x and o.x_opt is got
+    o._note_value(2.0, torch.zeros(4, dtype=torch.float64), owned=True)        # not better: nothing changes
+    assert o.f_opt == 1.0 and o.x_opt is got
+    y = torch.ones(4, dtype=torch.float64)
+    o._note_value(0.5, y, owned=True)
+    y.add_(1.0)
+    with pytest.raises(RuntimeError, match="modified in place"):
+        o.x_opt
+    z = np.array([3.0, 4.0])
+    o._note_value(0.25, z)                                                     # numpy iterate: deep copy right away
+    z[0] = -1.0
+    assert np.array_equal(o.x_opt, [3.0, 4.0]) and o.f_opt == 0.25
+    w = torch.full((4,), 7.0, dtype=torch.float64)
+    o._note_value(0.125, w)                                                    # not owned: cloned right away
+    w.zero_()
+    assert torch.equal(o.x_opt, torch.full((4,), 7.0, dtype=torch.float64))
+    o.x_opt = None
+    assert o.x_opt is None
