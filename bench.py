@@ -502,6 +502,8 @@ def main():
         state = (recs[-1][0], recs[-1][12], recs[-1][2])
         barrier()
         flush_l2()
+        if world > 1:
+            barrier()              # as in timed_steps: the ranks leave the flush at different times
         ev0.record()
         recs, _ = eng.krylov_run(K, args.m, bool(args.reorth), *state[:2], 0.5, state[2])
         ev1.record()
