@@ -360,3 +360,125 @@ def test_best_point_bookkeeping_of_the_oracle():
     assert torch.equal(o.x_opt, torch.full((4,), 7.0, dtype=torch.float64))
     o.x_opt = None
     assert o.x_opt is None
+
+
+class _OracleEngine:
+    """Stand-in for kcrn_b200.engine.Engine on a machine without a GPU: the two calls Cubic_Krylov_LS.step makes, answered
+    by the CPU oracle (test infrastructure), so that the HOST side of the step -- which M is tried first, the acceptance
+    test, M / beta on rejection, the commit, the counters, the best point -- can be checked against the oracle's own loop."""
+    world, p2p = 1, False
+
+    def __init__(self, L, d):
+        self.L, self.d, self.x, self.best = L, d, None, None
+        self.trials = 0
+
+    def new_vector(self, size=None):
+        return np.empty(self.d if size is None else size)
+
+    def _first(self, m, reorth):
+        from oracle import oracle as O
+        x = self.x
+        g = self.L.gradient(x)
+        self.V, al, be, _ = O.lanczos(lambda v: self.L.hess_vec_prod(x, v), g, m, reorth)
+        self.T = np.diag(al) + np.diag(be, -1) + np.diag(be, 1)
+        self.gs = np.zeros(al.size)
+        self.gs[0] = self.gnorm = np.linalg.norm(g)
+        self.hvps = m
+
+    def krylov_trial(self, first, m, reorth, M, r0, eps=1e-8, it_max=100, x_out=None):
+        from oracle import oracle as O
+        if first:
+            self._first(m, reorth)
+        self.trials += 1
+        s, its, r, dec = O.cubic_solver_root(self.gs, self.T, M, it_max=it_max, epsilon=eps, r0=r0)
+        xn = self.x + self.V @ s
+        x_out[:] = xn
+        self.x_trial = xn
+        return self.L.value(xn), dec, r, its, 0, self.gs.size, self.gnorm, self.hvps, float(np.linalg.norm(xn - self.x))
+
+    def krylov_step(self, m, reorth, value0, reg_coef, beta, r0, eps, solver_it_max, max_tries, f_opt):
+        """What kcrn_krylov_run does for one iteration: the line search of cubic.py:286-302 and the 16-double record."""
+        M, tries, first, x0 = reg_coef * beta, 0, True, self.x
+        while True:
+            xn = self.new_vector()
+            f, dec, r, its, _, m_eff, gnorm, hv, dx = self.krylov_trial(first, m, reorth, M, r0, eps, solver_it_max, x_out=xn)
+            first = False
+            if f < f_opt:
+                f_opt, self.best = f, xn.copy()
+            if not (f > value0 - dec and tries < max_tries):
+                break
+            M, tries = M / beta, tries + 1
+        self.x = xn
+        rec = [f, dec, r, its, 0, m_eff, gnorm, hv, dx, 0, 0, f_opt, M, tries, 0.0, 1.0]
+        return rec, 0, xn.copy()
+
+    def best_point(self):
+        return self.best.copy()
+
+
+def _stub_loss(P):
+    from optimizer.loss import Oracle
+    from oracle import oracle as O
+
+    class StubLoss(Oracle):
+        def __init__(self):
+            super().__init__(l1=0, l2=0)
+            self.L = O.OracleLogistic(P.indptr, P.indices, P.data, (P.n, P.d), P.b)
+            self.engine = _OracleEngine(self.L, P.d)
+            self.n, self.dim = P.n, P.d
+            self.calls = {"value": 0, "gradient": 0, "hess_vec_prod": 0, "forward": 0}
+
+        def to_device(self, x):
+            return np.array(x, dtype=np.float64)
+
+        def _value(self, x):
+            self.engine.x = np.array(x)
+            return self.L.value(x)
+
+        def _forward(self, x):
+            self.engine.x = np.array(x)
+
+        def adopt_iterate(self, x):
+            pass
+
+        def forget_iterate(self):
+            pass
+
+        def reset(self):
+            pass
+
+        @staticmethod
+        def norm(x):
+            return float(np.linalg.norm(x))
+    return StubLoss()
+
+
+@pytest.mark.parametrize("reg_coef", [1e-7, 1e-11])     # 12 rejections in the first step / the cap of 20 rejections
+@pytest.mark.parametrize("device_step", [False, True])
+def test_krylov_step_host_logic_against_the_oracle_loop(device_step, reg_coef):
+    """Cubic_Krylov_LS.step with the engine replaced by the oracle: every accepted value, M, backtrack count, Newton
+    iteration count and the best point must be the oracle loop's (oracle.KrylovCRN, cubic.py:265-309) exactly -- the same
+    arithmetic runs on both sides, only the control flow under test differs.  Both step paths of the mirror."""
+    from kcrn_b200.synth import make_problem
+    from optimizer.cubic import Cubic_Krylov_LS
+    from oracle import oracle as O
+    P = make_problem("tiny", seed=3)
+    loss = _stub_loss(P)
+    opt = Cubic_Krylov_LS(loss=loss, reg_coef=reg_coef, subspace_dim=6, tolerance=0, label="s", tqdm=False,
+                          device_step=device_step)
+    opt.run(P.x0, it_max=12)
+    ora = O.KrylovCRN(O.OracleLogistic(P.indptr, P.indices, P.data, (P.n, P.d), P.b), reg_coef=reg_coef, subspace_dim=6,
+                      tolerance=0)
+    ora.run(P.x0, it_max=12)
+    assert len(opt.history) == len(ora.history) == 12
+    for a, b in zip(opt.history, ora.history):
+        assert (a["f"], a["M"], a["backtracks"], a["solver_it"], a["m_eff"]) == \
+               (b["f"], b["M"], b["backtracks"], b["solver_it"], b["m_eff"]), (a, b)
+    assert ora.history[0]["backtracks"] == (12 if reg_coef == 1e-7 else 20)      # the line search rejected / hit its cap
+    assert np.array_equal(opt.x, ora.x) and opt.reg_coef == ora.M and opt.r0 == ora.r0
+    trials = 12 + sum(h["backtracks"] for h in ora.history)
+    assert loss.engine.trials == trials
+    assert loss.calls["gradient"] == 12 and loss.calls["hess_vec_prod"] == 12 * 6
+    assert loss.calls["value"] == trials == loss.calls["forward"]        # one value and one forward sweep per trial
+    assert loss.f_opt <= min(h["f"] for h in ora.history)                # rejected trial points count as well (loss.py:70-72)
+    assert loss.x_opt is not None and abs(loss.L.value(np.asarray(loss.x_opt)) - loss.f_opt) <= 1e-15
